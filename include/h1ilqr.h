@@ -1,0 +1,164 @@
+/*
+ * h1ilqr.h — C ABI of the B200-native H1 iLQR solver core (libh1ilqr.so).
+ *
+ * This is the drop-in boundary for the hot path of premsuggu/mpc-ilqr-mujoco. The reference has no
+ * FFI layer; its boundary is the C++ class API (include/ilqr/ilqr.hpp, include/ilqr/mpc.hpp,
+ * include/common/robot_utils.hpp). The C++ shim classes in mpc-ilqr-mujoco_b200/host/ keep those
+ * class names and signatures and call ONLY the functions below. Each entry point cites the
+ * reference function it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *  - plain C, IEEE fp64 everywhere, caller-allocated flat HOST arrays unless a name ends in _dev;
+ *  - matrices are COLUMN-MAJOR (Eigen's default) : A[k] is 51x51, B[k] 51x19, K[k] 19x51,
+ *    lxx[k] 51x51, luu[k] 19x19;
+ *  - batched arrays are instance-major: xbar is [batch][N+1][51], A is [batch][N][51*51] ...;
+ *  - state layout x = [qpos(26); qvel(25)] in MuJoCo conventions (quaternion w,x,y,z; world-frame
+ *    base linear velocity; body-frame base angular velocity), u = 19 motor torques;
+ *  - every function returns 0 on success or a negative H1ILQR_E* code; no exceptions, no stdout;
+ *  - one handle = one CUDA device context + one stream; a handle must not be used from two host
+ *    threads at once (the reference is single-threaded, robot_utils.hpp:18).
+ *  - there is NO CPU fallback: h1ilqr_create fails with H1ILQR_ECUDA when no sm_100 device exists.
+ */
+#ifndef H1ILQR_H
+#define H1ILQR_H
+
+#include "h1_model.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define H1ILQR_OK 0
+#define H1ILQR_EARG (-1)      /* bad argument (null pointer, size mismatch, bad stage) */
+#define H1ILQR_ECUDA (-2)     /* CUDA runtime error; h1ilqr_last_error() has the text */
+#define H1ILQR_ENOTFINITE (-3)/* a solve produced non-finite cost/gains for at least one instance */
+
+#define H1ILQR_MAX_ITERS 64
+#define H1ILQR_NALPHA 8
+
+/* Cost weights. Reference: Config::buildCostMatrices (src/common/config.cpp:66-122) builds DIAGONAL
+ * Q, R, Qf; the scalar task weights are RobotUtils::set*Weight (include/common/robot_utils.hpp:66-80)
+ * and setConstraintWeights (src/common/robot_utils.cpp:674-680). */
+typedef struct H1Weights {
+  double Qdiag[H1_NX];
+  double Rdiag[H1_NU];
+  double Qfdiag[H1_NX];
+  double w_com, w_com_vel, w_ee_pos, w_ee_vel, w_upright, w_balance;
+  double w_joint_limits, w_control_limits;
+} H1Weights;
+
+/* Solver options. Reference defaults: iLQR::iLQR (src/ilqr/ilqr.cpp:14-16), lambda bounds
+ * (ilqr.cpp:620,646), accept margin (ilqr.cpp:350), FD eps (include/common/robot_utils.hpp:53),
+ * alpha list (ilqr.cpp:320). */
+typedef struct H1SolverOptions {
+  int max_iterations;      /* 10 */
+  double tolerance;        /* 1e-4 */
+  double reg_init;         /* 1e-6 */
+  double reg_min;          /* 1e-6 */
+  double reg_max;          /* 1e-3 */
+  double accept_margin;    /* 1e-6 */
+  double fd_eps;           /* 1e-5 */
+  double divergence_cost;  /* 1e6 */
+  double alphas[H1ILQR_NALPHA]; /* 1,.8,.6,.4,.2,.1,.05,.01 */
+} H1SolverOptions;
+
+void h1ilqr_default_options(H1SolverOptions* opt);
+
+typedef struct H1Ilqr H1Ilqr; /* opaque */
+
+/* Lifetime. `dyn_model` / `cost_model` may be NULL to use the built-in H1 tables.
+ * Replaces: iLQR::iLQR buffer allocation (src/ilqr/ilqr.cpp:14-48) and MPC::MPC (src/ilqr/mpc.cpp:16-38),
+ * for `batch` independent MPC instances resident on CUDA device `device`. */
+int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1SolverOptions* opt,
+                  int batch, int N, int device, H1Ilqr** out);
+void h1ilqr_destroy(H1Ilqr* h);
+const char* h1ilqr_last_error(void);
+int h1ilqr_batch(const H1Ilqr* h);
+int h1ilqr_horizon(const H1Ilqr* h);
+
+/* Replaces RobotUtils::setCostWeights + set*Weight + setConstraintWeights. */
+int h1ilqr_set_weights(H1Ilqr* h, const H1Weights* w);
+
+/* Reference window for every instance. Replaces MPC::extractReferenceWindow /
+ * RobotUtils::getReferenceWindow (src/ilqr/mpc.cpp:163-166, robot_utils.cpp:422-443) plus the
+ * horizon-local lookups isStance / getEEReference / getCoMVelReference (robot_utils.cpp:494-549).
+ *   x_ref   [batch][N+1][51]   u_ref [batch][N][19]   com_ref [batch][N+1][3]
+ *   ee_ref  [batch][N+1][2][3] (left, right ankle)    stance  [batch][N+1][2] (1 = stance)
+ *   com_vel_ref [batch][N+1][3] (may be NULL when w_com_vel == 0)
+ * If `shared` != 0 the arrays hold ONE window ([1][...]) used by all instances. */
+int h1ilqr_set_reference_window(H1Ilqr* h, const double* x_ref, const double* u_ref, const double* com_ref,
+                                const double* ee_ref, const int* stance, const double* com_vel_ref,
+                                int shared);
+
+/* Initial guess. Replaces iLQR::initializeWithReference (src/ilqr/ilqr.cpp:50-117).
+ *  warm[i] != 0 : shift instance i's previous solution by one knot and roll out the last step;
+ *  warm[i] == 0 : cold start, ubar[t] = u_init (19 values per instance, or shared if u_init_shared)
+ *                 followed by a full rollout (the reference's gravity-compensation guess, Q15, is an
+ *                 explicit input here).
+ *  x0 [batch][51]; warm [batch] (NULL = all cold); u_init [batch][19] or [19]. */
+int h1ilqr_initialize(H1Ilqr* h, const double* x0, const int* warm, const double* u_init, int u_init_shared);
+
+/* Full multi-iteration solve for all instances. Replaces iLQR::solve (src/ilqr/ilqr.cpp:521-660).
+ * Outputs (any may be NULL): cost_out[batch], iters_out[batch], status_out[batch] (0 ok, 1 non-finite).
+ * The per-instance regularisation lambda persists across calls, as reg_lambda_ does (ilqr.hpp:54). */
+int h1ilqr_solve(H1Ilqr* h, const double* x0, double* cost_out, int* iters_out, int* status_out);
+
+/* MPC step for all instances: initialize (warm where a previous solution exists) + solve +
+ * u_apply = ubar[0] + K[0](x_measured - xbar[0]) + store previous solution.
+ * Replaces MPC::stepOnce (src/ilqr/mpc.cpp:40-127). u_apply [batch][19]. */
+int h1ilqr_mpc_step(H1Ilqr* h, const double* x_measured, const double* u_init, int u_init_shared,
+                    double* u_apply, double* cost_out);
+int h1ilqr_mpc_reset(H1Ilqr* h);
+
+/* ---- granular stages (used by the parity tests and by the iLQR shim class) ---- */
+/* iLQR::forwardRolloutNominal (ilqr.cpp:119-124): xbar[t+1] = f_D(xbar[t], ubar[t]) from xbar[0]=x0. */
+int h1ilqr_rollout_nominal(H1Ilqr* h, const double* x0);
+/* iLQR::computeLinearization -> RobotUtils::linearizeDynamicsFD (ilqr.cpp:126-131, robot_utils.cpp:120-160). */
+int h1ilqr_linearize(H1Ilqr* h);
+/* iLQR::computeCostQuadratics (ilqr.cpp:133-244) incl. derivatives.cpp cost terms and limit penalties. */
+int h1ilqr_cost_quadratics(H1Ilqr* h);
+/* iLQR::backwardPass (ilqr.cpp:250-309) with the instance's current lambda. */
+int h1ilqr_backward_pass(H1Ilqr* h);
+/* iLQR::forwardPassLineSearch (ilqr.cpp:311-361): improved[batch], new_cost[batch], alpha_index[batch] (-1 = none). */
+int h1ilqr_line_search(H1Ilqr* h, const double* x0, int* improved, double* new_cost, int* alpha_index);
+/* iLQR::computeTotalCost (ilqr.cpp:363-518) of the current xbar/ubar. */
+int h1ilqr_total_cost(H1Ilqr* h, double* cost_out);
+
+/* One-step dynamics for arbitrary states: RobotUtils::rolloutOneStep (robot_utils.cpp:106-117) and
+ * RobotUtils::step (robot_utils.cpp:99-103). x [n][51], u [n][19] -> x_next [n][51]. n <= batch*(N+1). */
+int h1ilqr_dynamics_step(H1Ilqr* h, int n, const double* x, const double* u, double* x_next);
+/* qfrc_bias analogue (Coriolis + gravity, 25 per state): RobotUtils::computeGravComp (robot_utils.cpp:844-866). */
+int h1ilqr_bias_forces(H1Ilqr* h, int n, const double* x, double* bias);
+/* Dynamics-model FK used to precompute references: CoM (subtree_com of the root) and ankle body
+ * positions, RobotUtils::loadReferences (robot_utils.cpp:370-403). com [n][3], ee [n][2][3]. */
+int h1ilqr_reference_kinematics(H1Ilqr* h, int n, const double* x, double* com, double* ee);
+
+/* ---- accessors (host copies). Sizes as in the conventions above. Any pointer may be NULL. ---- */
+int h1ilqr_set_trajectory(H1Ilqr* h, const double* xbar, const double* ubar);
+int h1ilqr_get_trajectory(H1Ilqr* h, double* xbar, double* ubar);
+int h1ilqr_get_gains(H1Ilqr* h, double* K, double* kff);
+int h1ilqr_set_gains(H1Ilqr* h, const double* K, const double* kff);
+int h1ilqr_get_linearization(H1Ilqr* h, double* A, double* B);
+int h1ilqr_set_linearization(H1Ilqr* h, const double* A, const double* B);
+int h1ilqr_get_cost_quadratics(H1Ilqr* h, double* lx, double* lu, double* lxx, double* luu);
+int h1ilqr_set_cost_quadratics(H1Ilqr* h, const double* lx, const double* lu, const double* lxx, const double* luu);
+int h1ilqr_get_regularization(H1Ilqr* h, double* lambda);
+int h1ilqr_set_regularization(H1Ilqr* h, const double* lambda, int shared);
+/* per-iteration trace of the last solve: cost_trace [batch][max_iterations], alpha_trace [batch][max_iterations][2] */
+int h1ilqr_get_solve_trace(H1Ilqr* h, double* cost_trace, int* alpha_trace);
+
+/* ---- timing of the last h1ilqr_solve, CUDA events on the handle's stream, milliseconds ---- */
+typedef struct H1StageTimes {
+  double total_ms;
+  double rollout_ms, linearize_ms, cost_quadratics_ms, backward_ms, line_search_ms;
+  int launches; /* kernels launched by the last solve */
+} H1StageTimes;
+int h1ilqr_enable_stage_timing(H1Ilqr* h, int enable);
+int h1ilqr_get_stage_times(H1Ilqr* h, H1StageTimes* t);
+/* raw CUDA stream (cudaStream_t) the handle launches on, for external event timing */
+void* h1ilqr_stream(H1Ilqr* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
