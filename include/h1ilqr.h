@@ -35,6 +35,9 @@ extern "C" {
 
 #define H1ILQR_MAX_ITERS 64
 #define H1ILQR_NALPHA 8
+/* H1SolverOptions.linearization */
+#define H1ILQR_LIN_ANALYTIC 0 /* exact dA/dB of f_D by forward-mode tangents (default; north star) */
+#define H1ILQR_LIN_FD 1       /* the reference's method: forward differences, fd_eps (robot_utils.cpp:120-160) */
 
 /* Cost weights. Reference: Config::buildCostMatrices (src/common/config.cpp:66-122) builds DIAGONAL
  * Q, R, Qf; the scalar task weights are RobotUtils::set*Weight (include/common/robot_utils.hpp:66-80)
@@ -59,6 +62,7 @@ typedef struct H1SolverOptions {
   double accept_margin;    /* 1e-6 */
   double fd_eps;           /* 1e-5 */
   double divergence_cost;  /* 1e6 */
+  int linearization;       /* H1ILQR_LIN_ANALYTIC (default) or H1ILQR_LIN_FD */
   double alphas[H1ILQR_NALPHA]; /* 1,.8,.6,.4,.2,.1,.05,.01 */
 } H1SolverOptions;
 

@@ -1,0 +1,64 @@
+// Shared definitions for the sm_100a kernels of the H1 iLQR hot path.
+#pragma once
+#include "../../include/h1ilqr.h"
+
+#if defined(__CUDACC__)
+#define H1_DEV __device__ __forceinline__
+#define H1_HD __host__ __device__ __forceinline__
+#else
+// Lane-emulation build (tests/emul): the warp-cooperative phase functions are plain C++ and are run
+// lane-by-lane between the points where the kernel has a __syncwarp().
+#define H1_DEV inline
+#define H1_HD inline
+#include <cmath>
+namespace h1 { using std::isfinite; }
+#endif
+
+namespace h1 {
+
+constexpr int NB = H1_NB, NQ = H1_NQ, NV = H1_NV, NX = H1_NX, NU = H1_NU;
+constexpr int MAXSLOT = 11;  // base 6 + longest hinge chain 5
+constexpr int NCPT = H1_NFOOT * H1_NCP;
+
+// Read-only kinematic tree + parameters of the dynamics model, built on the host from H1Model
+// (model_tables.cpp) and staged into shared memory by every kernel that evaluates f_D.
+struct DynModel {
+  double pos[NB][3];
+  double rfix[NB][9];
+  double ipos[NB][3];
+  double inertia[NB][6];
+  double mass[NB];
+  double armature[NV], damping[NV];
+  double ctrl_lo[NU], ctrl_hi[NU];
+  double jnt_lo[NU], jnt_hi[NU];
+  double foot_pts[NCPT][3];
+  double gravity[3];
+  double h, kn, bn, bt, eps, total_mass;
+  int parent[NB], axis[NB], has_rfix[NB], depth[NB];
+  int anc_body[NB][6];       // anc_body[b][d]: ancestor of b at depth d (d = depth[b] -> b itself)
+  int nlist[NV];             // #slots of dof j: its ancestor dofs root->self, self included
+  int alist[NV][MAXSLOT];    // dof ids of those slots
+  int level[NV];             // depth of dof j in the dof tree (0..10)
+  int dof_sub_end[NV];       // last dof of the dof-subtree rooted at j (dof subtrees are contiguous)
+  int chain_end[NB];         // last body of b's subtree (bodies are in DFS order)
+  int foot_body[H1_NFOOT];
+  int foot_dof[H1_NFOOT];    // ankle dof of each foot
+  int cp_lo[NV], cp_hi[NV];  // contact points [cp_lo, cp_hi) move with dof j
+  int base_child_slot[NB];   // index of body b among the base's children (only valid when parent[b] == 0)
+  int n_base_children;
+  int pad_;
+};
+
+// Same tree for the cost (URDF / Pinocchio-semantics) model; only what the cost kernel reads.
+struct CostModel {
+  double pos[NB][3];
+  double rfix[NB][9];
+  double ipos[NB][3];
+  double wmass[NB];          // mass[b] / total_mass
+  int parent[NB], axis[NB], has_rfix[NB], depth[NB];
+  int anc_body[NB][6];
+  int chain_end[NB];
+  int foot_body[H1_NFOOT];
+};
+
+}  // namespace h1

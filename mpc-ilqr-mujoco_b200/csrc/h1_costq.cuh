@@ -1,0 +1,480 @@
+// Warp-cooperative cost quadratics of one knot: lx, lu, lxx, luu
+// (reference: iLQR::computeCostQuadratics + add*CostDerivatives, /root/reference/src/ilqr/ilqr.cpp:133-244,
+//  662-800; the CasADi/Pinocchio derivative providers, /root/reference/src/common/derivatives.cpp:525-707;
+//  limit penalties, /root/reference/src/common/robot_utils.cpp:682-778).
+//
+// The reference differentiates Pinocchio FK with CasADi. Here the exact same gradients and full Hessians
+// (all second-order kinematic terms kept, raw un-normalised quaternion coordinates) are produced in closed
+// form. Everything is expressed in the BASE frame:
+//      P(z) = p_b + R(xi) r(theta)            position of a weighted point set (CoM, or an ankle frame)
+//      U(z) = R(xi) u(theta, v),  u = v_b + w_b x r + sum_j r_j thdot_j      its velocity (Pinocchio's
+//             LOCAL_WORLD_ALIGNED frame velocity / vcom, with v_b, w_b read as body-frame quantities — Q5)
+// with r_j = d r/d theta_j = a_j x mu_j, r_jk = a_j x r_k (j ancestor-or-self of k), and the third-order
+// terms needed by the velocity costs folded into D_l and Omega_l (see ph_cq_sets / ph_cq_tables).
+// R(xi) is Eigen's quaternion polynomial, so dR/dxi is linear and d2R/dxi2 constant.
+// Results are in the Pinocchio coordinate order (quaternion x,y,z,w at 3..6) and are accumulated at the SAME
+// indices of the MuJoCo-ordered lx / lxx — reference quirk Q3; the upright term reads x~[3..6] in the roles
+// (qw,qx,qy,qz) — quirk Q4. Lane <-> body for the kinematics, lane <-> matrix entries for the assembly.
+#pragma once
+#include "h1_dyn.cuh"
+
+namespace h1 {
+
+constexpr int CQ_SETS = 3;     // 0: CoM, 1: left ankle frame, 2: right ankle frame
+constexpr int CQ_ROWS = 20;    // Jacobian rows: per set P(3) then U(3) -> 18, + 2 balance residual rows
+constexpr int CQ_MAXOUTER = 28;
+
+struct CostWarp {
+  double xt[NX];                 // Pinocchio-ordered state
+  double sn[NB], cs[NB];
+  double ax[NB][3], o[NB][3], c[NB][3], Om[NB][3];   // hinge axis, body origin, body CoM, relative angular velocity
+  double rr[CQ_SETS][3], uu[CQ_SETS][3];
+  double rj[CQ_SETS][NB][3], uth[CQ_SETS][NB][3], D[CQ_SETS][NB][3];
+  double lamP[CQ_SETS][3], lamU[CQ_SETS][3];          // Hessian-contraction multipliers per set
+  double R[9], Ra[4][9];
+  double rows[CQ_ROWS][NX];
+  double gcoef[CQ_ROWS];
+  double QQ[4][4], QJ[4][NB], JJ[NB][NB], QV[4][NV], JV[NB][NV];
+  double gq[4];                  // upright gradient
+  int outer_a[CQ_MAXOUTER], outer_b[CQ_MAXOUTER];
+  double outer_c[CQ_MAXOUTER];
+  int n_outer;
+  int bal_on;                    // balance term active at this knot
+  double bal_sg, bal_k0, bal_k1; // sigma, U_x sigma', U_y sigma'
+};
+
+H1_DEV void cq_dR(const double* xi, int a, double* D) {
+  const double x = xi[0], y = xi[1], z = xi[2], w = xi[3];
+  if (a == 0) { D[0] = 0; D[1] = 2 * y; D[2] = 2 * z; D[3] = 2 * y; D[4] = -4 * x; D[5] = -2 * w; D[6] = 2 * z; D[7] = 2 * w; D[8] = -4 * x; }
+  else if (a == 1) { D[0] = -4 * y; D[1] = 2 * x; D[2] = 2 * w; D[3] = 2 * x; D[4] = 0; D[5] = 2 * z; D[6] = -2 * w; D[7] = 2 * z; D[8] = -4 * y; }
+  else if (a == 2) { D[0] = -4 * z; D[1] = -2 * w; D[2] = 2 * x; D[3] = 2 * w; D[4] = -4 * z; D[5] = 2 * y; D[6] = 2 * x; D[7] = 2 * y; D[8] = 0; }
+  else { D[0] = 0; D[1] = -2 * z; D[2] = 2 * y; D[3] = 2 * z; D[4] = 0; D[5] = -2 * x; D[6] = -2 * y; D[7] = 2 * x; D[8] = 0; }
+}
+H1_DEV void mv3(const double* M, const double* v, double* o) {
+  const double a = M[0] * v[0] + M[1] * v[1] + M[2] * v[2], b = M[3] * v[0] + M[4] * v[1] + M[5] * v[2],
+               c = M[6] * v[0] + M[7] * v[1] + M[8] * v[2];
+  o[0] = a; o[1] = b; o[2] = c;
+}
+H1_DEV void mtv3(const double* M, const double* v, double* o) {
+  const double a = M[0] * v[0] + M[3] * v[1] + M[6] * v[2], b = M[1] * v[0] + M[4] * v[1] + M[7] * v[2],
+               c = M[2] * v[0] + M[5] * v[1] + M[8] * v[2];
+  o[0] = a; o[1] = b; o[2] = c;
+}
+H1_DEV bool cq_is_anc(const CostModel& cm, int k, int l) {  // k ancestor-or-self of l
+  return cm.depth[k] <= cm.depth[l] && cm.anc_body[l][cm.depth[k]] == k;
+}
+
+// ---- phase 0: stage the state in Pinocchio order (convertMuJoCoToPinocchio), sin/cos ----
+H1_DEV void ph_cq_load(int lane, CostWarp& w, const double* x) {
+  for (int i = lane; i < NX; i += 32) {
+    int src = i;
+    if (i >= 3 && i < 6) src = i + 1; else if (i == 6) src = 3;
+    w.xt[i] = x[src];
+  }
+  if (lane >= 1 && lane < NB) {
+    double s, c;
+    sincos_t(x[6 + lane], &s, &c);
+    w.sn[lane] = s; w.cs[lane] = c;
+  }
+}
+
+// ---- phase 1: base-frame kinematics, lane <-> body ----
+H1_DEV void ph_cq_walk(int lane, const CostModel& cm, CostWarp& w) {
+  if (lane >= NB) return;
+  const int b = lane;
+  double E[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, r[3] = {0, 0, 0}, Om[3] = {0, 0, 0}, a[3] = {0, 0, 0};
+  const int dep = cm.depth[b];
+#pragma unroll 1
+  for (int d = 1; d <= 5; ++d) {
+    if (d <= dep) {
+      const int an = cm.anc_body[b][d];
+      const double* p = cm.pos[an];
+      r[0] += E[0] * p[0] + E[1] * p[1] + E[2] * p[2];
+      r[1] += E[3] * p[0] + E[4] * p[1] + E[5] * p[2];
+      r[2] += E[6] * p[0] + E[7] * p[1] + E[8] * p[2];
+      if (cm.has_rfix[an]) {
+        const double* F = cm.rfix[an];
+        double T[9];
+        for (int i = 0; i < 3; ++i)
+          for (int k = 0; k < 3; ++k) T[3 * i + k] = E[3 * i] * F[k] + E[3 * i + 1] * F[3 + k] + E[3 * i + 2] * F[6 + k];
+        for (int i = 0; i < 9; ++i) E[i] = T[i];
+      }
+      rot_right(E, cm.axis[an], w.sn[an], w.cs[an]);
+      col_of(E, cm.axis[an], a);
+      const double thd = w.xt[NQ + 5 + an];
+      Om[0] += thd * a[0]; Om[1] += thd * a[1]; Om[2] += thd * a[2];
+    }
+  }
+  const double* ip = cm.ipos[b];
+  for (int i = 0; i < 3; ++i) {
+    w.ax[b][i] = a[i]; w.o[b][i] = r[i]; w.Om[b][i] = Om[i];
+    w.c[b][i] = r[i] + E[3 * i] * ip[0] + E[3 * i + 1] * ip[1] + E[3 * i + 2] * ip[2];
+  }
+}
+
+// ---- phase 2: per point set, r_l = a_l x mu_l (lane <-> joint l); set centroids on lanes 20..22 ----
+H1_DEV void ph_cq_sets(int lane, const CostModel& cm, CostWarp& w) {
+  if (lane >= 1 && lane < NB) {
+    const int l = lane;
+    double Hs[3] = {0, 0, 0}, Ws = 0.0;
+    for (int i = l; i <= cm.chain_end[l]; ++i) {
+      const double m = cm.wmass[i];
+      Ws += m; Hs[0] += m * w.c[i][0]; Hs[1] += m * w.c[i][1]; Hs[2] += m * w.c[i][2];
+    }
+    double mu[3] = {Hs[0] - Ws * w.o[l][0], Hs[1] - Ws * w.o[l][1], Hs[2] - Ws * w.o[l][2]};
+    cross3(w.ax[l], mu, w.rj[0][l]);
+    for (int f = 0; f < H1_NFOOT; ++f) {
+      const int fb = cm.foot_body[f];
+      if (cq_is_anc(cm, l, fb)) {
+        double m2[3] = {w.o[fb][0] - w.o[l][0], w.o[fb][1] - w.o[l][1], w.o[fb][2] - w.o[l][2]};
+        cross3(w.ax[l], m2, w.rj[1 + f][l]);
+      } else {
+        w.rj[1 + f][l][0] = w.rj[1 + f][l][1] = w.rj[1 + f][l][2] = 0.0;
+      }
+    }
+  }
+  if (lane == 20) {
+    double s[3] = {0, 0, 0};
+    for (int i = 0; i < NB; ++i) { const double m = cm.wmass[i]; s[0] += m * w.c[i][0]; s[1] += m * w.c[i][1]; s[2] += m * w.c[i][2]; }
+    w.rr[0][0] = s[0]; w.rr[0][1] = s[1]; w.rr[0][2] = s[2];
+  }
+  if (lane == 21 || lane == 22) {
+    const int f = lane - 21, fb = cm.foot_body[f];
+    for (int i = 0; i < 3; ++i) w.rr[1 + f][i] = w.o[fb][i];
+  }
+  if (lane == 23) {
+    const double* xi = &w.xt[3];
+    const double x = xi[0], y = xi[1], z = xi[2], q = xi[3];
+    const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+    const double twx = tx * q, twy = ty * q, twz = tz * q, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y,
+                 tyz = tz * y, tzz = tz * z;
+    w.R[0] = 1.0 - (tyy + tzz); w.R[1] = txy - twz;         w.R[2] = txz + twy;
+    w.R[3] = txy + twz;         w.R[4] = 1.0 - (txx + tzz); w.R[5] = tyz - twx;
+    w.R[6] = txz - twy;         w.R[7] = tyz + twx;         w.R[8] = 1.0 - (txx + tyy);
+    for (int a = 0; a < 4; ++a) cq_dR(xi, a, w.Ra[a]);
+  }
+}
+
+// ---- phase 3: D_l, u_theta_l per set (lane <-> joint); set velocities u on lanes 20..22 ----
+H1_DEV void ph_cq_vel(int lane, const CostModel& cm, CostWarp& w) {
+  const double* vb = &w.xt[NQ];
+  const double* wb = &w.xt[NQ + 3];
+  if (lane >= 1 && lane < NB) {
+    const int l = lane;
+    for (int s = 0; s < CQ_SETS; ++s) {
+      double D[3] = {0, 0, 0};
+      for (int j = l + 1; j <= cm.chain_end[l]; ++j) {
+        const double thd = w.xt[NQ + 5 + j];
+        D[0] += thd * w.rj[s][j][0]; D[1] += thd * w.rj[s][j][1]; D[2] += thd * w.rj[s][j][2];
+      }
+      w.D[s][l][0] = D[0]; w.D[s][l][1] = D[1]; w.D[s][l][2] = D[2];
+      const double wk[3] = {wb[0] + w.Om[l][0], wb[1] + w.Om[l][1], wb[2] + w.Om[l][2]};
+      double t1[3], t2[3];
+      cross3(wk, w.rj[s][l], t1);
+      cross3(w.ax[l], D, t2);
+      w.uth[s][l][0] = t1[0] + t2[0]; w.uth[s][l][1] = t1[1] + t2[1]; w.uth[s][l][2] = t1[2] + t2[2];
+    }
+  }
+  if (lane >= 20 && lane < 20 + CQ_SETS) {
+    const int s = lane - 20;
+    double acc[3];
+    cross3(wb, w.rr[s], acc);
+    acc[0] += vb[0]; acc[1] += vb[1]; acc[2] += vb[2];
+    for (int j = 1; j < NB; ++j) {
+      const double thd = w.xt[NQ + 5 + j];
+      acc[0] += thd * w.rj[s][j][0]; acc[1] += thd * w.rj[s][j][1]; acc[2] += thd * w.rj[s][j][2];
+    }
+    w.uu[s][0] = acc[0]; w.uu[s][1] = acc[1]; w.uu[s][2] = acc[2];
+  }
+}
+
+// ---- phase 4 (lane 0): which terms are active at this knot, their multipliers, the rank-1 list ----
+struct KnotTargets {
+  const double* com_ref;      // [3]
+  const double* com_vel_ref;  // [3]
+  const double* ee_ref;       // [2][3]
+  const int* stance;          // [2]
+  bool terminal;
+};
+H1_DEV void ph_cq_terms(int lane, const H1Weights& wt, const KnotTargets& kt, CostWarp& w) {
+  if (lane != 0) return;
+  for (int s = 0; s < CQ_SETS; ++s)
+    for (int i = 0; i < 3; ++i) { w.lamP[s][i] = 0.0; w.lamU[s][i] = 0.0; }
+  for (int r = 0; r < CQ_ROWS; ++r) w.gcoef[r] = 0.0;
+  w.bal_on = 0;
+  int no = 0;
+  double P[CQ_SETS][3], U[CQ_SETS][3];
+  for (int s = 0; s < CQ_SETS; ++s) {
+    mv3(w.R, w.rr[s], P[s]);
+    P[s][0] += w.xt[0]; P[s][1] += w.xt[1]; P[s][2] += w.xt[2];
+    mv3(w.R, w.uu[s], U[s]);
+  }
+  auto sq_term = [&](int s, bool vel, const double* target, double wgt) {
+    const int r0 = 6 * s + (vel ? 3 : 0);
+    for (int c = 0; c < 3; ++c) {
+      const double lam = 2.0 * wgt * ((vel ? U[s][c] : P[s][c]) - target[c]);
+      (vel ? w.lamU[s][c] : w.lamP[s][c]) += lam;
+      w.gcoef[r0 + c] += lam;
+      w.outer_a[no] = r0 + c; w.outer_b[no] = r0 + c; w.outer_c[no] = 2.0 * wgt; ++no;
+    }
+  };
+  const double zero3[3] = {0.0, 0.0, 0.0};
+  if (wt.w_com > 0.0) sq_term(0, false, kt.com_ref, wt.w_com);
+  if (wt.w_com_vel > 0.0 && !kt.terminal) sq_term(0, true, kt.com_vel_ref, wt.w_com_vel);
+  if (wt.w_ee_pos > 0.0)
+    for (int f = 0; f < H1_NFOOT; ++f)
+      if (kt.stance[f] != 1) sq_term(1 + f, false, kt.ee_ref + 3 * f, wt.w_ee_pos);
+  if (wt.w_ee_vel > 0.0)
+    for (int f = 0; f < H1_NFOOT; ++f)
+      if (kt.stance[f] == 1) sq_term(1 + f, true, zero3, wt.w_ee_vel);
+  // upright: closed form on x~[3..6] read as (qw,qx,qy,qz)  (derivatives.cpp:646-666)
+  for (int a = 0; a < 4; ++a) { w.gq[a] = 0.0; for (int b = 0; b < 4; ++b) w.QQ[a][b] = 0.0; }
+  if (wt.w_upright > 0.0) {
+    const double* s = &w.xt[3];
+    const double z[3] = {2 * (s[1] * s[3] + s[0] * s[2]), 2 * (s[2] * s[3] - s[0] * s[1]), 1 - 2 * (s[1] * s[1] + s[2] * s[2])};
+    const double r[3] = {z[0], z[1], z[2] - 1.0};
+    const double J[3][4] = {{2 * s[2], 2 * s[3], 2 * s[0], 2 * s[1]}, {-2 * s[1], -2 * s[0], 2 * s[3], 2 * s[2]}, {0, -4 * s[1], -4 * s[2], 0}};
+    const double wu = wt.w_upright;
+    for (int a = 0; a < 4; ++a) {
+      w.gq[a] = wu * (J[0][a] * r[0] + J[1][a] * r[1] + J[2][a] * r[2]);
+      for (int b = 0; b < 4; ++b) w.QQ[a][b] = wu * (J[0][a] * J[0][b] + J[1][a] * J[1][b] + J[2][a] * J[2][b]);
+    }
+    w.QQ[0][2] += wu * r[0] * 2; w.QQ[2][0] += wu * r[0] * 2; w.QQ[1][3] += wu * r[0] * 2; w.QQ[3][1] += wu * r[0] * 2;
+    w.QQ[0][1] += wu * r[1] * -2; w.QQ[1][0] += wu * r[1] * -2; w.QQ[2][3] += wu * r[1] * 2; w.QQ[3][2] += wu * r[1] * 2;
+    w.QQ[1][1] += wu * r[2] * -4; w.QQ[2][2] += wu * r[2] * -4;
+  }
+  // balance: 0.5 w || com_xy + vcom_xy sqrt(com_z / 9.81) - p_support ||^2  (derivatives.cpp:668-707)
+  if (wt.w_balance > 0.0) {
+    double ps[2];
+    bool have = true;
+    const bool ls = kt.stance[0] == 1, rs = kt.stance[1] == 1;
+    const double* l = kt.ee_ref; const double* rf = kt.ee_ref + 3;
+    if (ls && rs) { ps[0] = 0.5 * (l[0] + rf[0]); ps[1] = 0.5 * (l[1] + rf[1]); }
+    else if (ls) { ps[0] = l[0]; ps[1] = l[1]; }
+    else if (rs) { ps[0] = rf[0]; ps[1] = rf[1]; }
+    else have = false;
+    if (have) {
+      const double wb = wt.w_balance, g9 = 9.81;
+      const double sg = sqrt(P[0][2] / g9), sg1 = 1.0 / (2.0 * g9 * sg), sg2 = -1.0 / (4.0 * g9 * g9 * sg * sg * sg);
+      const double rho0 = P[0][0] + sg * U[0][0] - ps[0], rho1 = P[0][1] + sg * U[0][1] - ps[1];
+      // residual rows 18,19 = J_Pk + sg J_Uk + U_k sg1 J_Pz are built in ph_cq_rows2
+      w.bal_on = 1; w.bal_sg = sg; w.bal_k0 = U[0][0] * sg1; w.bal_k1 = U[0][1] * sg1;
+      w.gcoef[18] = wb * rho0; w.gcoef[19] = wb * rho1;
+      w.outer_a[no] = 18; w.outer_b[no] = 18; w.outer_c[no] = wb; ++no;
+      w.outer_a[no] = 19; w.outer_b[no] = 19; w.outer_c[no] = wb; ++no;
+      w.outer_a[no] = 3; w.outer_b[no] = 2; w.outer_c[no] = wb * rho0 * sg1; ++no;
+      w.outer_a[no] = 2; w.outer_b[no] = 3; w.outer_c[no] = wb * rho0 * sg1; ++no;
+      w.outer_a[no] = 4; w.outer_b[no] = 2; w.outer_c[no] = wb * rho1 * sg1; ++no;
+      w.outer_a[no] = 2; w.outer_b[no] = 4; w.outer_c[no] = wb * rho1 * sg1; ++no;
+      w.outer_a[no] = 2; w.outer_b[no] = 2; w.outer_c[no] = wb * (rho0 * U[0][0] + rho1 * U[0][1]) * sg2; ++no;
+      w.lamP[0][0] += wb * rho0; w.lamP[0][1] += wb * rho1; w.lamP[0][2] += wb * sg1 * (rho0 * U[0][0] + rho1 * U[0][1]);
+      w.lamU[0][0] += wb * sg * rho0; w.lamU[0][1] += wb * sg * rho1;
+    }
+  }
+  w.n_outer = no;
+}
+
+// ---- phase 5: Jacobian rows (lane <-> state column) and the contraction tables (lane <-> joint pairs) ----
+H1_DEV void ph_cq_rows(int lane, const CostModel& cm, CostWarp& w) {
+  // rows: J_P(s) = [I | Ra rr | R r_l | 0],  J_U(s) = [0 | Ra u | R uth_l | R, R(e_m x rr), R r_j]
+  for (int i = lane; i < NX; i += 32) {
+    for (int s = 0; s < CQ_SETS; ++s) {
+      double cp[3] = {0, 0, 0}, cu[3] = {0, 0, 0};
+      if (i < 3) { cp[0] = (i == 0) ? 1.0 : 0.0; cp[1] = (i == 1) ? 1.0 : 0.0; cp[2] = (i == 2) ? 1.0 : 0.0; }
+      else if (i < 7) { mv3(w.Ra[i - 3], w.rr[s], cp); mv3(w.Ra[i - 3], w.uu[s], cu); }
+      else if (i < NQ) { mv3(w.R, w.rj[s][i - 6], cp); mv3(w.R, w.uth[s][i - 6], cu); }
+      else if (i < NQ + 3) { const int m = i - NQ; cu[0] = w.R[m]; cu[1] = w.R[3 + m]; cu[2] = w.R[6 + m]; }
+      else if (i < NQ + 6) {
+        const int m = i - NQ - 3;
+        const double e[3] = {m == 0 ? 1.0 : 0.0, m == 1 ? 1.0 : 0.0, m == 2 ? 1.0 : 0.0};
+        double er[3];
+        cross3(e, w.rr[s], er);
+        mv3(w.R, er, cu);
+      } else { mv3(w.R, w.rj[s][i - NQ - 5], cu); }
+      for (int c = 0; c < 3; ++c) { w.rows[6 * s + c][i] = cp[c]; w.rows[6 * s + 3 + c][i] = cu[c]; }
+    }
+  }
+}
+H1_DEV void ph_cq_rows2(int lane, CostWarp& w) {  // balance residual rows (need the CoM rows complete)
+  for (int i = lane; i < NX; i += 32) {
+    double a = 0.0, b = 0.0;
+    if (w.bal_on) {
+      a = w.rows[0][i] + w.bal_sg * w.rows[3][i] + w.bal_k0 * w.rows[2][i];
+      b = w.rows[1][i] + w.bal_sg * w.rows[4][i] + w.bal_k1 * w.rows[2][i];
+    }
+    w.rows[18][i] = a; w.rows[19][i] = b;
+  }
+}
+
+H1_DEV void ph_cq_tables(int lane, const CostModel& cm, CostWarp& w) {
+  const double* wb = &w.xt[NQ + 3];
+  // per-set transformed multipliers (recomputed per lane: cheap, avoids another exchange)
+  double RtP[CQ_SETS][3], RtU[CQ_SETS][3];
+  for (int s = 0; s < CQ_SETS; ++s) { mtv3(w.R, w.lamP[s], RtP[s]); mtv3(w.R, w.lamU[s], RtU[s]); }
+  // (theta_k, theta_l), (theta_k, thdot_l): lane <-> ordered pair index
+  for (int idx = lane; idx < (NB - 1) * (NB - 1); idx += 32) {
+    const int k = idx / (NB - 1) + 1, l = idx % (NB - 1) + 1;
+    if (k > l) continue;
+    double jj = 0.0, jv = 0.0;
+    if (cq_is_anc(cm, k, l)) {
+      for (int s = 0; s < CQ_SETS; ++s) {
+        double rkl[3], t[3], t2[3], acc[3];
+        cross3(w.ax[k], w.rj[s][l], rkl);
+        const double wk[3] = {wb[0] + w.Om[k][0], wb[1] + w.Om[k][1], wb[2] + w.Om[k][2]};
+        cross3(wk, rkl, acc);
+        const double dO[3] = {w.Om[l][0] - w.Om[k][0], w.Om[l][1] - w.Om[k][1], w.Om[l][2] - w.Om[k][2]};
+        cross3(dO, w.rj[s][l], t); cross3(w.ax[k], t, t2);
+        acc[0] += t2[0]; acc[1] += t2[1]; acc[2] += t2[2];
+        cross3(w.ax[l], w.D[s][l], t); cross3(w.ax[k], t, t2);
+        acc[0] += t2[0]; acc[1] += t2[1]; acc[2] += t2[2];
+        jj += dot3(RtP[s], rkl) + dot3(RtU[s], acc);
+        jv += dot3(RtU[s], rkl);
+      }
+    }
+    w.JJ[k][l] = jj; w.JJ[l][k] = jj;
+    w.JV[k][5 + l] = jv; w.JV[l][5 + k] = jv;
+  }
+  // (theta_k, omega_m) and (xi_a, theta_l): lane <-> joint
+  if (lane >= 1 && lane < NB) {
+    const int k = lane;
+    for (int m = 0; m < 3; ++m) {
+      const double e[3] = {m == 0 ? 1.0 : 0.0, m == 1 ? 1.0 : 0.0, m == 2 ? 1.0 : 0.0};
+      double v = 0.0;
+      for (int s = 0; s < CQ_SETS; ++s) { double er[3]; cross3(e, w.rj[s][k], er); v += dot3(RtU[s], er); }
+      w.JV[k][3 + m] = v;
+      w.JV[k][m] = 0.0;
+    }
+    for (int a = 0; a < 4; ++a) {
+      double v = 0.0;
+      for (int s = 0; s < CQ_SETS; ++s) {
+        double RaP[3], RaU[3];
+        mtv3(w.Ra[a], w.lamP[s], RaP); mtv3(w.Ra[a], w.lamU[s], RaU);
+        v += dot3(RaP, w.rj[s][k]) + dot3(RaU, w.uth[s][k]);
+      }
+      w.QJ[a][k] = v;
+    }
+  }
+  // (xi_a, v) : lanes 0..24 <-> velocity entry ; (xi_a, xi_b): lanes 25..31 + wrap
+  if (lane < NV) {
+    const int m = lane;
+    for (int a = 0; a < 4; ++a) {
+      double v = 0.0;
+      for (int s = 0; s < CQ_SETS; ++s) {
+        double RaU[3];
+        mtv3(w.Ra[a], w.lamU[s], RaU);
+        if (m < 3) v += RaU[m];
+        else if (m < 6) {
+          const int mm = m - 3;
+          const double e[3] = {mm == 0 ? 1.0 : 0.0, mm == 1 ? 1.0 : 0.0, mm == 2 ? 1.0 : 0.0};
+          double er[3];
+          cross3(e, w.rr[s], er);
+          v += dot3(RaU, er);
+        } else v += dot3(RaU, w.rj[s][m - 5]);
+      }
+      w.QV[a][m] = v;
+    }
+  }
+  if (lane >= 16) {  // 16 (a,b) pairs on lanes 16..31; d2R/dxi_a dxi_b = dR/dxi_a evaluated at e_b
+    const int a = (lane - 16) >> 2, b = (lane - 16) & 3;
+    double e[4] = {0, 0, 0, 0};
+    if (b == 0) e[0] = 1.0; else if (b == 1) e[1] = 1.0; else if (b == 2) e[2] = 1.0; else e[3] = 1.0;
+    double Rab[9];
+    cq_dR(e, a, Rab);
+    double v = 0.0;
+    for (int s = 0; s < CQ_SETS; ++s) {
+      double t[3];
+      mv3(Rab, w.rr[s], t); v += dot3(w.lamP[s], t);
+      mv3(Rab, w.uu[s], t); v += dot3(w.lamU[s], t);
+    }
+    w.QQ[a][b] += v;  // on top of the upright block written in ph_cq_terms
+  }
+}
+
+// ---- phase 6: assemble and store lx, lu, lxx, luu (column-major), incl. Q/R tracking and limit penalties ----
+H1_DEV double cq_block(const CostWarp& w, int i, int j) {  // contraction part of H(i,j), i >= j
+  // classes: [0,3) p, [3,7) xi, [7,26) theta, [26,51) velocity entries
+  if (j < 3 || i < 3) return 0.0;
+  if (i < 7) return w.QQ[i - 3][j - 3];                       // (xi, xi)
+  if (i < NQ) return (j < 7) ? w.QJ[j - 3][i - 6] : w.JJ[i - 6][j - 6];  // (theta, xi) / (theta, theta)
+  if (j < 7) return w.QV[j - 3][i - NQ];                      // (v, xi)
+  if (j < NQ) return w.JV[j - 6][i - NQ];                     // (v, theta)
+  return 0.0;                                                 // (v, v)
+}
+H1_DEV void limit_d(double val, double lo, double hi, double wgt, double* g, double* h) {
+  const double margin = 0.1 * (hi - lo), lo_s = lo + margin, hi_s = hi - margin;
+  if (val > hi_s) *g += 2.0 * wgt * (val - hi_s);
+  if (val < lo_s) *g += -2.0 * wgt * (lo_s - val);
+  if (val > hi_s || val < lo_s) *h += 2.0 * wgt;
+}
+H1_DEV void ph_cq_store(int lane, const DynModel& md, const H1Weights& wt, const CostWarp& w, const double* x,
+                        const double* u, const double* x_ref, const double* u_ref, bool terminal, double* lx,
+                        double* lu, double* lxx, double* luu) {
+  const double* Qd = terminal ? wt.Qfdiag : wt.Qdiag;
+  for (int i = lane; i < NX; i += 32) {
+    double g = Qd[i] * (x[i] - x_ref[i]);
+    for (int r = 0; r < CQ_ROWS; ++r)
+      if (w.gcoef[r] != 0.0) g += w.gcoef[r] * w.rows[r][i];
+    if (i >= 3 && i < 7) g += w.gq[i - 3];
+    if (i >= 7 && i < NQ) {
+      const double lo = md.jnt_lo[i - 7], hi = md.jnt_hi[i - 7];
+      double hd = 0.0;
+      if (isfinite(lo) && isfinite(hi) && lo < hi) limit_d(x[i], lo, hi, wt.w_joint_limits, &g, &hd);
+    }
+    lx[i] = g;
+  }
+  const int no = w.n_outer;
+  for (int j = 0; j < NX; ++j) {      // lower triangle column by column, mirrored on store
+    for (int i = j + lane; i < NX; i += 32) {
+      double h = cq_block(w, i, j);
+      for (int k = 0; k < no; ++k) h += w.outer_c[k] * w.rows[w.outer_a[k]][i] * w.rows[w.outer_b[k]][j];
+      if (i == j) {
+        h += Qd[i];
+        if (i >= 7 && i < NQ) {
+          const double lo = md.jnt_lo[i - 7], hi = md.jnt_hi[i - 7];
+          double gd = 0.0;
+          if (isfinite(lo) && isfinite(hi) && lo < hi) limit_d(x[i], lo, hi, wt.w_joint_limits, &gd, &h);
+        }
+      }
+      lxx[j * NX + i] = h;
+      lxx[i * NX + j] = h;
+    }
+  }
+  if (!terminal) {
+    for (int e = lane; e < NU * NU; e += 32) {
+      const int i = e % NU, j = e / NU;
+      double h = 0.0;
+      if (i == j) {
+        double g = wt.Rdiag[i] * (u[i] - u_ref[i]);
+        h = wt.Rdiag[i];
+        limit_d(u[i], md.ctrl_lo[i], md.ctrl_hi[i], wt.w_control_limits, &g, &h);
+        lu[i] = g;
+      }
+      luu[e] = h;
+    }
+  }
+}
+
+#if defined(__CUDACC__)
+#define H1_CQ_PHASE(call) { call; __syncwarp(); }
+#define H1_CQ_LANE const int lane = threadIdx.x & 31;
+#else
+#define H1_CQ_PHASE(call) { for (int lane = 0; lane < 32; ++lane) { call; } }
+#define H1_CQ_LANE
+#endif
+
+H1_DEV void cost_quadratics_warp(const CostModel& cm, const DynModel& md, const H1Weights& wt, CostWarp& w,
+                                 const double* x, const double* u, const double* x_ref, const double* u_ref,
+                                 const KnotTargets& kt, double* lx, double* lu, double* lxx, double* luu) {
+  H1_CQ_LANE
+  H1_CQ_PHASE(ph_cq_load(lane, w, x))
+  H1_CQ_PHASE(ph_cq_walk(lane, cm, w))
+  H1_CQ_PHASE(ph_cq_sets(lane, cm, w))
+  H1_CQ_PHASE(ph_cq_vel(lane, cm, w))
+  H1_CQ_PHASE(ph_cq_terms(lane, wt, kt, w))
+  H1_CQ_PHASE(ph_cq_rows(lane, cm, w))
+  H1_CQ_PHASE(ph_cq_rows2(lane, w))
+  H1_CQ_PHASE(ph_cq_tables(lane, cm, w))
+  H1_CQ_PHASE(ph_cq_store(lane, md, wt, w, x, u, x_ref, u_ref, kt.terminal, lx, lu, lxx, luu))
+}
+
+}  // namespace h1

@@ -1,0 +1,155 @@
+// Kernels built on the warp-cooperative f_D: batched one-step dynamics, nominal rollout with on-device cost,
+// forward-difference linearization, and kinematic queries.
+#pragma once
+#include "h1_cost_eval.cuh"
+
+namespace h1 {
+
+// Stage the (read-only) model into shared memory; returns the aligned start of the per-warp scratch area.
+template <class Model>
+__device__ __forceinline__ unsigned char* stage_model(unsigned char* smem, const Model* g, const Model** out) {
+  Model* s = reinterpret_cast<Model*>(smem);
+  const int nwords = sizeof(Model) / 4;
+  const unsigned* src = reinterpret_cast<const unsigned*>(g);
+  unsigned* dst = reinterpret_cast<unsigned*>(s);
+  for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+  *out = s;
+  return smem + ((sizeof(Model) + 15) / 16) * 16;
+}
+
+// ---- x_next[i] = f_D(x[i], u[i]) : one warp per state (RobotUtils::rolloutOneStep / step) ----
+__global__ void k_dyn_step(const DynModel* gmd, int n, const double* __restrict__ x, const double* __restrict__ u,
+                           double* __restrict__ xn) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const DynModel* md;
+  unsigned char* p = stage_model(smem, gmd, &md);
+  DynWarp& w = reinterpret_cast<DynWarp*>(p)[threadIdx.x >> 5];
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  dyn_step_warp(*md, w, x + (size_t)i * NX, u + (size_t)i * NU, xn + (size_t)i * NX);
+}
+
+// ---- bias forces, dynamics-model CoM and ankle positions of arbitrary states (computeGravComp,
+//      loadReferences' per-row FK) ----
+__global__ void k_dyn_query(const DynModel* gmd, int n, const double* __restrict__ x, double* __restrict__ bias,
+                            double* __restrict__ com, double* __restrict__ ee) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const DynModel* md;
+  unsigned char* p = stage_model(smem, gmd, &md);
+  DynWarp& w = reinterpret_cast<DynWarp*>(p)[threadIdx.x >> 5];
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int lane = threadIdx.x & 31;
+  dyn_assemble_warp(*md, w, x + (size_t)i * NX, nullptr);
+  if (bias && lane < NV) bias[(size_t)i * NV + lane] = w.biasv[lane];
+  if (com && lane < 3) com[(size_t)i * 3 + lane] = w.com[lane];
+  if (ee && lane < 6) ee[(size_t)i * 6 + lane] = w.q[lane % 3] + w.footr[lane / 3][lane % 3];
+}
+
+// ---- nominal rollout xbar[t+1] = f_D(xbar[t], ubar[t]) with the trajectory cost as a by-product
+//      (iLQR::forwardRolloutNominal + the baseline computeTotalCost of the following line search).
+//      One warp per instance. t_begin > 0 rolls out only the tail (warm start: last knot). ----
+__global__ void k_rollout(const DynModel* gmd, const H1Weights* gw, RefTable refs, int B, int N, int t_begin,
+                          const int* __restrict__ active, const double* __restrict__ x0, double* __restrict__ xbar,
+                          const double* __restrict__ ubar, double* __restrict__ cost_out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const DynModel* md;
+  unsigned char* p = stage_model(smem, gmd, &md);
+  DynWarp& w = reinterpret_cast<DynWarp*>(p)[threadIdx.x >> 5];
+  const int inst = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (inst >= B) return;
+  if (active && !active[inst]) return;
+  const int lane = threadIdx.x & 31;
+  double* xb = xbar + (size_t)inst * (N + 1) * NX;
+  const double* ub = ubar + (size_t)inst * N * NU;
+  if (x0) {
+    for (int i = lane; i < NX; i += 32) xb[i] = x0[(size_t)inst * NX + i];
+    __syncwarp();
+  }
+  const RefView r = refs.view(inst);
+  double total = 0.0;
+  for (int t = 0; t < N; ++t) {
+    if (t >= t_begin) {
+      dyn_step_warp(*md, w, xb + t * NX, ub + t * NU, xb + (t + 1) * NX);
+    } else if (cost_out) {
+      dyn_assemble_warp(*md, w, xb + t * NX, ub + t * NU);
+    }
+    if (cost_out) total += knot_cost_warp(*md, w, *gw, r, t, ub + t * NU, false);
+    __syncwarp();
+  }
+  if (cost_out) {
+    dyn_assemble_warp(*md, w, xb + N * NX, nullptr);
+    total += knot_cost_warp(*md, w, *gw, r, N, nullptr, true);
+    if (lane == 0) cost_out[inst] = total;
+  }
+}
+
+// ---- forward-difference linearization (iLQR::computeLinearization -> RobotUtils::linearizeDynamicsFD):
+//      A[:,i] = (f(x + eps e_i, u) - f(x,u)) / eps, B[:,j] likewise; 1 + 51 + 19 evaluations per knot.
+//      One CTA per (instance, knot); its warps share the 71 evaluations through a shared-memory table. ----
+constexpr int LIN_WARPS = 6;
+constexpr int LIN_EVALS = 1 + NX + NU;
+__global__ void __launch_bounds__(LIN_WARPS * 32)
+k_linearize_fd(const DynModel* gmd, int N, double eps, const int* __restrict__ active,
+               const double* __restrict__ xbar, const double* __restrict__ ubar, double* __restrict__ A,
+               double* __restrict__ Bm) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int inst = blockIdx.x / N, t = blockIdx.x % N;
+  if (active && !active[inst]) return;
+  const DynModel* md;
+  unsigned char* p = stage_model(smem, gmd, &md);
+  DynWarp* ws = reinterpret_cast<DynWarp*>(p);
+  double* fx = reinterpret_cast<double*>(p + sizeof(DynWarp) * LIN_WARPS);  // [LIN_EVALS][NX]
+  double* xs = fx + LIN_EVALS * NX;                                         // [NX + NU] staged inputs
+  const double* x = xbar + ((size_t)inst * (N + 1) + t) * NX;
+  const double* u = ubar + ((size_t)inst * N + t) * NU;
+  for (int i = threadIdx.x; i < NX + NU; i += blockDim.x) xs[i] = (i < NX) ? x[i] : u[i - NX];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  for (int e = warp; e < LIN_EVALS; e += LIN_WARPS)
+    dyn_step_warp(*md, ws[warp], xs, xs + NX, fx + e * NX, e - 1, eps);
+  __syncthreads();
+  double* Ak = A + ((size_t)inst * N + t) * NX * NX;
+  double* Bk = Bm + ((size_t)inst * N + t) * NX * NU;
+  const double inv = 1.0 / eps;
+  (void)inv;
+  for (int i = threadIdx.x; i < NX * (NX + NU); i += blockDim.x) {
+    const int col = i / NX, row = i - col * NX;
+    const double v = (fx[(1 + col) * NX + row] - fx[row]) / eps;
+    if (col < NX) Ak[i] = v; else Bk[i - NX * NX] = v;
+  }
+}
+
+// ---- analytic linearization: A = d f_D/dx, B = d f_D/du exactly, by forward-mode tangents sharing one
+//      factorisation of Mhat per knot (see h1_dyn.cuh). One CTA per (instance, knot); warp 0 does the primal
+//      pass while the other warps already assemble their first tangent direction. ----
+constexpr int LINA_WARPS = 4;
+__global__ void __launch_bounds__(LINA_WARPS * 32)
+k_linearize_analytic(const DynModel* gmd, int N, const int* __restrict__ active, const double* __restrict__ xbar,
+                     const double* __restrict__ ubar, double* __restrict__ A, double* __restrict__ Bm) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int inst = blockIdx.x / N, t = blockIdx.x % N;
+  if (active && !active[inst]) return;
+  const DynModel* md;
+  unsigned char* p = stage_model(smem, gmd, &md);
+  DynWarpT<Dual>* ws = reinterpret_cast<DynWarpT<Dual>*>(p);
+  PrimalFactor* pf = reinterpret_cast<PrimalFactor*>(p + sizeof(DynWarpT<Dual>) * LINA_WARPS);
+  double* xs = reinterpret_cast<double*>(pf + 1);
+  const double* x = xbar + ((size_t)inst * (N + 1) + t) * NX;
+  const double* u = ubar + ((size_t)inst * N + t) * NU;
+  for (int i = threadIdx.x; i < NX + NU; i += blockDim.x) xs[i] = (i < NX) ? x[i] : u[i - NX];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) dyn_primal_factor_warp(*md, *reinterpret_cast<DynWarp*>(&ws[0]), xs, xs + NX, nullptr, *pf);
+  double* Ak = A + ((size_t)inst * N + t) * NX * NX;
+  double* Bk = Bm + ((size_t)inst * N + t) * NX * NU;
+  bool first = true;
+  for (int e = warp; e < NX + NU; e += LINA_WARPS) {
+    dyn_tangent_assemble_warp(*md, ws[warp], xs, xs + NX, e);
+    if (first) { __syncthreads(); first = false; }
+    dyn_tangent_solve_warp(*md, ws[warp], *pf, e < NX ? Ak + e * NX : Bk + (e - NX) * NX);
+  }
+}
+
+}  // namespace h1

@@ -1,0 +1,512 @@
+// C ABI of the B200-native H1 iLQR solver core (include/h1ilqr.h): handle, device-resident buffers, kernel
+// launch sequences. Host language above this file is C++ (host/) or Python ctypes (tests, bench).
+// There is no CPU fallback anywhere in this library: every entry point runs CUDA kernels on the handle's
+// device or returns H1ILQR_ECUDA.
+#include "h1_kernels_solve.cuh"
+#include "h1_riccati.cuh"
+#include "model_tables.h"
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace h1;
+
+static thread_local std::string g_err;
+static int set_err(int code, const char* what, cudaError_t e = cudaSuccess) {
+  g_err = what;
+  if (e != cudaSuccess) { g_err += ": "; g_err += cudaGetErrorString(e); }
+  return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return set_err(H1ILQR_ECUDA, #call, e_); } while (0)
+
+struct H1Ilqr {
+  int B = 0, N = 0, device = 0;
+  cudaStream_t stream = nullptr;
+  H1SolverOptions opt;
+  DynModel* d_dyn = nullptr; CostModel* d_cost = nullptr; H1Weights* d_w = nullptr; H1SolverOptions* d_opt = nullptr;
+  double *xbar = nullptr, *ubar = nullptr, *K = nullptr, *kff = nullptr, *A = nullptr, *Bm = nullptr;
+  double *lx = nullptr, *lu = nullptr, *lxx = nullptr, *luu = nullptr, *xnew = nullptr, *unew = nullptr;
+  double *x0 = nullptr, *u_init = nullptr, *u_apply = nullptr, *prev_xbar = nullptr, *prev_ubar = nullptr;
+  double *x_ref = nullptr, *u_ref = nullptr, *com_ref = nullptr, *ee_ref = nullptr, *com_vel_ref = nullptr;
+  int* stance = nullptr; int ref_shared = 1;
+  double *lambda = nullptr, *cost = nullptr, *prev_cost = nullptr, *nominal_cost = nullptr, *ls_cost = nullptr;
+  int *active = nullptr, *second = nullptr, *iters = nullptr, *status = nullptr, *ls_ok = nullptr, *ls_alpha = nullptr;
+  int *has_prev = nullptr, *warm_mask = nullptr, *cold_mask = nullptr, *warm_in = nullptr;
+  double* cost_trace = nullptr; int* alpha_trace = nullptr;
+  double* scratch = nullptr; size_t scratch_bytes = 0;   // device staging for n-state queries
+  void* pin = nullptr; size_t pin_bytes = 0;              // pinned host staging
+  std::vector<void*> allocs;
+  // timing
+  bool timing = false;
+  H1StageTimes times;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  int launches = 0;
+  size_t smem_lina = 0;
+  size_t smem_dyn4 = 0, smem_lin = 0, smem_cq = 0, smem_ls = 0, smem_ric = 0;
+};
+
+template <class T> static cudaError_t dalloc(H1Ilqr* h, T** p, size_t n) {
+  cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+  if (e == cudaSuccess) { h->allocs.push_back(*p); e = cudaMemsetAsync(*p, 0, n * sizeof(T), h->stream); }
+  return e;
+}
+
+static RefTable ref_table(const H1Ilqr* h) {
+  RefTable r;
+  r.x_ref = h->x_ref; r.u_ref = h->u_ref; r.com_ref = h->com_ref; r.ee_ref = h->ee_ref;
+  r.com_vel_ref = h->com_vel_ref; r.stance = h->stance; r.shared = h->ref_shared; r.N = h->N;
+  return r;
+}
+
+extern "C" {
+
+void h1ilqr_default_options(H1SolverOptions* o) {
+  o->max_iterations = 10; o->tolerance = 1e-4; o->reg_init = 1e-6; o->reg_min = 1e-6; o->reg_max = 1e-3;
+  o->accept_margin = 1e-6; o->fd_eps = 1e-5; o->divergence_cost = 1e6; o->linearization = H1ILQR_LIN_ANALYTIC;
+  const double a[H1ILQR_NALPHA] = {1.0, 0.8, 0.6, 0.4, 0.2, 0.1, 0.05, 0.01};
+  std::memcpy(o->alphas, a, sizeof(a));
+}
+
+const char* h1ilqr_last_error(void) { return g_err.c_str(); }
+int h1ilqr_batch(const H1Ilqr* h) { return h ? h->B : 0; }
+int h1ilqr_horizon(const H1Ilqr* h) { return h ? h->N : 0; }
+void* h1ilqr_stream(H1Ilqr* h) { return h ? (void*)h->stream : nullptr; }
+
+void h1ilqr_destroy(H1Ilqr* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->pin) cudaFreeHost(h->pin);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1SolverOptions* opt, int batch, int N,
+                  int device, H1Ilqr** out) {
+  if (!out || batch < 1 || N < 2) return set_err(H1ILQR_EARG, "h1ilqr_create: bad arguments");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return set_err(H1ILQR_ECUDA, "no CUDA device (this library has no CPU fallback)", e);
+  if (device < 0 || device >= ndev) return set_err(H1ILQR_EARG, "h1ilqr_create: bad device index");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return set_err(H1ILQR_ECUDA, "device is not sm_100 class (kernels are built for sm_100a only)");
+  H1Ilqr* h = new H1Ilqr;
+  h->B = batch; h->N = N; h->device = device;
+  if (opt) h->opt = *opt; else h1ilqr_default_options(&h->opt);
+  if (h->opt.max_iterations < 1 || h->opt.max_iterations > H1ILQR_MAX_ITERS) { delete h; return set_err(H1ILQR_EARG, "max_iterations out of range"); }
+  DynModel dm; CostModel cm;
+  if (!build_dyn_model(dyn_model ? *dyn_model : *h1_default_dynamics_model(), &dm) ||
+      !build_cost_model(cost_model ? *cost_model : *h1_default_cost_model(), &cm)) {
+    delete h; return set_err(H1ILQR_EARG, "model is not a DFS-ordered H1-like tree");
+  }
+#define CUH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(H1ILQR_ECUDA, #call, e_); h1ilqr_destroy(h); return H1ILQR_ECUDA; } } while (0)
+  CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUH(cudaEventCreate(&h->ev[0])); CUH(cudaEventCreate(&h->ev[1]));
+  const size_t B = batch, N1 = N + 1;
+  CUH(dalloc(h, &h->d_dyn, 1)); CUH(dalloc(h, &h->d_cost, 1)); CUH(dalloc(h, &h->d_w, 1)); CUH(dalloc(h, &h->d_opt, 1));
+  CUH(cudaMemcpyAsync(h->d_dyn, &dm, sizeof(dm), cudaMemcpyHostToDevice, h->stream));
+  CUH(cudaMemcpyAsync(h->d_cost, &cm, sizeof(cm), cudaMemcpyHostToDevice, h->stream));
+  CUH(cudaMemcpyAsync(h->d_opt, &h->opt, sizeof(h->opt), cudaMemcpyHostToDevice, h->stream));
+  CUH(cudaStreamSynchronize(h->stream));  // dm / cm are stack objects
+  CUH(dalloc(h, &h->xbar, B * N1 * NX)); CUH(dalloc(h, &h->ubar, B * N * NU));
+  CUH(dalloc(h, &h->K, B * N * NU * NX)); CUH(dalloc(h, &h->kff, B * N * NU));
+  CUH(dalloc(h, &h->A, B * N * NX * NX)); CUH(dalloc(h, &h->Bm, B * N * NX * NU));
+  CUH(dalloc(h, &h->lx, B * N1 * NX)); CUH(dalloc(h, &h->lu, B * N * NU));
+  CUH(dalloc(h, &h->lxx, B * N1 * NX * NX)); CUH(dalloc(h, &h->luu, B * N * NU * NU));
+  CUH(dalloc(h, &h->xnew, B * H1ILQR_NALPHA * N1 * NX)); CUH(dalloc(h, &h->unew, B * H1ILQR_NALPHA * N * NU));
+  CUH(dalloc(h, &h->x0, B * NX)); CUH(dalloc(h, &h->u_init, B * NU)); CUH(dalloc(h, &h->u_apply, B * NU));
+  CUH(dalloc(h, &h->prev_xbar, B * N1 * NX)); CUH(dalloc(h, &h->prev_ubar, B * N * NU));
+  CUH(dalloc(h, &h->x_ref, B * N1 * NX)); CUH(dalloc(h, &h->u_ref, B * N * NU)); CUH(dalloc(h, &h->com_ref, B * N1 * 3));
+  CUH(dalloc(h, &h->ee_ref, B * N1 * 6)); CUH(dalloc(h, &h->com_vel_ref, B * N1 * 3)); CUH(dalloc(h, &h->stance, B * N1 * 2));
+  CUH(dalloc(h, &h->lambda, B)); CUH(dalloc(h, &h->cost, B)); CUH(dalloc(h, &h->prev_cost, B));
+  CUH(dalloc(h, &h->nominal_cost, B)); CUH(dalloc(h, &h->ls_cost, B));
+  CUH(dalloc(h, &h->active, B)); CUH(dalloc(h, &h->second, B)); CUH(dalloc(h, &h->iters, B)); CUH(dalloc(h, &h->status, B));
+  CUH(dalloc(h, &h->ls_ok, B)); CUH(dalloc(h, &h->ls_alpha, B)); CUH(dalloc(h, &h->has_prev, B));
+  CUH(dalloc(h, &h->warm_mask, B)); CUH(dalloc(h, &h->cold_mask, B)); CUH(dalloc(h, &h->warm_in, B));
+  CUH(dalloc(h, &h->cost_trace, B * h->opt.max_iterations)); CUH(dalloc(h, &h->alpha_trace, B * h->opt.max_iterations * 2));
+  h->scratch_bytes = B * N1 * (NX + NU + NX + NV + 9) * sizeof(double);
+  { double* sp = nullptr; CUH(dalloc(h, &sp, h->scratch_bytes / sizeof(double))); h->scratch = sp; }
+  h->pin_bytes = B * (NX + 2 * NU + 4) * sizeof(double);
+  CUH(cudaMallocHost(&h->pin, h->pin_bytes));
+  k_fill_double<<<(batch + 255) / 256, 256, 0, h->stream>>>(batch, h->lambda, h->opt.reg_init);
+  k_fill_int<<<(int)((B * N1 * 2 + 255) / 256), 256, 0, h->stream>>>((int)(B * N1 * 2), h->stance, 1);
+  // dynamic shared memory sizes
+  const size_t mdl = ((sizeof(DynModel) + 15) / 16) * 16, cml = ((sizeof(CostModel) + 15) / 16) * 16;
+  h->smem_dyn4 = mdl + 4 * sizeof(DynWarp);
+  h->smem_lin = mdl + LIN_WARPS * sizeof(DynWarp) + (LIN_EVALS * NX + NX + NU) * sizeof(double);
+  h->smem_lina = mdl + LINA_WARPS * sizeof(DynWarpT<Dual>) + sizeof(PrimalFactor) + (NX + NU) * sizeof(double);
+  h->smem_cq = cml + CQ_WARPS * sizeof(CostWarp);
+  h->smem_ls = mdl + H1ILQR_NALPHA * sizeof(DynWarp) + (H1ILQR_NALPHA + H1ILQR_NALPHA * (NX + NU)) * sizeof(double);
+  h->smem_ric = sizeof(RiccatiSmem);
+  CUH(cudaFuncSetAttribute(k_dyn_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
+  CUH(cudaFuncSetAttribute(k_dyn_query, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
+  CUH(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
+  CUH(cudaFuncSetAttribute(k_linearize_fd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_lin));
+  CUH(cudaFuncSetAttribute(k_linearize_analytic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_lina));
+  CUH(cudaFuncSetAttribute(k_cost_quadratics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_cq));
+  CUH(cudaFuncSetAttribute(k_line_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_ls));
+  CUH(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_ric));
+  CUH(cudaStreamSynchronize(h->stream));
+  CUH(cudaGetLastError());
+#undef CUH
+  std::memset(&h->times, 0, sizeof(h->times));
+  *out = h;
+  return H1ILQR_OK;
+}
+
+static int guard(H1Ilqr* h) {
+  if (!h) return set_err(H1ILQR_EARG, "null handle");
+  CU(cudaSetDevice(h->device));
+  return 0;
+}
+#define GUARD(h) do { int g_ = guard(h); if (g_) return g_; } while (0)
+#define H2D(dst, src, n) CU(cudaMemcpyAsync(dst, src, (n), cudaMemcpyHostToDevice, h->stream))
+#define D2H(dst, src, n) CU(cudaMemcpyAsync(dst, src, (n), cudaMemcpyDeviceToHost, h->stream))
+#define SYNC() CU(cudaStreamSynchronize(h->stream))
+#define LAUNCHED() do { ++h->launches; } while (0)
+
+int h1ilqr_set_weights(H1Ilqr* h, const H1Weights* w) {
+  GUARD(h);
+  if (!w) return set_err(H1ILQR_EARG, "null weights");
+  H2D(h->d_w, w, sizeof(*w));
+  SYNC();
+  return 0;
+}
+
+int h1ilqr_set_reference_window(H1Ilqr* h, const double* x_ref, const double* u_ref, const double* com_ref,
+                                const double* ee_ref, const int* stance, const double* com_vel_ref, int shared) {
+  GUARD(h);
+  if (!x_ref || !u_ref || !com_ref || !ee_ref || !stance) return set_err(H1ILQR_EARG, "null reference array");
+  const size_t n = shared ? 1 : h->B, N1 = h->N + 1, N = h->N;
+  h->ref_shared = shared ? 1 : 0;
+  H2D(h->x_ref, x_ref, n * N1 * NX * sizeof(double)); H2D(h->u_ref, u_ref, n * N * NU * sizeof(double));
+  H2D(h->com_ref, com_ref, n * N1 * 3 * sizeof(double)); H2D(h->ee_ref, ee_ref, n * N1 * 6 * sizeof(double));
+  H2D(h->stance, stance, n * N1 * 2 * sizeof(int));
+  if (com_vel_ref) H2D(h->com_vel_ref, com_vel_ref, n * N1 * 3 * sizeof(double));
+  else CU(cudaMemsetAsync(h->com_vel_ref, 0, n * N1 * 3 * sizeof(double), h->stream));
+  SYNC();
+  return 0;
+}
+
+// ---------------- stage launchers (no host sync) ----------------
+static void launch_rollout(H1Ilqr* h, const int* mask, const double* x0_dev, int t_begin, double* cost_out) {
+  const int wpb = 4, blocks = (h->B + wpb - 1) / wpb;
+  k_rollout<<<blocks, wpb * 32, h->smem_dyn4, h->stream>>>(h->d_dyn, h->d_w, ref_table(h), h->B, h->N, t_begin, mask,
+                                                          x0_dev, h->xbar, h->ubar, cost_out);
+  LAUNCHED();
+}
+static void launch_linearize(H1Ilqr* h, const int* mask) {
+  if (h->opt.linearization != H1ILQR_LIN_FD) {
+    k_linearize_analytic<<<h->B * h->N, LINA_WARPS * 32, h->smem_lina, h->stream>>>(h->d_dyn, h->N, mask, h->xbar, h->ubar,
+                                                                                 h->A, h->Bm);
+    LAUNCHED();
+    return;
+  }
+  k_linearize_fd<<<h->B * h->N, LIN_WARPS * 32, h->smem_lin, h->stream>>>(h->d_dyn, h->N, h->opt.fd_eps, mask, h->xbar,
+                                                                         h->ubar, h->A, h->Bm);
+  LAUNCHED();
+}
+static void launch_cost_quadratics(H1Ilqr* h, const int* mask) {
+  const long warps = (long)h->B * (h->N + 1);
+  const int blocks = (int)((warps + CQ_WARPS - 1) / CQ_WARPS);
+  k_cost_quadratics<<<blocks, CQ_WARPS * 32, h->smem_cq, h->stream>>>(h->d_cost, h->d_dyn, h->d_w, ref_table(h), h->B,
+                                                                     h->N, mask, h->xbar, h->ubar, h->lx, h->lu, h->lxx,
+                                                                     h->luu);
+  LAUNCHED();
+}
+static void launch_backward(H1Ilqr* h, const int* mask) {
+  k_backward<<<h->B, RIC_THREADS, h->smem_ric, h->stream>>>(h->N, mask, h->lambda, h->A, h->Bm, h->lx, h->lu, h->lxx,
+                                                           h->luu, h->K, h->kff, h->status);
+  LAUNCHED();
+}
+static void launch_line_search(H1Ilqr* h, const int* mask) {
+  k_line_search<<<h->B, H1ILQR_NALPHA * 32, h->smem_ls, h->stream>>>(h->d_dyn, h->d_w, h->d_opt, ref_table(h), h->N, mask,
+                                                                    h->x0, h->nominal_cost, h->xbar, h->ubar, h->K, h->kff,
+                                                                    h->xnew, h->unew, h->ls_ok, h->ls_cost, h->ls_alpha);
+  LAUNCHED();
+}
+static SolveState solve_state(H1Ilqr* h) {
+  SolveState st;
+  st.lambda = h->lambda; st.cost = h->cost; st.prev_cost = h->prev_cost; st.nominal_cost = h->nominal_cost;
+  st.active = h->active; st.second = h->second; st.iters = h->iters; st.status = h->status;
+  st.ls_ok = h->ls_ok; st.ls_cost = h->ls_cost; st.ls_alpha = h->ls_alpha;
+  st.cost_trace = h->cost_trace; st.alpha_trace = h->alpha_trace;
+  return st;
+}
+static void launch_state(H1Ilqr* h, int it, int phase) {
+  k_solve_state<<<(h->B + 127) / 128, 128, 0, h->stream>>>(solve_state(h), h->d_opt, h->B, it, phase);
+  LAUNCHED();
+}
+
+struct StageTimer {
+  H1Ilqr* h; double* acc;
+  StageTimer(H1Ilqr* h_, double* acc_) : h(h_), acc(acc_) { if (h->timing) cudaEventRecord(h->ev[0], h->stream); }
+  ~StageTimer() {
+    if (!h->timing) return;
+    cudaEventRecord(h->ev[1], h->stream);
+    cudaEventSynchronize(h->ev[1]);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    *acc += ms;
+  }
+};
+
+// The whole iLQR::solve launch sequence, stream-ordered, no host round trips (unless stage timing is on).
+static void enqueue_solve(H1Ilqr* h) {
+  launch_rollout(h, nullptr, nullptr, h->N, h->cost);  // current_cost = computeTotalCost(xbar, ubar)
+  for (int it = 0; it < h->opt.max_iterations; ++it) {
+    launch_state(h, it, 0);
+    { StageTimer t(h, &h->times.rollout_ms); launch_rollout(h, h->active, h->x0, 0, h->nominal_cost); }
+    { StageTimer t(h, &h->times.linearize_ms); launch_linearize(h, h->active); }
+    { StageTimer t(h, &h->times.cost_quadratics_ms); launch_cost_quadratics(h, h->active); }
+    { StageTimer t(h, &h->times.backward_ms); launch_backward(h, h->active); }
+    { StageTimer t(h, &h->times.line_search_ms); launch_line_search(h, h->active); }
+    launch_state(h, it, 1);
+    { StageTimer t(h, &h->times.backward_ms); launch_backward(h, h->second); }
+    { StageTimer t(h, &h->times.line_search_ms); launch_line_search(h, h->second); }
+    launch_state(h, it, 2);
+  }
+}
+
+static int enqueue_initialize(H1Ilqr* h, const int* warm_dev, int u_shared) {
+  k_init_guess<<<h->B, 128, 0, h->stream>>>(h->B, h->N, h->x0, warm_dev, h->has_prev, h->u_init, u_shared, h->prev_xbar,
+                                            h->prev_ubar, h->xbar, h->ubar, h->warm_mask, h->cold_mask);
+  LAUNCHED();
+  launch_rollout(h, h->cold_mask, nullptr, 0, nullptr);
+  launch_rollout(h, h->warm_mask, nullptr, h->N - 1, nullptr);
+  return 0;
+}
+
+int h1ilqr_initialize(H1Ilqr* h, const double* x0, const int* warm, const double* u_init, int u_init_shared) {
+  GUARD(h);
+  if (!x0) return set_err(H1ILQR_EARG, "null x0");
+  H2D(h->x0, x0, (size_t)h->B * NX * sizeof(double));
+  if (u_init) H2D(h->u_init, u_init, (u_init_shared ? 1 : (size_t)h->B) * NU * sizeof(double));
+  else CU(cudaMemsetAsync(h->u_init, 0, (size_t)h->B * NU * sizeof(double), h->stream));
+  const int* wd = nullptr;
+  if (warm) { H2D(h->warm_in, warm, (size_t)h->B * sizeof(int)); wd = h->warm_in; }
+  else { k_fill_int<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->B, h->warm_in, 0); wd = h->warm_in; }
+  enqueue_initialize(h, wd, u_init ? u_init_shared : 1);
+  SYNC();
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static int finish_solve(H1Ilqr* h, double* cost_out, int* iters_out, int* status_out) {
+  if (cost_out) D2H(cost_out, h->cost, (size_t)h->B * sizeof(double));
+  if (iters_out) D2H(iters_out, h->iters, (size_t)h->B * sizeof(int));
+  std::vector<int> st(h->B);
+  D2H(st.data(), h->status, (size_t)h->B * sizeof(int));
+  SYNC();
+  CU(cudaGetLastError());
+  int bad = 0;
+  for (int i = 0; i < h->B; ++i) bad |= st[i];
+  if (status_out) std::memcpy(status_out, st.data(), (size_t)h->B * sizeof(int));
+  return bad ? H1ILQR_ENOTFINITE : 0;
+}
+
+int h1ilqr_solve(H1Ilqr* h, const double* x0, double* cost_out, int* iters_out, int* status_out) {
+  GUARD(h);
+  if (!x0) return set_err(H1ILQR_EARG, "null x0");
+  H2D(h->x0, x0, (size_t)h->B * NX * sizeof(double));
+  const int l0 = h->launches;
+  std::memset(&h->times, 0, sizeof(h->times));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, h->stream));
+  enqueue_solve(h);
+  CU(cudaEventRecord(e1, h->stream));
+  int rc = finish_solve(h, cost_out, iters_out, status_out);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  h->times.total_ms = ms; h->times.launches = h->launches - l0;
+  if (rc == H1ILQR_ENOTFINITE) set_err(rc, "non-finite cost or gains in at least one instance");
+  return rc;
+}
+
+int h1ilqr_mpc_reset(H1Ilqr* h) {
+  GUARD(h);
+  k_fill_int<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->B, h->has_prev, 0);
+  k_fill_double<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->B, h->lambda, h->opt.reg_init);
+  SYNC();
+  return 0;
+}
+
+int h1ilqr_mpc_step(H1Ilqr* h, const double* x_measured, const double* u_init, int u_init_shared, double* u_apply,
+                    double* cost_out) {
+  GUARD(h);
+  if (!x_measured || !u_apply) return set_err(H1ILQR_EARG, "null x_measured / u_apply");
+  const size_t B = h->B, N = h->N;
+  // pinned staging: x in, u_apply + cost out
+  double* pin_x = (double*)h->pin; double* pin_u = pin_x + B * NX; double* pin_c = pin_u + B * NU;
+  double* pin_ui = pin_c + B;
+  std::memcpy(pin_x, x_measured, B * NX * sizeof(double));
+  H2D(h->x0, pin_x, B * NX * sizeof(double));
+  if (u_init) {
+    const size_t n = (u_init_shared ? 1 : B) * NU;
+    std::memcpy(pin_ui, u_init, n * sizeof(double));
+    H2D(h->u_init, pin_ui, n * sizeof(double));
+  } else CU(cudaMemsetAsync(h->u_init, 0, B * NU * sizeof(double), h->stream));
+  const int l0 = h->launches;
+  std::memset(&h->times, 0, sizeof(h->times));
+  enqueue_initialize(h, nullptr, u_init ? u_init_shared : 1);
+  enqueue_solve(h);
+  k_first_control<<<h->B, 32, 0, h->stream>>>(h->B, h->N, h->x0, h->xbar, h->ubar, h->K, h->u_apply);
+  LAUNCHED();
+  CU(cudaMemcpyAsync(h->prev_xbar, h->xbar, B * (N + 1) * NX * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->prev_ubar, h->ubar, B * N * NU * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  k_fill_int<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->B, h->has_prev, 1);
+  D2H(pin_u, h->u_apply, B * NU * sizeof(double));
+  D2H(pin_c, h->cost, B * sizeof(double));
+  SYNC();
+  CU(cudaGetLastError());
+  h->times.launches = h->launches - l0;
+  std::memcpy(u_apply, pin_u, B * NU * sizeof(double));
+  if (cost_out) std::memcpy(cost_out, pin_c, B * sizeof(double));
+  return 0;
+}
+
+// ---------------- granular stages ----------------
+int h1ilqr_rollout_nominal(H1Ilqr* h, const double* x0) {
+  GUARD(h);
+  if (!x0) return set_err(H1ILQR_EARG, "null x0");
+  H2D(h->x0, x0, (size_t)h->B * NX * sizeof(double));
+  launch_rollout(h, nullptr, h->x0, 0, h->nominal_cost);
+  SYNC(); CU(cudaGetLastError());
+  return 0;
+}
+int h1ilqr_linearize(H1Ilqr* h) { GUARD(h); launch_linearize(h, nullptr); SYNC(); CU(cudaGetLastError()); return 0; }
+int h1ilqr_cost_quadratics(H1Ilqr* h) { GUARD(h); launch_cost_quadratics(h, nullptr); SYNC(); CU(cudaGetLastError()); return 0; }
+int h1ilqr_backward_pass(H1Ilqr* h) { GUARD(h); launch_backward(h, nullptr); SYNC(); CU(cudaGetLastError()); return 0; }
+int h1ilqr_total_cost(H1Ilqr* h, double* cost_out) {
+  GUARD(h);
+  if (!cost_out) return set_err(H1ILQR_EARG, "null cost_out");
+  launch_rollout(h, nullptr, nullptr, h->N, h->nominal_cost);
+  D2H(cost_out, h->nominal_cost, (size_t)h->B * sizeof(double));
+  SYNC(); CU(cudaGetLastError());
+  return 0;
+}
+int h1ilqr_line_search(H1Ilqr* h, const double* x0, int* improved, double* new_cost, int* alpha_index) {
+  GUARD(h);
+  if (!x0) return set_err(H1ILQR_EARG, "null x0");
+  H2D(h->x0, x0, (size_t)h->B * NX * sizeof(double));  // candidates start from x0 (ilqr.cpp:327)
+  launch_rollout(h, nullptr, nullptr, h->N, h->nominal_cost);  // baseline = computeTotalCost(xbar, ubar)
+  launch_line_search(h, nullptr);
+  if (improved) D2H(improved, h->ls_ok, (size_t)h->B * sizeof(int));
+  if (new_cost) D2H(new_cost, h->ls_cost, (size_t)h->B * sizeof(double));
+  if (alpha_index) D2H(alpha_index, h->ls_alpha, (size_t)h->B * sizeof(int));
+  SYNC(); CU(cudaGetLastError());
+  return 0;
+}
+
+static int ensure_scratch(H1Ilqr* h, size_t bytes) {
+  if (bytes <= h->scratch_bytes) return 0;
+  double* p = nullptr;
+  CU(cudaMalloc((void**)&p, bytes));
+  h->allocs.push_back(p);
+  h->scratch = p; h->scratch_bytes = bytes;
+  return 0;
+}
+
+int h1ilqr_dynamics_step(H1Ilqr* h, int n, const double* x, const double* u, double* x_next) {
+  GUARD(h);
+  if (n < 1 || !x || !u || !x_next) return set_err(H1ILQR_EARG, "h1ilqr_dynamics_step: bad arguments");
+  int rc = ensure_scratch(h, (size_t)n * (2 * NX + NU) * sizeof(double));
+  if (rc) return rc;
+  double* dx = h->scratch; double* du = dx + (size_t)n * NX; double* dn = du + (size_t)n * NU;
+  H2D(dx, x, (size_t)n * NX * sizeof(double)); H2D(du, u, (size_t)n * NU * sizeof(double));
+  k_dyn_step<<<(n + 3) / 4, 128, h->smem_dyn4, h->stream>>>(h->d_dyn, n, dx, du, dn);
+  LAUNCHED();
+  D2H(x_next, dn, (size_t)n * NX * sizeof(double));
+  SYNC(); CU(cudaGetLastError());
+  return 0;
+}
+
+static int query(H1Ilqr* h, int n, const double* x, double* bias, double* com, double* ee) {
+  if (n < 1 || !x) return set_err(H1ILQR_EARG, "bad query arguments");
+  int rc = ensure_scratch(h, (size_t)n * (NX + NV + 9) * sizeof(double));
+  if (rc) return rc;
+  double* dx = h->scratch; double* db = dx + (size_t)n * NX; double* dc = db + (size_t)n * NV; double* de = dc + (size_t)n * 3;
+  H2D(dx, x, (size_t)n * NX * sizeof(double));
+  k_dyn_query<<<(n + 3) / 4, 128, h->smem_dyn4, h->stream>>>(h->d_dyn, n, dx, bias ? db : nullptr, com ? dc : nullptr,
+                                                            ee ? de : nullptr);
+  LAUNCHED();
+  if (bias) D2H(bias, db, (size_t)n * NV * sizeof(double));
+  if (com) D2H(com, dc, (size_t)n * 3 * sizeof(double));
+  if (ee) D2H(ee, de, (size_t)n * 6 * sizeof(double));
+  SYNC(); CU(cudaGetLastError());
+  return 0;
+}
+int h1ilqr_bias_forces(H1Ilqr* h, int n, const double* x, double* bias) { GUARD(h); return query(h, n, x, bias, nullptr, nullptr); }
+int h1ilqr_reference_kinematics(H1Ilqr* h, int n, const double* x, double* com, double* ee) { GUARD(h); return query(h, n, x, nullptr, com, ee); }
+
+// ---------------- accessors ----------------
+#define COPY_PAIR(fn_get, fn_set, p1, n1, p2, n2)                                              \
+  int fn_get(H1Ilqr* h, double* a, double* b) {                                                \
+    GUARD(h);                                                                                  \
+    if (a) D2H(a, h->p1, (n1) * sizeof(double));                                               \
+    if (b) D2H(b, h->p2, (n2) * sizeof(double));                                               \
+    SYNC(); return 0;                                                                          \
+  }                                                                                            \
+  int fn_set(H1Ilqr* h, const double* a, const double* b) {                                    \
+    GUARD(h);                                                                                  \
+    if (a) H2D(h->p1, a, (n1) * sizeof(double));                                               \
+    if (b) H2D(h->p2, b, (n2) * sizeof(double));                                               \
+    SYNC(); return 0;                                                                          \
+  }
+#define SZ(x) ((size_t)h->B * (x))
+COPY_PAIR(h1ilqr_get_trajectory, h1ilqr_set_trajectory, xbar, SZ((h->N + 1) * NX), ubar, SZ(h->N * NU))
+COPY_PAIR(h1ilqr_get_gains, h1ilqr_set_gains, K, SZ(h->N * NU * NX), kff, SZ(h->N * NU))
+COPY_PAIR(h1ilqr_get_linearization, h1ilqr_set_linearization, A, SZ(h->N * NX * NX), Bm, SZ(h->N * NX * NU))
+
+int h1ilqr_get_cost_quadratics(H1Ilqr* h, double* lx, double* lu, double* lxx, double* luu) {
+  GUARD(h);
+  if (lx) D2H(lx, h->lx, SZ((h->N + 1) * NX) * sizeof(double));
+  if (lu) D2H(lu, h->lu, SZ(h->N * NU) * sizeof(double));
+  if (lxx) D2H(lxx, h->lxx, SZ((h->N + 1) * NX * NX) * sizeof(double));
+  if (luu) D2H(luu, h->luu, SZ(h->N * NU * NU) * sizeof(double));
+  SYNC(); return 0;
+}
+int h1ilqr_set_cost_quadratics(H1Ilqr* h, const double* lx, const double* lu, const double* lxx, const double* luu) {
+  GUARD(h);
+  if (lx) H2D(h->lx, lx, SZ((h->N + 1) * NX) * sizeof(double));
+  if (lu) H2D(h->lu, lu, SZ(h->N * NU) * sizeof(double));
+  if (lxx) H2D(h->lxx, lxx, SZ((h->N + 1) * NX * NX) * sizeof(double));
+  if (luu) H2D(h->luu, luu, SZ(h->N * NU * NU) * sizeof(double));
+  SYNC(); return 0;
+}
+int h1ilqr_get_regularization(H1Ilqr* h, double* lambda) {
+  GUARD(h);
+  if (!lambda) return set_err(H1ILQR_EARG, "null lambda");
+  D2H(lambda, h->lambda, SZ(1) * sizeof(double)); SYNC(); return 0;
+}
+int h1ilqr_set_regularization(H1Ilqr* h, const double* lambda, int shared) {
+  GUARD(h);
+  if (!lambda) return set_err(H1ILQR_EARG, "null lambda");
+  if (shared) { k_fill_double<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->B, h->lambda, lambda[0]); }
+  else H2D(h->lambda, lambda, SZ(1) * sizeof(double));
+  SYNC(); return 0;
+}
+int h1ilqr_get_solve_trace(H1Ilqr* h, double* cost_trace, int* alpha_trace) {
+  GUARD(h);
+  if (cost_trace) D2H(cost_trace, h->cost_trace, SZ(h->opt.max_iterations) * sizeof(double));
+  if (alpha_trace) D2H(alpha_trace, h->alpha_trace, SZ(h->opt.max_iterations * 2) * sizeof(int));
+  SYNC(); return 0;
+}
+int h1ilqr_enable_stage_timing(H1Ilqr* h, int enable) { GUARD(h); h->timing = enable != 0; return 0; }
+int h1ilqr_get_stage_times(H1Ilqr* h, H1StageTimes* t) {
+  GUARD(h);
+  if (!t) return set_err(H1ILQR_EARG, "null times");
+  *t = h->times;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+// Host-side construction of the device model tables (h1::DynModel / h1::CostModel) from the plain-C
+// H1Model description: ancestor lists, dof-tree levels and subtree ranges used by the lane-parallel kernels.
+#include "model_tables.h"
+#include "../../include/h1_model_data.h"
+#include <cstring>
+
+extern "C" const H1Model* h1_default_dynamics_model(void) { return &H1_DYNAMICS_MODEL; }
+extern "C" const H1Model* h1_default_cost_model(void) { return &H1_COST_MODEL; }
+
+namespace h1 {
+
+static void tree_common(const H1Model& m, int* parent, int* axis, int* has_rfix, int* depth, int (*anc_body)[6],
+                        int* chain_end) {
+  for (int b = 0; b < NB; ++b) {
+    parent[b] = m.parent[b]; axis[b] = m.axis[b] < 0 ? 0 : m.axis[b]; has_rfix[b] = m.has_rfix[b];
+    depth[b] = (b == 0) ? 0 : depth[m.parent[b]] + 1;
+  }
+  for (int b = 0; b < NB; ++b) {
+    for (int d = 0; d < 6; ++d) anc_body[b][d] = 0;
+    for (int a = b; a >= 0; a = m.parent[a]) anc_body[b][depth[a]] = a;
+    chain_end[b] = b;
+  }
+  for (int b = NB - 1; b >= 1; --b)
+    if (chain_end[b] > chain_end[m.parent[b]]) chain_end[m.parent[b]] = chain_end[b];
+}
+
+bool build_dyn_model(const H1Model& m, DynModel* d) {
+  std::memset(d, 0, sizeof(*d));
+  for (int b = 0; b < NB; ++b) {
+    if (b > 0 && (m.parent[b] < 0 || m.parent[b] >= b)) return false;  // DFS order required
+    for (int i = 0; i < 3; ++i) { d->pos[b][i] = m.pos[b][i]; d->ipos[b][i] = m.ipos[b][i]; }
+    for (int i = 0; i < 9; ++i) d->rfix[b][i] = m.rfix[b][i];
+    for (int i = 0; i < 6; ++i) d->inertia[b][i] = m.inertia[b][i];
+    d->mass[b] = m.mass[b];
+  }
+  tree_common(m, d->parent, d->axis, d->has_rfix, d->depth, d->anc_body, d->chain_end);
+  for (int b = 0; b < NB; ++b) if (d->depth[b] > 5) return false;
+  for (int j = 0; j < NV; ++j) { d->armature[j] = m.armature[j]; d->damping[j] = m.damping[j]; }
+  for (int i = 0; i < NU; ++i) {
+    d->ctrl_lo[i] = m.ctrl_range[i][0]; d->ctrl_hi[i] = m.ctrl_range[i][1];
+    d->jnt_lo[i] = m.jnt_range[i][0]; d->jnt_hi[i] = m.jnt_range[i][1];
+  }
+  for (int f = 0; f < H1_NFOOT; ++f) {
+    d->foot_body[f] = m.foot_body[f];
+    d->foot_dof[f] = 5 + m.foot_body[f];
+    for (int c = 0; c < H1_NCP; ++c)
+      for (int i = 0; i < 3; ++i) d->foot_pts[f * H1_NCP + c][i] = m.foot_pts[f][c][i];
+  }
+  for (int i = 0; i < 3; ++i) d->gravity[i] = m.gravity[i];
+  d->h = m.timestep; d->kn = m.contact_kn; d->bn = m.contact_bn; d->bt = m.contact_bt; d->eps = m.contact_eps;
+  d->total_mass = m.total_mass;
+  // dof tree: base dofs 0..5 form a chain, hinge dof 5+b hangs below its parent body's last dof
+  for (int j = 0; j < NV; ++j) {
+    int n = 0;
+    if (j < 6) { for (int k = 0; k <= j; ++k) d->alist[j][n++] = k; }
+    else {
+      int b = j - 5;
+      for (int k = 0; k < 6; ++k) d->alist[j][n++] = k;
+      for (int dd = 1; dd <= d->depth[b]; ++dd) d->alist[j][n++] = 5 + d->anc_body[b][dd];
+    }
+    if (n > MAXSLOT) return false;
+    d->nlist[j] = n;
+    d->level[j] = n - 1;
+    d->dof_sub_end[j] = (j < 6) ? NV - 1 : 5 + d->chain_end[j - 5];
+  }
+  // each foot must hang on a full-depth chain so that its dof list has MAXSLOT entries
+  for (int f = 0; f < H1_NFOOT; ++f) if (d->nlist[d->foot_dof[f]] != MAXSLOT) return false;
+  for (int j = 0; j < NV; ++j) { d->cp_lo[j] = NCPT; d->cp_hi[j] = 0; }
+  for (int f = 0; f < H1_NFOOT; ++f)
+    for (int s = 0; s < MAXSLOT; ++s) {
+      int j = d->alist[d->foot_dof[f]][s];
+      if (f * H1_NCP < d->cp_lo[j]) d->cp_lo[j] = f * H1_NCP;
+      if ((f + 1) * H1_NCP > d->cp_hi[j]) d->cp_hi[j] = (f + 1) * H1_NCP;
+    }
+  for (int j = 0; j < NV; ++j) if (d->cp_hi[j] == 0) d->cp_lo[j] = 0;
+  d->n_base_children = 0;
+  for (int b = 1; b < NB; ++b)
+    if (m.parent[b] == 0) { d->base_child_slot[b] = d->n_base_children++; }
+  if (d->n_base_children > 4) return false;
+  return true;
+}
+
+bool build_cost_model(const H1Model& m, CostModel* c) {
+  std::memset(c, 0, sizeof(*c));
+  for (int b = 0; b < NB; ++b) {
+    if (b > 0 && (m.parent[b] < 0 || m.parent[b] >= b)) return false;
+    for (int i = 0; i < 3; ++i) { c->pos[b][i] = m.pos[b][i]; c->ipos[b][i] = m.ipos[b][i]; }
+    for (int i = 0; i < 9; ++i) c->rfix[b][i] = m.rfix[b][i];
+    c->wmass[b] = m.mass[b] / m.total_mass;
+  }
+  tree_common(m, c->parent, c->axis, c->has_rfix, c->depth, c->anc_body, c->chain_end);
+  for (int f = 0; f < H1_NFOOT; ++f) c->foot_body[f] = m.foot_body[f];
+  return true;
+}
+
+}  // namespace h1

@@ -2,6 +2,7 @@
 import ctypes as C
 
 NB, NQ, NV, NX, NU, NFOOT, NCP, NALPHA = 20, 26, 25, 51, 19, 2, 4, 8
+LIN_ANALYTIC, LIN_FD = 0, 1
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
 
@@ -33,7 +34,8 @@ class H1SolverOptions(C.Structure):
     _fields_ = [
         ("max_iterations", C.c_int), ("tolerance", C.c_double), ("reg_init", C.c_double),
         ("reg_min", C.c_double), ("reg_max", C.c_double), ("accept_margin", C.c_double),
-        ("fd_eps", C.c_double), ("divergence_cost", C.c_double), ("alphas", C.c_double * NALPHA),
+        ("fd_eps", C.c_double), ("divergence_cost", C.c_double), ("linearization", C.c_int),
+        ("alphas", C.c_double * NALPHA),
     ]
 
 

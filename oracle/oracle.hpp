@@ -16,6 +16,7 @@ void dyn_body_pos(const H1Model& md, const double* x, int body, double* p);
 void dyn_bias(const H1Model& md, const double* x, double* bias);
 void dyn_step(const H1Model& md, const double* x, const double* u, double* xn);
 void dyn_linearize_fd(const H1Model& md, const double* x, const double* u, double eps, double* A, double* B);
+void dyn_linearize_ad(const H1Model& md, const double* x, const double* u, double* A, double* B);
 
 // ---- cost terms (oracle_cost.cpp) ----
 // All gradients/Hessians are w.r.t. the Pinocchio-ordered state x~ (quaternion x,y,z,w at 3..6) and are

@@ -84,6 +84,36 @@ template <int NV> inline D2<NV> operator*(const D2<NV>& a, double b) { return a 
 template <int NV> inline D2<NV> operator*(double b, const D2<NV>& a) { return a * D2<NV>(b); }
 template <int NV> inline D2<NV> operator/(const D2<NV>& a, double b) { return a * D2<NV>(1.0 / b); }
 
+// ---- first-order forward-mode dual with N tangent directions (exact Jacobian of f_D in one pass) ----
+template <int N> struct D1 {
+  double v;
+  double d[N];
+  D1() : v(0) { for (int i = 0; i < N; ++i) d[i] = 0; }
+  D1(double x) : v(x) { for (int i = 0; i < N; ++i) d[i] = 0; }
+  static D1 var(double x, int i) { D1 r(x); r.d[i] = 1.0; return r; }
+};
+template <int N> inline D1<N> operator+(const D1<N>& a, const D1<N>& b) { D1<N> r; r.v = a.v + b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] + b.d[i]; return r; }
+template <int N> inline D1<N> operator-(const D1<N>& a, const D1<N>& b) { D1<N> r; r.v = a.v - b.v; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] - b.d[i]; return r; }
+template <int N> inline D1<N> operator-(const D1<N>& a) { D1<N> r; r.v = -a.v; for (int i = 0; i < N; ++i) r.d[i] = -a.d[i]; return r; }
+template <int N> inline D1<N> operator*(const D1<N>& a, const D1<N>& b) { D1<N> r; r.v = a.v * b.v; for (int i = 0; i < N; ++i) r.d[i] = a.v * b.d[i] + a.d[i] * b.v; return r; }
+template <int N> inline D1<N> operator/(const D1<N>& a, const D1<N>& b) { D1<N> r; r.v = a.v / b.v; for (int i = 0; i < N; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) / b.v; return r; }
+template <int N> inline D1<N> operator+(const D1<N>& a, double b) { D1<N> r = a; r.v += b; return r; }
+template <int N> inline D1<N> operator+(double b, const D1<N>& a) { D1<N> r = a; r.v += b; return r; }
+template <int N> inline D1<N> operator-(const D1<N>& a, double b) { D1<N> r = a; r.v -= b; return r; }
+template <int N> inline D1<N> operator-(double b, const D1<N>& a) { return D1<N>(b) - a; }
+template <int N> inline D1<N> operator*(const D1<N>& a, double b) { D1<N> r; r.v = a.v * b; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * b; return r; }
+template <int N> inline D1<N> operator*(double b, const D1<N>& a) { return a * b; }
+template <int N> inline D1<N> operator/(const D1<N>& a, double b) { D1<N> r; r.v = a.v / b; for (int i = 0; i < N; ++i) r.d[i] = a.d[i] / b; return r; }
+template <int N> inline D1<N>& operator+=(D1<N>& a, const D1<N>& b) { a = a + b; return a; }
+template <int N> inline D1<N>& operator-=(D1<N>& a, const D1<N>& b) { a = a - b; return a; }
+template <int N> inline bool operator<(const D1<N>& a, double b) { return a.v < b; }
+template <int N> inline bool operator>(const D1<N>& a, double b) { return a.v > b; }
+template <int N> inline D1<N> sqrt(const D1<N>& a) { D1<N> r; r.v = std::sqrt(a.v); for (int i = 0; i < N; ++i) r.d[i] = 0.5 * a.d[i] / r.v; return r; }
+template <int N> inline D1<N> sin(const D1<N>& a) { D1<N> r; double c = std::cos(a.v); r.v = std::sin(a.v); for (int i = 0; i < N; ++i) r.d[i] = c * a.d[i]; return r; }
+template <int N> inline D1<N> cos(const D1<N>& a) { D1<N> r; double s = std::sin(a.v); r.v = std::cos(a.v); for (int i = 0; i < N; ++i) r.d[i] = -s * a.d[i]; return r; }
+inline double value_of(double x) { return x; }
+template <int N> inline double value_of(const D1<N>& x) { return x.v; }
+
 inline double sqrt(double x) { return std::sqrt(x); }
 inline double sin(double x) { return std::sin(x); }
 inline double cos(double x) { return std::cos(x); }

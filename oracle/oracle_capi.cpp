@@ -24,7 +24,7 @@ const H1Model* orc_default_cost_model(void) { return &H1_COST_MODEL; }
 
 void orc_default_options(H1SolverOptions* o) {
   o->max_iterations = 10; o->tolerance = 1e-4; o->reg_init = 1e-6; o->reg_min = 1e-6; o->reg_max = 1e-3;
-  o->accept_margin = 1e-6; o->fd_eps = 1e-5; o->divergence_cost = 1e6;
+  o->accept_margin = 1e-6; o->fd_eps = 1e-5; o->divergence_cost = 1e6; o->linearization = H1ILQR_LIN_ANALYTIC;
   const double a[H1ILQR_NALPHA] = {1.0, 0.8, 0.6, 0.4, 0.2, 0.1, 0.05, 0.01};
   std::memcpy(o->alphas, a, sizeof(a));
 }
@@ -35,6 +35,9 @@ void orc_dyn_step(const H1Model* m, int n, const double* x, const double* u, dou
 }
 void orc_dyn_linearize(const H1Model* m, const double* x, const double* u, double eps, double* A, double* B) {
   dyn_linearize_fd(*pick(m, H1_DYNAMICS_MODEL), x, u, eps, A, B);
+}
+void orc_dyn_linearize_ad(const H1Model* m, const double* x, const double* u, double* A, double* B) {
+  dyn_linearize_ad(*pick(m, H1_DYNAMICS_MODEL), x, u, A, B);
 }
 void orc_dyn_com(const H1Model* m, const double* x, double* com) { dyn_com(*pick(m, H1_DYNAMICS_MODEL), x, com); }
 void orc_dyn_bias(const H1Model* m, const double* x, double* bias) { dyn_bias(*pick(m, H1_DYNAMICS_MODEL), x, bias); }

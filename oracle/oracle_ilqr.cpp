@@ -36,8 +36,12 @@ void rollout_nominal(Solver& s, const double* x0) {
 }
 
 void linearize(Solver& s) {
-  for (int t = 0; t < s.N; ++t)
-    dyn_linearize_fd(s.p->dyn, &s.xbar[t * NX], &s.ubar[t * NU], s.p->opt.fd_eps, &s.A[t * NX * NX], &s.B[t * NX * NU]);
+  for (int t = 0; t < s.N; ++t) {
+    if (s.p->opt.linearization == H1ILQR_LIN_FD)
+      dyn_linearize_fd(s.p->dyn, &s.xbar[t * NX], &s.ubar[t * NU], s.p->opt.fd_eps, &s.A[t * NX * NX], &s.B[t * NX * NU]);
+    else
+      dyn_linearize_ad(s.p->dyn, &s.xbar[t * NX], &s.ubar[t * NU], &s.A[t * NX * NX], &s.B[t * NX * NU]);
+  }
 }
 
 static void term(const Problem& p, int t, int ee, const double* x, const double* target, double w, double* g, double* H) {

@@ -82,6 +82,15 @@ def dyn_linearize(x, u, eps=1e-5, model=None):
     return A, B
 
 
+def dyn_linearize_ad(x, u, model=None):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    A = np.empty((NX, NX), order="F")
+    B = np.empty((NX, NU), order="F")
+    lib().orc_dyn_linearize_ad(_mp(model), dptr(x), dptr(u), A.ctypes.data_as(c_double_p), B.ctypes.data_as(c_double_p))
+    return A, B
+
+
 def dyn_com(x, model=None):
     x = np.ascontiguousarray(x, dtype=np.float64)
     out = np.empty(3)

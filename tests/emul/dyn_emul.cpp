@@ -1,0 +1,33 @@
+// Lane-emulation build of the warp-cooperative f_D (mpc-ilqr-mujoco_b200/csrc/h1_dyn.cuh) for the CPU test
+// suite: the phase functions are compiled as plain C++ and the 32 lanes of a phase run one after another.
+// This checks the kernel's index tables / sparse factorisation logic without a GPU; it is not a product path.
+#include "../../mpc-ilqr-mujoco_b200/csrc/h1_dyn.cuh"
+#include "../../mpc-ilqr-mujoco_b200/csrc/model_tables.h"
+
+extern "C" int emul_dyn_step(int n, const double* x, const double* u, double* xn, double* com) {
+  static h1::DynModel md;
+  static bool init = false;
+  if (!init) { if (!h1::build_dyn_model(*h1_default_dynamics_model(), &md)) return -1; init = true; }
+  static h1::DynWarp w;
+  for (int i = 0; i < n; ++i) {
+    h1::dyn_step_warp(md, w, x + i * h1::NX, u + i * h1::NU, xn + i * h1::NX);
+    if (com) for (int k = 0; k < 3; ++k) com[3 * i + k] = w.com[k];
+  }
+  return 0;
+}
+
+// exact linearization through the tangent phases (csrc/h1_dyn.cuh), column-major A[51x51], B[51x19]
+extern "C" int emul_dyn_linearize_analytic(const double* x, const double* u, double* A, double* B) {
+  static h1::DynModel md;
+  static bool init = false;
+  if (!init) { if (!h1::build_dyn_model(*h1_default_dynamics_model(), &md)) return -1; init = true; }
+  static h1::DynWarp w;
+  static h1::DynWarpT<h1::Dual> wd;
+  static h1::PrimalFactor pf;
+  h1::dyn_primal_factor_warp(md, w, x, u, nullptr, pf);
+  for (int e = 0; e < h1::NX + h1::NU; ++e) {
+    h1::dyn_tangent_assemble_warp(md, wd, x, u, e);
+    h1::dyn_tangent_solve_warp(md, wd, pf, e < h1::NX ? A + e * h1::NX : B + (e - h1::NX) * h1::NX);
+  }
+  return 0;
+}

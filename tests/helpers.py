@@ -40,10 +40,12 @@ def grav_comp_guess(x0):
     return u
 
 
-def make_oracle(tag="standing", N=25, t0=0, batch=1, cfg=None):
+def make_oracle(tag="standing", N=25, t0=0, batch=1, cfg=None, linearization=0):
     cfg = cfg or Config()
     w = cfg.build_weights()
-    s = po.OracleSolver(w, N, batch=batch)
+    opt = po.default_options()
+    opt.linearization = linearization  # 0 analytic (default), 1 forward differences (the reference's method)
+    s = po.OracleSolver(w, N, batch=batch, options=opt)
     refs = reference_set(tag)
     win = refs.window(t0, N)
     s.set_reference_window(*win)
