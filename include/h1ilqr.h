@@ -151,6 +151,18 @@ int h1ilqr_set_regularization(H1Ilqr* h, const double* lambda, int shared);
 /* per-iteration trace of the last solve: cost_trace [batch][max_iterations], alpha_trace [batch][max_iterations][2] */
 int h1ilqr_get_solve_trace(H1Ilqr* h, double* cost_trace, int* alpha_trace);
 
+/* ---- device-resident stepping (measurement + closed-loop batches without host round trips) ----
+ * h1ilqr_upload_inputs stages x_measured / u_init once; h1ilqr_run_resident_steps then enqueues `steps` complete
+ * MPC steps (initialize + solve + first control, exactly h1ilqr_mpc_step's kernel sequence) on the handle's
+ * stream with NO host<->device copies inside, brackets them with CUDA events on that stream and returns the
+ * elapsed milliseconds. cold_each_step != 0 forgets the previous solution and resets lambda before every step
+ * so that every step is the same cold-start solve. */
+int h1ilqr_upload_inputs(H1Ilqr* h, const double* x_measured, const double* u_init, int u_init_shared);
+int h1ilqr_run_resident_steps(H1Ilqr* h, int steps, int cold_each_step, double* elapsed_ms);
+/* sustained fp64 FMA throughput of the device (TFLOP/s), measured with a register-resident DFMA kernel: the
+ * FP64 roofline denominator (MEASURED_PEAKS.json carries none). */
+int h1ilqr_measure_fp64_peak(H1Ilqr* h, double* tflops);
+
 /* ---- timing of the last h1ilqr_solve, CUDA events on the handle's stream, milliseconds ---- */
 typedef struct H1StageTimes {
   double total_ms;

@@ -332,6 +332,97 @@ int h1ilqr_solve(H1Ilqr* h, const double* x0, double* cost_out, int* iters_out, 
   return rc;
 }
 
+static void enqueue_mpc_tail(H1Ilqr* h) {
+  const size_t B = h->B, N = h->N;
+  k_first_control<<<h->B, 32, 0, h->stream>>>(h->B, h->N, h->x0, h->xbar, h->ubar, h->K, h->u_apply);
+  LAUNCHED();
+  cudaMemcpyAsync(h->prev_xbar, h->xbar, B * (N + 1) * NX * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+  cudaMemcpyAsync(h->prev_ubar, h->ubar, B * N * NU * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+  k_fill_int<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->B, h->has_prev, 1);
+  LAUNCHED();
+}
+
+int h1ilqr_upload_inputs(H1Ilqr* h, const double* x_measured, const double* u_init, int u_init_shared) {
+  GUARD(h);
+  if (!x_measured) return set_err(H1ILQR_EARG, "null x_measured");
+  H2D(h->x0, x_measured, (size_t)h->B * NX * sizeof(double));
+  if (u_init) {
+    if (u_init_shared) {  // replicate so that the resident steps can always read per-instance guesses
+      std::vector<double> rep((size_t)h->B * NU);
+      for (int i = 0; i < h->B; ++i) std::memcpy(&rep[(size_t)i * NU], u_init, NU * sizeof(double));
+      H2D(h->u_init, rep.data(), rep.size() * sizeof(double));
+      SYNC();
+    } else H2D(h->u_init, u_init, (size_t)h->B * NU * sizeof(double));
+  } else CU(cudaMemsetAsync(h->u_init, 0, (size_t)h->B * NU * sizeof(double), h->stream));
+  SYNC();
+  return 0;
+}
+
+int h1ilqr_run_resident_steps(H1Ilqr* h, int steps, int cold_each_step, double* elapsed_ms) {
+  GUARD(h);
+  if (steps < 1) return set_err(H1ILQR_EARG, "steps < 1");
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  const int l0 = h->launches;
+  const bool timing = h->timing;
+  h->timing = false;  // stage timing would insert host syncs
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaEventRecord(e0, h->stream));
+  for (int s = 0; s < steps; ++s) {
+    if (cold_each_step) {
+      k_fill_int<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->B, h->has_prev, 0);
+      k_fill_double<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->B, h->lambda, h->opt.reg_init);
+      h->launches += 2;
+    }
+    enqueue_initialize(h, nullptr, 0);
+    enqueue_solve(h);
+    enqueue_mpc_tail(h);
+  }
+  CU(cudaEventRecord(e1, h->stream));
+  CU(cudaEventSynchronize(e1));
+  CU(cudaGetLastError());
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  h->timing = timing;
+  h->times.launches = h->launches - l0;
+  if (elapsed_ms) *elapsed_ms = ms;
+  return 0;
+}
+
+__global__ void k_fp64_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) out[0] = a0;
+}
+int h1ilqr_measure_fp64_peak(H1Ilqr* h, double* tflops) {
+  GUARD(h);
+  if (!tflops) return set_err(H1ILQR_EARG, "null tflops");
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, h->device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CU(cudaEventRecord(e0, h->stream));
+    k_fp64_peak<<<blocks, threads, 0, h->stream>>>(h->scratch, iters);
+    CU(cudaEventRecord(e1, h->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8.0 * (double)iters * threads * blocks;
+    if (rep > 0) best = fmax(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *tflops = best;
+  return 0;
+}
+
 int h1ilqr_mpc_reset(H1Ilqr* h) {
   GUARD(h);
   k_fill_int<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->B, h->has_prev, 0);
@@ -344,7 +435,7 @@ int h1ilqr_mpc_step(H1Ilqr* h, const double* x_measured, const double* u_init, i
                     double* cost_out) {
   GUARD(h);
   if (!x_measured || !u_apply) return set_err(H1ILQR_EARG, "null x_measured / u_apply");
-  const size_t B = h->B, N = h->N;
+  const size_t B = h->B;
   // pinned staging: x in, u_apply + cost out
   double* pin_x = (double*)h->pin; double* pin_u = pin_x + B * NX; double* pin_c = pin_u + B * NU;
   double* pin_ui = pin_c + B;
@@ -359,11 +450,7 @@ int h1ilqr_mpc_step(H1Ilqr* h, const double* x_measured, const double* u_init, i
   std::memset(&h->times, 0, sizeof(h->times));
   enqueue_initialize(h, nullptr, u_init ? u_init_shared : 1);
   enqueue_solve(h);
-  k_first_control<<<h->B, 32, 0, h->stream>>>(h->B, h->N, h->x0, h->xbar, h->ubar, h->K, h->u_apply);
-  LAUNCHED();
-  CU(cudaMemcpyAsync(h->prev_xbar, h->xbar, B * (N + 1) * NX * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  CU(cudaMemcpyAsync(h->prev_ubar, h->ubar, B * N * NU * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  k_fill_int<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->B, h->has_prev, 1);
+  enqueue_mpc_tail(h);
   D2H(pin_u, h->u_apply, B * NU * sizeof(double));
   D2H(pin_c, h->cost, B * sizeof(double));
   SYNC();

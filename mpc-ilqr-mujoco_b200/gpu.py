@@ -23,7 +23,7 @@ EXPORTS = [
     "h1ilqr_reference_kinematics", "h1ilqr_set_trajectory", "h1ilqr_get_trajectory", "h1ilqr_get_gains",
     "h1ilqr_set_gains", "h1ilqr_get_linearization", "h1ilqr_set_linearization", "h1ilqr_get_cost_quadratics",
     "h1ilqr_set_cost_quadratics", "h1ilqr_get_regularization", "h1ilqr_set_regularization", "h1ilqr_get_solve_trace",
-    "h1ilqr_enable_stage_timing", "h1ilqr_get_stage_times", "h1ilqr_stream", "h1_default_dynamics_model",
+    "h1ilqr_upload_inputs", "h1ilqr_run_resident_steps", "h1ilqr_measure_fp64_peak", "h1ilqr_enable_stage_timing", "h1ilqr_get_stage_times", "h1ilqr_stream", "h1_default_dynamics_model",
     "h1_default_cost_model",
 ]
 
@@ -250,6 +250,29 @@ class H1IlqrBatch:
         at = np.empty((self.B, self.opt.max_iterations, 2), dtype=np.int32)
         _check(lib().h1ilqr_get_solve_trace(self._h, dptr(ct), iptr(at)))
         return ct, at
+
+    def upload_inputs(self, x_measured, u_init=None):
+        x = _f(x_measured).reshape(self.B, NX)
+        shared = 1
+        if u_init is not None:
+            u_init = _f(u_init)
+            shared = int(u_init.size == NU)
+        _check(lib().h1ilqr_upload_inputs(self._h, dptr(x), dptr(u_init), C.c_int(shared)))
+
+    def run_resident_steps(self, steps, cold_each_step=True):
+        """`steps` MPC steps with inputs already on the device; returns CUDA-event milliseconds on the handle's stream."""
+        ms = C.c_double()
+        _check(lib().h1ilqr_run_resident_steps(self._h, C.c_int(steps), C.c_int(int(cold_each_step)), C.byref(ms)))
+        return ms.value
+
+    def measure_fp64_peak(self):
+        t = C.c_double()
+        _check(lib().h1ilqr_measure_fp64_peak(self._h, C.byref(t)))
+        return t.value
+
+    def get_costs(self):
+        """Final cost / iterations / status of the last solve (device -> host)."""
+        return self.solve_trace()
 
     def enable_stage_timing(self, flag=True):
         _check(lib().h1ilqr_enable_stage_timing(self._h, C.c_int(int(flag))))

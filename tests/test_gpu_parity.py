@@ -275,3 +275,64 @@ def test_horizon_sweep(gpu, oracle):
             sg.rollout_nominal(x0[None]); sg.linearize(); sg.cost_quadratics(); sg.backward_pass()
             ok, c, a = sg.line_search(x0[None])
             assert a[0] == a_o and abs(c[0] - c_o) / abs(c_o) < 1e-6
+
+
+def test_against_committed_golden_vectors(gpu):
+    """GPU vs tests/golden/oracle_golden.npz (generated by tools/make_golden.py from the oracle in the build
+    container) — fixed targets that do not depend on the oracle being rebuilt on the GPU box."""
+    import os
+    from helpers import ROOT
+    g = np.load(os.path.join(ROOT, "tests", "golden", "oracle_golden.npz"))
+    w = Config().build_weights()
+    s = gpu.H1IlqrBatch(w, N=25, batch=1)
+    assert np.abs(s.dynamics_step(g["dyn_x"], g["dyn_u"]) - g["dyn_xnext"]).max() < 1e-11
+    assert np.abs(s.bias_forces(g["dyn_x"]) - g["dyn_bias"]).max() < 1e-10
+    com, _ = s.reference_kinematics(g["dyn_x"])
+    assert np.abs(com - g["dyn_com"]).max() < 1e-13
+    for tag in ("standing", "walking"):
+        refs = reference_set(tag)
+        s.set_reference_window(*refs.window(0, 25), shared=True)
+        x0 = standing_state(); ug = g[f"{tag}_u_guess"]
+        s.mpc_reset(); s.initialize(x0[None], None, ug)
+        s.rollout_nominal(x0[None]); s.linearize(); s.cost_quadratics(); s.backward_pass()
+        A, B = s.get_linearization(); lx, lu, lxx, luu = s.get_cost_quadratics(); K, kff = s.get_gains()
+        for t in range(25):
+            assert rel(A[0, t], g[f"{tag}_iter0_A"][t]) < 1e-9 and rel(B[0, t], g[f"{tag}_iter0_B"][t]) < 1e-9
+            assert rel(lxx[0, t], g[f"{tag}_iter0_lxx"][t]) < 1e-9 and rel(lx[0, t], g[f"{tag}_iter0_lx"][t]) < 1e-9
+        assert rel(K[0], g[f"{tag}_iter0_K"]) < 1e-8 and rel(kff[0], g[f"{tag}_iter0_kff"]) < 1e-8
+        s.mpc_reset(); s.initialize(x0[None], None, ug)
+        c, it, st = s.solve(x0[None])
+        ct, at = s.solve_trace()
+        assert (at[0] == g[f"{tag}_solve_alpha"]).all()
+        assert rel(ct[0], g[f"{tag}_solve_trace"]) < 1e-6
+        xg, ugp = s.get_trajectory()
+        assert rel(xg[0], g[f"{tag}_solve_xbar"]) < 1e-6 and rel(ugp[0], g[f"{tag}_solve_ubar"]) < 1e-6
+
+
+def test_full_size_batch_properties(gpu):
+    """BASELINE-size batch (1024 standing instances, config 3): size-independent properties — every instance's
+    accepted costs are non-increasing, every trajectory is dynamically consistent (a fresh rollout of the
+    returned controls reproduces the returned states bit for bit), identical instances give identical
+    results, and nothing is non-finite."""
+    w = Config().build_weights()
+    B = 1024
+    s = gpu.H1IlqrBatch(w, N=25, batch=B)
+    refs = reference_set("standing")
+    s.set_reference_window(*refs.window(0, 25), shared=True)
+    jr = np.array(gpu.default_dynamics_model().jnt_range)
+    x0 = perturbed_states(standing_state(), B, seed=0, jnt_range=jr)
+    x0[1] = x0[0]  # two identical instances
+    ug = grav_comp_guess(standing_state())
+    s.initialize(x0, None, ug)
+    cost, iters, status = s.solve(x0)
+    assert (status == 0).all() and np.isfinite(cost).all() and (iters >= 1).all() and (iters <= 10).all()
+    ct, at = s.solve_trace()
+    for i in range(0, B, 37):
+        c = ct[i][:iters[i]]
+        assert (np.diff(c) <= 1e-9 * np.abs(c[:-1])).all()
+    xg, ugp = s.get_trajectory()
+    assert (xg[0] == xg[1]).all() and cost[0] == cost[1]
+    s.rollout_nominal(x0)
+    xr, _ = s.get_trajectory()
+    assert (xr == xg).all()
+    assert np.abs(np.linalg.norm(xg[:, 1:, 3:7], axis=2) - 1).max() < 1e-12
