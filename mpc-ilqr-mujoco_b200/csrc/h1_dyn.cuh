@@ -49,6 +49,8 @@ H1_HD bool operator<(const Dual& a, double b) { return a.v < b; }
 H1_HD bool operator>(const Dual& a, double b) { return a.v > b; }
 H1_HD double sqrt_t(double a) { return ::sqrt(a); }
 H1_HD Dual sqrt_t(const Dual& a) { double r = ::sqrt(a.v); return Dual(r, 0.5 * a.d / r); }
+H1_HD double tangent_of(double) { return 0.0; }
+H1_HD double tangent_of(const Dual& a) { return a.d; }
 H1_HD double val(double a) { return a; }
 H1_HD double val(const Dual& a) { return a.v; }
 H1_HD void sincos_t(double a, double* s, double* c) {
@@ -148,8 +150,8 @@ template <class T> H1_DEV void quat_to_mat(const T* q, T* R) {
 
 // ---- phase: stage inputs. `seed` selects one input entry (0..50 state, 51..69 control, -1 none): it is
 //      shifted by eps when T = double (finite-difference column) or carries the tangent when T = Dual. ----
-template <class T>
-H1_DEV void ph_load(int lane, const DynModel& md, DynWarpT<T>& w, const double* x, const double* u, int seed,
+template <class T, class W>
+H1_DEV void ph_load(int lane, const DynModel& md, W& w, const double* x, const double* u, int seed,
                     double eps) {
   if (lane < NQ) w.q[lane] = seeded<T>(x[lane], seed == lane, eps);
   if (lane < NV) {
@@ -381,7 +383,7 @@ H1_DEV void ph_back(int lane, int lev, const DynModel& md, DynWarp& w) {
 // ---- phase: integrate and store x_next (T = double) or its tangent (T = Dual, stores .d) ----
 H1_HD void store_out(double* p, double a) { *p = a; }
 H1_HD void store_out(double* p, const Dual& a) { *p = a.d; }
-template <class T> H1_DEV void ph_integrate(int lane, const DynModel& md, DynWarpT<T>& w, double* xn) {
+template <class T, class W> H1_DEV void ph_integrate(int lane, const DynModel& md, W& w, double* xn) {
   if (lane >= NV) return;
   const double h = md.h;
   const T vn = w.v[lane] + h * w.acc[lane];
@@ -426,19 +428,19 @@ template <class T> H1_DEV void ph_integrate(int lane, const DynModel& md, DynWar
 H1_DEV void dyn_step_warp(const DynModel& md, DynWarp& w, const double* x, const double* u, double* xn,
                           int seed = -1, double eps = 0.0) {
   H1_LANES_DECL(double)
-  H1_PHASE(ph_load<double>(lane, md, w, x, u, seed, eps))
+  H1_PHASE((ph_load<double, DynWarp>(lane, md, w, x, u, seed, eps)))
   H1_PHASE(ph_walk<double>(lane, md, w, H1_LR))
   H1_PHASE(ph_sums<double>(lane, md, w, H1_LR))
   H1_PHASE(ph_rows<double>(lane, md, w, H1_LR))
   for (int k = NV - 1; k >= 1; --k) H1_PHASE(ph_ltdl(lane, k, md, w))
   for (int lev = 0; lev < MAXSLOT; ++lev) H1_PHASE(ph_back(lane, lev, md, w))
-  H1_PHASE(ph_integrate<double>(lane, md, w, xn))
+  H1_PHASE((ph_integrate<double, DynWarp>(lane, md, w, xn)))
 }
 
 // Assembly only: fills w.com, w.footr/footR, w.M and w.rhs (= tau - bias - damping*v + contact).
 H1_DEV void dyn_assemble_warp(const DynModel& md, DynWarp& w, const double* x, const double* u) {
   H1_LANES_DECL(double)
-  H1_PHASE(ph_load<double>(lane, md, w, x, u, -1, 0.0))
+  H1_PHASE((ph_load<double, DynWarp>(lane, md, w, x, u, -1, 0.0)))
   H1_PHASE(ph_walk<double>(lane, md, w, H1_LR))
   H1_PHASE(ph_sums<double>(lane, md, w, H1_LR))
   H1_PHASE(ph_rows<double>(lane, md, w, H1_LR))
@@ -494,21 +496,21 @@ H1_DEV void ph_tan_back(int lane, int lev, const DynModel& md, DynWarpT<Dual>& w
 H1_DEV void dyn_primal_factor_warp(const DynModel& md, DynWarp& w, const double* x, const double* u, double* xn,
                                    PrimalFactor& pf) {
   H1_LANES_DECL(double)
-  H1_PHASE(ph_load<double>(lane, md, w, x, u, -1, 0.0))
+  H1_PHASE((ph_load<double, DynWarp>(lane, md, w, x, u, -1, 0.0)))
   H1_PHASE(ph_walk<double>(lane, md, w, H1_LR))
   H1_PHASE(ph_sums<double>(lane, md, w, H1_LR))
   H1_PHASE(ph_rows<double>(lane, md, w, H1_LR))
   for (int k = NV - 1; k >= 1; --k) H1_PHASE(ph_ltdl(lane, k, md, w))
   for (int lev = 0; lev < MAXSLOT; ++lev) H1_PHASE(ph_back(lane, lev, md, w))
   H1_PHASE(ph_save_factor(lane, md, w, pf))
-  if (xn) H1_PHASE(ph_integrate<double>(lane, md, w, xn))
+  if (xn) H1_PHASE((ph_integrate<double, DynWarp>(lane, md, w, xn)))
 }
 
 // assembly of one tangent direction (no dependence on the primal factor)
 H1_DEV void dyn_tangent_assemble_warp(const DynModel& md, DynWarpT<Dual>& w, const double* x, const double* u,
                                       int seed) {
   H1_LANES_DECL(Dual)
-  H1_PHASE(ph_load<Dual>(lane, md, w, x, u, seed, 0.0))
+  H1_PHASE((ph_load<Dual, DynWarpT<Dual> >(lane, md, w, x, u, seed, 0.0)))
   H1_PHASE(ph_walk<Dual>(lane, md, w, H1_LR))
   H1_PHASE(ph_sums<Dual>(lane, md, w, H1_LR))
   H1_PHASE(ph_rows<Dual>(lane, md, w, H1_LR))
@@ -521,7 +523,232 @@ H1_DEV void dyn_tangent_solve_warp(const DynModel& md, DynWarpT<Dual>& w, const 
   H1_PHASE(ph_tan_rhs(lane, md, w, pf))
   for (int lev = MAXSLOT - 1; lev >= 0; --lev) H1_PHASE(ph_tan_fwd(lane, lev, md, w, pf))
   for (int lev = 0; lev < MAXSLOT; ++lev) H1_PHASE(ph_tan_back(lane, lev, md, w, pf))
-  H1_PHASE(ph_integrate<Dual>(lane, md, w, out_col))
+  H1_PHASE((ph_integrate<Dual, DynWarpT<Dual> >(lane, md, w, out_col)))
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Inverse-dynamics form of the tangent right-hand side. With a (the primal acceleration) held fixed,
+//     g(q, v, u; a) = Mhat(q) a - rhs(q, v, u) = ID(q, v, a) + (armature + h D) a + D v - tau(u) - sum_i J_i^T F_i ,
+//     F_i = phi_i(q, v) - W_i(q) (J_i a)            (linearly-implicit contact force at sole point i)
+// so that  t = rhsdot - Mhatdot a = -d g / d(direction): ONE recursive Newton-Euler pass on dual numbers per
+// direction, no mass-matrix rows, no contact Jacobian table. Scratch per warp drops to ~8.7 KB.
+// ------------------------------------------------------------------------------------------------------
+template <class T> struct TanWarpT {
+  T q[NQ], v[NV], tau[NV];
+  T sn[NB], cs[NB];
+  T S[NV][6];
+  T body[NB][6];             // body wrench about the base origin [n; l]
+  T part[4][6];
+  T footR[H1_NFOOT][9], footr[H1_NFOOT][3], footV[H1_NFOOT][6], footVa[H1_NFOOT][6];
+  T cw[NCPT][6];             // contact wrench of each sole point about the base origin
+  T acc[NV];
+  double tvec[NV];
+};
+
+template <class T> struct TanLaneT {
+  T R[9], r[3], V[6], Va[6], Ab[6], S[6];
+};
+
+template <class T> H1_DEV void ph_id_walk(int lane, const DynModel& md, TanWarpT<T>& w, TanLaneT<T>& L,
+                                          const double* a) {
+  if (lane >= NV) return;
+  const int b = lane < 6 ? 0 : lane - 5;
+  T qn[4];
+  quat_normalize(&w.q[3], qn);
+  quat_to_mat(qn, L.R);
+  L.r[0] = L.r[1] = L.r[2] = T(0.0);
+  const T wb[3] = {w.v[3], w.v[4], w.v[5]};
+  for (int i = 0; i < 3; ++i) {
+    L.V[i] = L.R[3 * i] * wb[0] + L.R[3 * i + 1] * wb[1] + L.R[3 * i + 2] * wb[2];
+    L.Va[i] = L.R[3 * i] * a[3] + L.R[3 * i + 1] * a[4] + L.R[3 * i + 2] * a[5];
+    L.V[3 + i] = w.v[i];
+    L.Va[3 + i] = T(a[i]);
+  }
+  {
+    T vxw[3];
+    cross3(L.V + 3, L.V, vxw);
+    L.Ab[0] = L.Ab[1] = L.Ab[2] = T(0.0);
+    L.Ab[3] = vxw[0] - md.gravity[0]; L.Ab[4] = vxw[1] - md.gravity[1]; L.Ab[5] = vxw[2] - md.gravity[2];
+  }
+  for (int i = 0; i < 6; ++i) L.S[i] = T(0.0);
+  if (lane < 3) { L.S[3] = T(lane == 0 ? 1.0 : 0.0); L.S[4] = T(lane == 1 ? 1.0 : 0.0); L.S[5] = T(lane == 2 ? 1.0 : 0.0); }
+  else if (lane < 6) { col_of(L.R, lane - 3, L.S); }
+  const int dep = md.depth[b];
+#pragma unroll 1
+  for (int d = 1; d <= 5; ++d) {
+    if (d <= dep) {
+      const int an = md.anc_body[b][d];
+      const double* p = md.pos[an];
+      L.r[0] += L.R[0] * p[0] + L.R[1] * p[1] + L.R[2] * p[2];
+      L.r[1] += L.R[3] * p[0] + L.R[4] * p[1] + L.R[5] * p[2];
+      L.r[2] += L.R[6] * p[0] + L.R[7] * p[1] + L.R[8] * p[2];
+      if (md.has_rfix[an]) {
+        const double* F = md.rfix[an];
+        T Tm[9];
+        for (int i = 0; i < 3; ++i)
+          for (int k = 0; k < 3; ++k)
+            Tm[3 * i + k] = L.R[3 * i] * F[k] + L.R[3 * i + 1] * F[3 + k] + L.R[3 * i + 2] * F[6 + k];
+        for (int i = 0; i < 9; ++i) L.R[i] = Tm[i];
+      }
+      const int ax = md.axis[an];
+      rot_right(L.R, ax, w.sn[an], w.cs[an]);
+      col_of(L.R, ax, L.S);
+      cross3(L.r, L.S, L.S + 3);
+      const T vj = w.v[5 + an];
+      const double aj = a[5 + an];
+      for (int i = 0; i < 6; ++i) { L.V[i] += L.S[i] * vj; L.Va[i] += L.S[i] * aj; }
+      T c1[3], c2[3], c3[3];
+      cross3(L.V, L.S, c1); cross3(L.V, L.S + 3, c2); cross3(L.V + 3, L.S, c3);
+      L.Ab[0] += c1[0] * vj; L.Ab[1] += c1[1] * vj; L.Ab[2] += c1[2] * vj;
+      L.Ab[3] += (c2[0] + c3[0]) * vj; L.Ab[4] += (c2[1] + c3[1]) * vj; L.Ab[5] += (c2[2] + c3[2]) * vj;
+    }
+  }
+  for (int i = 0; i < 6; ++i) w.S[lane][i] = L.S[i];
+  if (lane < 5) return;
+  for (int f = 0; f < H1_NFOOT; ++f)
+    if (b == md.foot_body[f]) {
+      for (int i = 0; i < 9; ++i) w.footR[f][i] = L.R[i];
+      for (int i = 0; i < 3; ++i) w.footr[f][i] = L.r[i];
+      for (int i = 0; i < 6; ++i) { w.footV[f][i] = L.V[i]; w.footVa[f][i] = L.Va[i]; }
+    }
+  T I[10];
+  {
+    const double* ip = md.ipos[b];
+    T c[3] = {L.r[0] + L.R[0] * ip[0] + L.R[1] * ip[1] + L.R[2] * ip[2],
+              L.r[1] + L.R[3] * ip[0] + L.R[4] * ip[1] + L.R[5] * ip[2],
+              L.r[2] + L.R[6] * ip[0] + L.R[7] * ip[1] + L.R[8] * ip[2]};
+    const double* J = md.inertia[b];
+    T Tm[9];
+    for (int i = 0; i < 3; ++i) {
+      Tm[3 * i + 0] = L.R[3 * i] * J[0] + L.R[3 * i + 1] * J[3] + L.R[3 * i + 2] * J[4];
+      Tm[3 * i + 1] = L.R[3 * i] * J[3] + L.R[3 * i + 1] * J[1] + L.R[3 * i + 2] * J[5];
+      Tm[3 * i + 2] = L.R[3 * i] * J[4] + L.R[3 * i + 1] * J[5] + L.R[3 * i + 2] * J[2];
+    }
+    const double m = md.mass[b];
+    const T cc = dot3(c, c);
+    I[0] = T(m); I[1] = m * c[0]; I[2] = m * c[1]; I[3] = m * c[2];
+    I[4] = dot3(Tm, L.R) + m * (cc - c[0] * c[0]);
+    I[5] = dot3(Tm + 3, L.R + 3) + m * (cc - c[1] * c[1]);
+    I[6] = dot3(Tm + 6, L.R + 6) + m * (cc - c[2] * c[2]);
+    I[7] = dot3(Tm, L.R + 3) - m * (c[0] * c[1]);
+    I[8] = dot3(Tm, L.R + 6) - m * (c[0] * c[2]);
+    I[9] = dot3(Tm + 3, L.R + 6) - m * (c[1] * c[2]);
+  }
+  T At[6], Ia[6], Iv[6];
+  for (int i = 0; i < 6; ++i) At[i] = L.Va[i] + L.Ab[i];
+  spi_apply(I, At, Ia);
+  spi_apply(I, L.V, Iv);
+  T a1[3], a2[3], a3[3];
+  cross3(L.V, Iv, a1); cross3(L.V + 3, Iv + 3, a2); cross3(L.V, Iv + 3, a3);
+  w.body[b][0] = Ia[0] + a1[0] + a2[0]; w.body[b][1] = Ia[1] + a1[1] + a2[1]; w.body[b][2] = Ia[2] + a1[2] + a2[2];
+  w.body[b][3] = Ia[3] + a3[0]; w.body[b][4] = Ia[4] + a3[1]; w.body[b][5] = Ia[5] + a3[2];
+}
+
+template <class T> H1_DEV void ph_id_contact(int lane, const DynModel& md, TanWarpT<T>& w) {
+  if (lane >= NCPT) return;
+  const int f = lane / H1_NCP;
+  const T* R = w.footR[f];
+  const double* pt = md.foot_pts[lane];
+  T rho[3] = {w.footr[f][0] + R[0] * pt[0] + R[1] * pt[1] + R[2] * pt[2],
+              w.footr[f][1] + R[3] * pt[0] + R[4] * pt[1] + R[5] * pt[2],
+              w.footr[f][2] + R[6] * pt[0] + R[7] * pt[1] + R[8] * pt[2]};
+  T t1[3], t2[3];
+  cross3(w.footV[f], rho, t1);
+  cross3(w.footVa[f], rho, t2);
+  const T pd[3] = {w.footV[f][3] + t1[0], w.footV[f][4] + t1[1], w.footV[f][5] + t1[2]};
+  const T pa[3] = {w.footVa[f][3] + t2[0], w.footVa[f][4] + t2[1], w.footVa[f][5] + t2[2]};
+  const double h = md.h;
+  const T dd = -(w.q[2] + rho[2]);
+  const T root = sqrt_t(dd * dd + md.eps * md.eps);
+  const T sp = 0.5 * (dd + root), al = 0.5 * (1.0 + dd / root);
+  T F[3];
+  F[0] = -(al * md.bt) * (pd[0] + h * pa[0]);
+  F[1] = -(al * md.bt) * (pd[1] + h * pa[1]);
+  F[2] = md.kn * sp - al * ((md.bn + h * md.kn) * pd[2] + (h * md.bn + h * h * md.kn) * pa[2]);
+  T n[3];
+  cross3(rho, F, n);
+  w.cw[lane][0] = n[0]; w.cw[lane][1] = n[1]; w.cw[lane][2] = n[2];
+  w.cw[lane][3] = F[0]; w.cw[lane][4] = F[1]; w.cw[lane][5] = F[2];
+}
+
+template <class T> H1_DEV void ph_id_sums(int lane, const DynModel& md, TanWarpT<T>& w, T* T6) {
+  if (lane < 6 || lane >= NV) return;
+  const int b = lane - 5, e = md.chain_end[b];
+  for (int i = 0; i < 6; ++i) T6[i] = T(0.0);
+#pragma unroll 1
+  for (int k = b; k <= e; ++k) {
+    for (int i = 0; i < 6; ++i) T6[i] += w.body[k][i];
+    for (int f = 0; f < H1_NFOOT; ++f)
+      if (k == md.foot_body[f])
+        for (int c = 0; c < H1_NCP; ++c)
+          for (int i = 0; i < 6; ++i) T6[i] -= w.cw[f * H1_NCP + c][i];
+  }
+  if (md.parent[b] == 0) {
+    const int slot = md.base_child_slot[b];
+    for (int i = 0; i < 6; ++i) w.part[slot][i] = T6[i];
+  }
+}
+
+template <class T> H1_DEV void ph_id_resid(int lane, const DynModel& md, TanWarpT<T>& w, const TanLaneT<T>& L, T* T6,
+                                           const double* a) {
+  if (lane >= NV) return;
+  if (lane < 6) {
+    for (int i = 0; i < 6; ++i) T6[i] = w.body[0][i];
+    for (int c = 0; c < md.n_base_children; ++c)
+      for (int i = 0; i < 6; ++i) T6[i] += w.part[c][i];
+  }
+  const int j = lane;
+  const T g = dot6(L.S, T6) + (md.armature[j] + md.h * md.damping[j]) * a[j] + md.damping[j] * w.v[j] - w.tau[j];
+  w.tvec[j] = -tangent_of(g);
+  w.acc[j] = T(a[j]);
+}
+template <class W> H1_DEV void ph_ctrl_rhs(int lane, W& w, const double* a) {  // control direction: t = d tau
+  if (lane >= NV) return;
+  w.tvec[lane] = w.tau[lane].d;
+  w.acc[lane] = Dual(a[lane], 0.0);
+}
+
+template <class W> H1_DEV void ph_tan_fwd_g(int lane, int lev, const DynModel& md, W& w, const PrimalFactor& pf) {
+  if (lane >= NV || md.level[lane] != lev) return;
+  const int i = lane, slot = md.nlist[i] - 1, e = md.dof_sub_end[i];
+  double y = w.tvec[i];
+  for (int k = i + 1; k <= e; ++k) y -= pf.Lm[k][slot] * w.tvec[k];
+  w.tvec[i] = y;
+}
+template <class W> H1_DEV void ph_tan_back_g(int lane, int lev, const DynModel& md, W& w, const PrimalFactor& pf) {
+  if (lane >= NV || md.level[lane] != lev) return;
+  const int k = lane, n = md.nlist[k];
+  double ad = w.tvec[k] / pf.D[k];
+  for (int s = 0; s < n - 1; ++s) ad -= pf.Lm[k][s] * w.acc[md.alist[k][s]].d;
+  w.acc[k] = Dual(pf.a[k], ad);
+}
+
+#if defined(__CUDACC__)
+#define H1_TLANES_DECL TanLaneT<Dual> Lr; Dual T6r[6]; const int lane = threadIdx.x & 31;
+#define H1_TLR Lr
+#define H1_T6 T6r
+#else
+#define H1_TLANES_DECL static thread_local TanLaneT<Dual> Lr_[32]; static thread_local Dual T6r_[32][6];
+#define H1_TLR Lr_[lane]
+#define H1_T6 T6r_[lane]
+#endif
+
+// One exact column of [A | B]: d f_D / d(input `seed`), written to out_col[51].
+H1_DEV void dyn_tangent_id_warp(const DynModel& md, TanWarpT<Dual>& w, const PrimalFactor& pf, const double* x,
+                                const double* u, int seed, double* out_col) {
+  H1_TLANES_DECL
+  H1_PHASE((ph_load<Dual, TanWarpT<Dual> >(lane, md, w, x, u, seed, 0.0)))
+  if (seed >= NX) {
+    H1_PHASE(ph_ctrl_rhs(lane, w, pf.a))
+  } else {
+    H1_PHASE(ph_id_walk<Dual>(lane, md, w, H1_TLR, pf.a))
+    H1_PHASE(ph_id_contact<Dual>(lane, md, w))
+    H1_PHASE(ph_id_sums<Dual>(lane, md, w, H1_T6))
+    H1_PHASE(ph_id_resid<Dual>(lane, md, w, H1_TLR, H1_T6, pf.a))
+  }
+  for (int lev = MAXSLOT - 1; lev >= 0; --lev) H1_PHASE(ph_tan_fwd_g(lane, lev, md, w, pf))
+  for (int lev = 0; lev < MAXSLOT; ++lev) H1_PHASE(ph_tan_back_g(lane, lev, md, w, pf))
+  H1_PHASE((ph_integrate<Dual, TanWarpT<Dual> >(lane, md, w, out_col)))
 }
 
 }  // namespace h1

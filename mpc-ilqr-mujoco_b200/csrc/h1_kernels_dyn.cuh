@@ -52,7 +52,8 @@ __global__ void k_dyn_query(const DynModel* gmd, int n, const double* __restrict
 //      One warp per instance. t_begin > 0 rolls out only the tail (warm start: last knot). ----
 __global__ void k_rollout(const DynModel* gmd, const H1Weights* gw, RefTable refs, int B, int N, int t_begin,
                           const int* __restrict__ active, const double* __restrict__ x0, double* __restrict__ xbar,
-                          const double* __restrict__ ubar, double* __restrict__ cost_out) {
+                          const double* __restrict__ ubar, double* __restrict__ cost_out,
+                          PrimalFactor* __restrict__ pf_out) {
   extern __shared__ __align__(16) unsigned char smem[];
   const DynModel* md;
   unsigned char* p = stage_model(smem, gmd, &md);
@@ -71,7 +72,8 @@ __global__ void k_rollout(const DynModel* gmd, const H1Weights* gw, RefTable ref
   double total = 0.0;
   for (int t = 0; t < N; ++t) {
     if (t >= t_begin) {
-      dyn_step_warp(*md, w, xb + t * NX, ub + t * NU, xb + (t + 1) * NX);
+      if (pf_out) dyn_primal_factor_warp(*md, w, xb + t * NX, ub + t * NU, xb + (t + 1) * NX, pf_out[(size_t)inst * N + t]);
+      else dyn_step_warp(*md, w, xb + t * NX, ub + t * NU, xb + (t + 1) * NX);
     } else if (cost_out) {
       dyn_assemble_warp(*md, w, xb + t * NX, ub + t * NU);
     }
@@ -121,35 +123,52 @@ k_linearize_fd(const DynModel* gmd, int N, double eps, const int* __restrict__ a
   }
 }
 
-// ---- analytic linearization: A = d f_D/dx, B = d f_D/du exactly, by forward-mode tangents sharing one
-//      factorisation of Mhat per knot (see h1_dyn.cuh). One CTA per (instance, knot); warp 0 does the primal
-//      pass while the other warps already assemble their first tangent direction. ----
+// ---- factorisation of Mhat at every knot of the current trajectory (granular API path; inside a solve the
+//      nominal rollout produces the same factors as a by-product) ----
+__global__ void k_primal_factor(const DynModel* gmd, int B, int N, const double* __restrict__ xbar,
+                                const double* __restrict__ ubar, PrimalFactor* __restrict__ pf_out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const DynModel* md;
+  unsigned char* p = stage_model(smem, gmd, &md);
+  DynWarp& w = reinterpret_cast<DynWarp*>(p)[threadIdx.x >> 5];
+  const long k = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= (long)B * N) return;
+  const int inst = (int)(k / N), t = (int)(k % N);
+  dyn_primal_factor_warp(*md, w, xbar + ((size_t)inst * (N + 1) + t) * NX, ubar + ((size_t)inst * N + t) * NU, nullptr,
+                         pf_out[k]);
+}
+
+// ---- analytic linearization: A = d f_D/dx, B = d f_D/du exactly. Per knot, ONE factorisation of Mhat (taken
+//      from the nominal rollout) serves all 70 tangent directions; each direction is a dual-number
+//      inverse-dynamics pass + two sparse triangular solves (h1_dyn.cuh). One CTA per (instance, knot),
+//      directions round-robin over its warps, columns written straight to A_k / B_k. ----
 constexpr int LINA_WARPS = 4;
-__global__ void __launch_bounds__(LINA_WARPS * 32)
+__global__ void __launch_bounds__(LINA_WARPS * 32, 3)
 k_linearize_analytic(const DynModel* gmd, int N, const int* __restrict__ active, const double* __restrict__ xbar,
-                     const double* __restrict__ ubar, double* __restrict__ A, double* __restrict__ Bm) {
+                     const double* __restrict__ ubar, const PrimalFactor* __restrict__ pf_g, double* __restrict__ A,
+                     double* __restrict__ Bm) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int inst = blockIdx.x / N, t = blockIdx.x % N;
   if (active && !active[inst]) return;
   const DynModel* md;
   unsigned char* p = stage_model(smem, gmd, &md);
-  DynWarpT<Dual>* ws = reinterpret_cast<DynWarpT<Dual>*>(p);
-  PrimalFactor* pf = reinterpret_cast<PrimalFactor*>(p + sizeof(DynWarpT<Dual>) * LINA_WARPS);
+  TanWarpT<Dual>* ws = reinterpret_cast<TanWarpT<Dual>*>(p);
+  PrimalFactor* pf = reinterpret_cast<PrimalFactor*>(p + sizeof(TanWarpT<Dual>) * LINA_WARPS);
   double* xs = reinterpret_cast<double*>(pf + 1);
   const double* x = xbar + ((size_t)inst * (N + 1) + t) * NX;
   const double* u = ubar + ((size_t)inst * N + t) * NU;
   for (int i = threadIdx.x; i < NX + NU; i += blockDim.x) xs[i] = (i < NX) ? x[i] : u[i - NX];
+  {
+    const double* src = reinterpret_cast<const double*>(pf_g + ((size_t)inst * N + t));
+    double* dst = reinterpret_cast<double*>(pf);
+    for (int i = threadIdx.x; i < (int)(sizeof(PrimalFactor) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5;
-  if (warp == 0) dyn_primal_factor_warp(*md, *reinterpret_cast<DynWarp*>(&ws[0]), xs, xs + NX, nullptr, *pf);
   double* Ak = A + ((size_t)inst * N + t) * NX * NX;
   double* Bk = Bm + ((size_t)inst * N + t) * NX * NU;
-  bool first = true;
-  for (int e = warp; e < NX + NU; e += LINA_WARPS) {
-    dyn_tangent_assemble_warp(*md, ws[warp], xs, xs + NX, e);
-    if (first) { __syncthreads(); first = false; }
-    dyn_tangent_solve_warp(*md, ws[warp], *pf, e < NX ? Ak + e * NX : Bk + (e - NX) * NX);
-  }
+  for (int e = warp; e < NX + NU; e += LINA_WARPS)
+    dyn_tangent_id_warp(*md, ws[warp], *pf, xs, xs + NX, e, e < NX ? Ak + e * NX : Bk + (e - NX) * NX);
 }
 
 }  // namespace h1

@@ -51,69 +51,55 @@ __device__ __forceinline__ void gemm_smem(int m, int n, int k, const double* __r
 
 struct RiccatiSmem {
   double Vxx[NX * NX];
-  double AB[NX * NXU];     // [A | B]
-  double W[NX * NXU];      // Vxx [A | B]; later reused as scratch (QuuK, T)
+  double AB[NX * NXU];     // [A | B] of the current knot; refilled with the next knot's by cp.async
+  double W[NX * NXU];      // Vxx [A | B]; later reused as scratch (QuuK, Qxu K)
   double Qx_[NX * NXU];    // [Qxx | Qxu]
+  double Lnext[NX * NX];   // lxx of the next knot (cp.async prefetch)
+  double T1[NX * NX];      // K' Quu K
   double Quu[NU * NU];
-  double Lf[NU * NU];      // permuted LDLT factor (unit lower), D on the diagonal slot array below
+  double Lf[NU * NU];      // permuted Quu, reduced in place to its Schur complements
+  double Ls[NU * NU];      // unit-lower factor of the permuted LDL^T
   double Kt[NU * (NX + 1)];// solves: columns 0..50 -> K(:,j), column 51 -> kff
   double Vx[NX], Qx[NX], Qu[NU], D[NU], tmp[NX];
   int perm[NU];
-  int llt_fail;
+  int not_pd;
 };
 
-// Cholesky positive-definiteness test of Quu (Eigen::LLT info()); one warp, lane <-> row. Scratch in Lf.
-__device__ __forceinline__ void quu_llt_check(RiccatiSmem& s) {
-  const int lane = threadIdx.x;  // called by warp 0 only
-  const int n = NU;
-  for (int e = lane; e < n * n; e += 32) s.Lf[e] = s.Quu[e];
-  if (lane == 0) s.llt_fail = 0;
-  __syncwarp();
-  for (int j = 0; j < n; ++j) {
-    const double d = s.Lf[j * n + j];
-    if (!(d > 0.0)) { if (lane == 0) s.llt_fail = 1; break; }
-    const double sd = sqrt(d);
-    double lij = 0.0;
-    if (lane > j && lane < n) { lij = s.Lf[j * n + lane] / sd; s.Lf[j * n + lane] = lij; }
-    __syncwarp();
-    // trailing update of row `lane`: M[lane][c] -= l[lane][j] * l[c][j], c in (j, lane]
-    if (lane > j && lane < n)
-      for (int c = j + 1; c <= lane; ++c) s.Lf[c * n + lane] -= lij * s.Lf[j * n + c];
-    __syncwarp();
-  }
-  __syncwarp();
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
-// LDL^T with symmetric pivoting by largest |original diagonal| (selection order as Eigen::LDLT), one warp.
+// LDL^T of Quu with symmetric pivoting by largest |diagonal| (Eigen::LDLT's selection rule), one warp,
+// right-looking: after step k, row i holds the Schur complement. Sets not_pd when a pivot is <= 0, which for
+// a symmetric matrix is equivalent to Eigen::LLT reporting failure (Sylvester's law of inertia).
 __device__ __forceinline__ void quu_ldlt(RiccatiSmem& s) {
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x;  // warp 0 only
   const int n = NU;
-  if (lane == 0) {
-    int p[NU];
-    for (int i = 0; i < n; ++i) p[i] = i;
-    for (int k = 0; k < n; ++k) {
-      int best = k;
-      double bv = fabs(s.Quu[p[k] * n + p[k]]);
-      for (int i = k + 1; i < n; ++i) { const double v = fabs(s.Quu[p[i] * n + p[i]]); if (v > bv) { bv = v; best = i; } }
-      const int t = p[k]; p[k] = p[best]; p[best] = t;
+  if (lane < n) {  // rank of |Q_ii| in descending order, ties by index
+    const double di = fabs(s.Quu[lane * n + lane]);
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const double dj = fabs(s.Quu[j * n + j]);
+      rank += (dj > di) || (dj == di && j < lane);
     }
-    for (int i = 0; i < n; ++i) s.perm[i] = p[i];
+    s.perm[rank] = lane;
   }
+  if (lane == 0) s.not_pd = 0;
   __syncwarp();
   for (int e = lane; e < n * n; e += 32) { const int i = e % n, j = e / n; s.Lf[e] = s.Quu[s.perm[j] * n + s.perm[i]]; }
   __syncwarp();
   for (int k = 0; k < n; ++k) {
-    if (lane == k) {
-      double d = s.Lf[k * n + k];
-      for (int c = 0; c < k; ++c) d -= s.Lf[c * n + k] * s.Lf[c * n + k] * s.D[c];
-      s.D[k] = d;
-    }
-    __syncwarp();
+    const double d = s.Lf[k * n + k];
+    if (lane == 0) { s.D[k] = d; if (!(d > 0.0)) s.not_pd = 1; }
     if (lane > k && lane < n) {
-      double acc = s.Lf[k * n + lane];
-      for (int c = 0; c < k; ++c) acc -= s.Lf[c * n + lane] * s.Lf[c * n + k] * s.D[c];
-      const double d = s.D[k];
-      s.Lf[k * n + lane] = (fabs(d) > 0.0) ? acc / d : 0.0;
+      const double pik = s.Lf[k * n + lane];                       // P(i,k)
+      const double lik = (fabs(d) > 0.0) ? pik / d : 0.0;
+      for (int c = k + 1; c <= lane; ++c) s.Lf[c * n + lane] -= lik * s.Lf[k * n + c];   // P(i,c) -= l_ik P(c,k)
+      s.Ls[k * n + lane] = lik;   // separate array: column k of Lf is still being read by the other lanes
     }
     __syncwarp();
   }
@@ -132,18 +118,22 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
   const double lam = lambda[inst];
   const double* lxN = lx + ((size_t)inst * (N + 1) + N) * NX;
   const double* lxxN = lxx + ((size_t)inst * (N + 1) + N) * NX * NX;
+  auto prefetch = [&](int t) {  // A_t, B_t -> s.AB ; lxx_t -> s.Lnext  (8-byte async copies)
+    const double* At = A + ((size_t)inst * N + t) * NX * NX;
+    const double* Bt = Bm + ((size_t)inst * N + t) * NX * NU;
+    const double* Lt = lxx + ((size_t)inst * (N + 1) + t) * NX * NX;
+    for (int i = tid; i < NX * NX; i += nt) { cp_async8(&s.AB[i], At + i); cp_async8(&s.Lnext[i], Lt + i); }
+    for (int i = tid; i < NX * NU; i += nt) cp_async8(&s.AB[NX * NX + i], Bt + i);
+  };
+  prefetch(N - 1);
   for (int i = tid; i < NX; i += nt) s.Vx[i] = lxN[i];
   for (int i = tid; i < NX * NX; i += nt) s.Vxx[i] = lxxN[i];
   bool nonfinite = false;
   for (int t = N - 1; t >= 0; --t) {
-    const double* At = A + ((size_t)inst * N + t) * NX * NX;
-    const double* Bt = Bm + ((size_t)inst * N + t) * NX * NU;
     const double* lxt = lx + ((size_t)inst * (N + 1) + t) * NX;
     const double* lut = lu + ((size_t)inst * N + t) * NU;
-    const double* lxxt = lxx + ((size_t)inst * (N + 1) + t) * NX * NX;
     const double* luut = luu + ((size_t)inst * N + t) * NU * NU;
-    for (int i = tid; i < NX * NX; i += nt) s.AB[i] = At[i];
-    for (int i = tid; i < NX * NU; i += nt) s.AB[NX * NX + i] = Bt[i];
+    cp_async_commit_wait_all();
     __syncthreads();
     // W = Vxx [A|B]
     gemm_smem<false>(NX, NXU, NX, s.Vxx, NX, s.AB, NX, s.W, NX);
@@ -159,16 +149,18 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
     gemm_smem<true>(NX, NXU, NX, s.AB, NX, s.W, NX, s.Qx_, NX);
     gemm_smem<true>(NU, NU, NX, s.AB + NX * NX, NX, s.W + NX * NX, NX, s.Quu, NU);
     __syncthreads();
-    for (int i = tid; i < NX * NX; i += nt) s.Qx_[i] += lxxt[i];
+    for (int i = tid; i < NX * NX; i += nt) s.Qx_[i] += s.Lnext[i];
     for (int i = tid; i < NU * NU; i += nt) s.Quu[i] += luut[i] + ((i % NU == i / NU) ? lam : 0.0);
     __syncthreads();
-    if (tid < 32) quu_llt_check(s);
-    __syncthreads();
-    if (s.llt_fail) {
-      for (int i = tid; i < NU; i += nt) s.Quu[i * NU + i] += 1e-4;
-      __syncthreads();
+    if (t > 0) prefetch(t - 1);   // s.AB / s.Lnext are free from here on; overlaps the factorisation and solves
+    if (tid < 32) {
+      quu_ldlt(s);
+      if (s.not_pd) {             // Eigen::LLT failed: Quu += 1e-4 I once, no re-check (quirk Q9), refactor
+        for (int i = tid; i < NU; i += 32) s.Quu[i * NU + i] += 1e-4;
+        __syncwarp();
+        quu_ldlt(s);
+      }
     }
-    if (tid < 32) quu_ldlt(s);
     __syncthreads();
     // solves: rhs r < 51 -> column r of Qxu' (= row r of Qxu), rhs 51 -> Qu ; result negated
     if (tid <= NX) {
@@ -182,13 +174,13 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
 #pragma unroll
       for (int i = 0; i < NU; ++i)
 #pragma unroll
-        for (int c = 0; c < i; ++c) y[i] -= s.Lf[c * NU + i] * y[c];
+        for (int c = 0; c < i; ++c) y[i] -= s.Ls[c * NU + i] * y[c];
 #pragma unroll
       for (int i = 0; i < NU; ++i) y[i] = (fabs(s.D[i]) > 2.2250738585072014e-308) ? y[i] / s.D[i] : 0.0;
 #pragma unroll
       for (int i = NU - 1; i >= 0; --i)
 #pragma unroll
-        for (int c = i + 1; c < NU; ++c) y[i] -= s.Lf[i * NU + c] * y[c];
+        for (int c = i + 1; c < NU; ++c) y[i] -= s.Ls[i * NU + c] * y[c];
 #pragma unroll
       for (int i = 0; i < NU; ++i) {
         const double v = -y[i];
@@ -202,9 +194,9 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
     double* kf_g = kff + ((size_t)inst * N + t) * NU;
     for (int i = tid; i < NU * NX; i += nt) Kt_g[i] = s.Kt[i];
     for (int i = tid; i < NU; i += nt) kf_g[i] = s.Kt[NX * NU + i];
-    // QuuK (19x51) into W scratch, Quu k into tmp
+    // QuuK (19x51) and Qxu K (51x51) into W scratch, Quu k into tmp
     double* QuuK = s.W;
-    double* T3 = s.W + NU * NX;  // Qxu K (51x51)
+    double* T3 = s.W + NU * NX;
     gemm_smem<false>(NU, NX, NU, s.Quu, NU, s.Kt, NU, QuuK, NU);
     gemm_smem<false>(NX, NX, NU, s.Qx_ + NX * NX, NX, s.Kt, NU, T3, NX);
     if (tid < NU) {
@@ -213,7 +205,7 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
       s.tmp[tid] = acc;
     }
     __syncthreads();
-    // Vx = Qx + K'(Quu k) + K'Qu + Qxu k
+    // Vx = Qx + K'(Quu k) + K'Qu + Qxu k ;  T1 = K' (Quu K)
     if (tid < NX) {
       double a1 = 0.0, a2 = 0.0, a3 = 0.0;
       for (int l = 0; l < NU; ++l) {
@@ -222,17 +214,14 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
       }
       s.Vx[tid] = s.Qx[tid] + a1 + a2 + a3;
     }
-    // T(i,j) = Qxx + K'QuuK + (QxuK)' + QxuK, written over the Qxx block
-    for (int e = tid; e < NX * NX; e += nt) {
-      const int i = e % NX, j = e / NX;
-      double acc = 0.0;
-      for (int l = 0; l < NU; ++l) acc += s.Kt[i * NU + l] * QuuK[j * NU + l];
-      s.Qx_[e] = s.Qx_[e] + acc + T3[i * NX + j] + T3[e];
-    }
+    gemm_smem<true>(NX, NX, NU, s.Kt, NU, QuuK, NU, s.T1, NX);
     __syncthreads();
+    // Vxx = sym(Qxx + K'QuuK + (QxuK)' + QxuK)
     for (int e = tid; e < NX * NX; e += nt) {
-      const int i = e % NX, j = e / NX;
-      s.Vxx[e] = 0.5 * (s.Qx_[e] + s.Qx_[i * NX + j]);
+      const int i = e % NX, j = e / NX, et = i * NX + j;
+      const double tij = s.Qx_[e] + s.T1[e] + T3[et] + T3[e];
+      const double tji = s.Qx_[et] + s.T1[et] + T3[e] + T3[et];
+      s.Vxx[e] = 0.5 * (tij + tji);
     }
     __syncthreads();
   }

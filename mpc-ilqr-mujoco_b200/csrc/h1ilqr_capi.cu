@@ -35,6 +35,7 @@ struct H1Ilqr {
   int *active = nullptr, *second = nullptr, *iters = nullptr, *status = nullptr, *ls_ok = nullptr, *ls_alpha = nullptr;
   int *has_prev = nullptr, *warm_mask = nullptr, *cold_mask = nullptr, *warm_in = nullptr;
   double* cost_trace = nullptr; int* alpha_trace = nullptr;
+  PrimalFactor* pf = nullptr;   // [B][N] factorisation of Mhat at every knot of the nominal trajectory
   double* scratch = nullptr; size_t scratch_bytes = 0;   // device staging for n-state queries
   void* pin = nullptr; size_t pin_bytes = 0;              // pinned host staging
   std::vector<void*> allocs;
@@ -130,6 +131,7 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   CUH(dalloc(h, &h->active, B)); CUH(dalloc(h, &h->second, B)); CUH(dalloc(h, &h->iters, B)); CUH(dalloc(h, &h->status, B));
   CUH(dalloc(h, &h->ls_ok, B)); CUH(dalloc(h, &h->ls_alpha, B)); CUH(dalloc(h, &h->has_prev, B));
   CUH(dalloc(h, &h->warm_mask, B)); CUH(dalloc(h, &h->cold_mask, B)); CUH(dalloc(h, &h->warm_in, B));
+  CUH(dalloc(h, &h->pf, B * N));
   CUH(dalloc(h, &h->cost_trace, B * h->opt.max_iterations)); CUH(dalloc(h, &h->alpha_trace, B * h->opt.max_iterations * 2));
   h->scratch_bytes = B * N1 * (NX + NU + NX + NV + 9) * sizeof(double);
   { double* sp = nullptr; CUH(dalloc(h, &sp, h->scratch_bytes / sizeof(double))); h->scratch = sp; }
@@ -141,13 +143,14 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   const size_t mdl = ((sizeof(DynModel) + 15) / 16) * 16, cml = ((sizeof(CostModel) + 15) / 16) * 16;
   h->smem_dyn4 = mdl + 4 * sizeof(DynWarp);
   h->smem_lin = mdl + LIN_WARPS * sizeof(DynWarp) + (LIN_EVALS * NX + NX + NU) * sizeof(double);
-  h->smem_lina = mdl + LINA_WARPS * sizeof(DynWarpT<Dual>) + sizeof(PrimalFactor) + (NX + NU) * sizeof(double);
+  h->smem_lina = mdl + LINA_WARPS * sizeof(TanWarpT<Dual>) + sizeof(PrimalFactor) + (NX + NU) * sizeof(double);
   h->smem_cq = cml + CQ_WARPS * sizeof(CostWarp);
   h->smem_ls = mdl + H1ILQR_NALPHA * sizeof(DynWarp) + (H1ILQR_NALPHA + H1ILQR_NALPHA * (NX + NU)) * sizeof(double);
   h->smem_ric = sizeof(RiccatiSmem);
   CUH(cudaFuncSetAttribute(k_dyn_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
   CUH(cudaFuncSetAttribute(k_dyn_query, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
   CUH(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
+  CUH(cudaFuncSetAttribute(k_primal_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
   CUH(cudaFuncSetAttribute(k_linearize_fd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_lin));
   CUH(cudaFuncSetAttribute(k_linearize_analytic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_lina));
   CUH(cudaFuncSetAttribute(k_cost_quadratics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_cq));
@@ -196,16 +199,24 @@ int h1ilqr_set_reference_window(H1Ilqr* h, const double* x_ref, const double* u_
 }
 
 // ---------------- stage launchers (no host sync) ----------------
-static void launch_rollout(H1Ilqr* h, const int* mask, const double* x0_dev, int t_begin, double* cost_out) {
+static void launch_rollout(H1Ilqr* h, const int* mask, const double* x0_dev, int t_begin, double* cost_out,
+                           bool keep_factors = false) {
   const int wpb = 4, blocks = (h->B + wpb - 1) / wpb;
   k_rollout<<<blocks, wpb * 32, h->smem_dyn4, h->stream>>>(h->d_dyn, h->d_w, ref_table(h), h->B, h->N, t_begin, mask,
-                                                          x0_dev, h->xbar, h->ubar, cost_out);
+                                                          x0_dev, h->xbar, h->ubar, cost_out,
+                                                          keep_factors ? h->pf : nullptr);
   LAUNCHED();
 }
-static void launch_linearize(H1Ilqr* h, const int* mask) {
+// `factors_ready`: the nominal rollout that just ran kept the per-knot factorisations of Mhat
+static void launch_linearize(H1Ilqr* h, const int* mask, bool factors_ready = false) {
   if (h->opt.linearization != H1ILQR_LIN_FD) {
+    if (!factors_ready) {
+      const long warps = (long)h->B * h->N;
+      k_primal_factor<<<(int)((warps + 3) / 4), 128, h->smem_dyn4, h->stream>>>(h->d_dyn, h->B, h->N, h->xbar, h->ubar, h->pf);
+      LAUNCHED();
+    }
     k_linearize_analytic<<<h->B * h->N, LINA_WARPS * 32, h->smem_lina, h->stream>>>(h->d_dyn, h->N, mask, h->xbar, h->ubar,
-                                                                                 h->A, h->Bm);
+                                                                                 h->pf, h->A, h->Bm);
     LAUNCHED();
     return;
   }
@@ -260,11 +271,12 @@ struct StageTimer {
 
 // The whole iLQR::solve launch sequence, stream-ordered, no host round trips (unless stage timing is on).
 static void enqueue_solve(H1Ilqr* h) {
+  const bool analytic = h->opt.linearization != H1ILQR_LIN_FD;
   launch_rollout(h, nullptr, nullptr, h->N, h->cost);  // current_cost = computeTotalCost(xbar, ubar)
   for (int it = 0; it < h->opt.max_iterations; ++it) {
     launch_state(h, it, 0);
-    { StageTimer t(h, &h->times.rollout_ms); launch_rollout(h, h->active, h->x0, 0, h->nominal_cost); }
-    { StageTimer t(h, &h->times.linearize_ms); launch_linearize(h, h->active); }
+    { StageTimer t(h, &h->times.rollout_ms); launch_rollout(h, h->active, h->x0, 0, h->nominal_cost, analytic); }
+    { StageTimer t(h, &h->times.linearize_ms); launch_linearize(h, h->active, analytic); }
     { StageTimer t(h, &h->times.cost_quadratics_ms); launch_cost_quadratics(h, h->active); }
     { StageTimer t(h, &h->times.backward_ms); launch_backward(h, h->active); }
     { StageTimer t(h, &h->times.line_search_ms); launch_line_search(h, h->active); }

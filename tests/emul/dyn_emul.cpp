@@ -31,3 +31,17 @@ extern "C" int emul_dyn_linearize_analytic(const double* x, const double* u, dou
   }
   return 0;
 }
+
+// same, through the inverse-dynamics tangent (the path the kernel k_linearize_analytic runs)
+extern "C" int emul_dyn_linearize_id(const double* x, const double* u, double* A, double* B) {
+  static h1::DynModel md;
+  static bool init = false;
+  if (!init) { if (!h1::build_dyn_model(*h1_default_dynamics_model(), &md)) return -1; init = true; }
+  static h1::DynWarp w;
+  static h1::TanWarpT<h1::Dual> wt;
+  static h1::PrimalFactor pf;
+  h1::dyn_primal_factor_warp(md, w, x, u, nullptr, pf);
+  for (int e = 0; e < h1::NX + h1::NU; ++e)
+    h1::dyn_tangent_id_warp(md, wt, pf, x, u, e, e < h1::NX ? A + e * h1::NX : B + (e - h1::NX) * h1::NX);
+  return 0;
+}
