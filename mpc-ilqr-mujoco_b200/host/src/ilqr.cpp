@@ -1,0 +1,111 @@
+// iLQR shim over the C ABI (reference: src/ilqr/ilqr.cpp). All numerical stages run on the GPU.
+#include "ilqr/ilqr.hpp"
+#include <iostream>
+#include <stdexcept>
+
+iLQR::iLQR(RobotUtils& robot, int N, double dt, const std::string& urdf_path)
+    : robot_(robot), N_(N), dt_(dt), h_(nullptr) {
+  (void)urdf_path;  // the cost (URDF) model tables are compiled in; see tools/gen_h1_model.py
+  h1ilqr_default_options(&opt_);
+  const int nx = robot_.nx(), nu = robot_.nu();
+  xbar_.assign(N_ + 1, Eigen::VectorXd::Zero(nx));
+  ubar_.assign(N_, Eigen::VectorXd::Zero(nu));
+  kff_.assign(N_, Eigen::VectorXd::Zero(nu));
+  K_.assign(N_, Eigen::MatrixXd::Zero(nu, nx));
+  if (!recreate()) throw std::runtime_error(std::string("iLQR: cannot create the GPU solver: ") + h1ilqr_last_error());
+  std::cout << "iLQR initialized with horizon N=" << N_ << ", dt=" << dt_ << std::endl;
+}
+iLQR::~iLQR() { if (h_) h1ilqr_destroy(h_); }
+
+bool iLQR::recreate() {
+  double lambda = opt_.reg_init;
+  if (h_) { h1ilqr_get_regularization(h_, &lambda); h1ilqr_destroy(h_); h_ = nullptr; }
+  H1Model dm = robot_.dynamics_model();
+  if (h1ilqr_create(&dm, nullptr, &opt_, 1, N_, 0, &h_) != H1ILQR_OK) return false;
+  return h1ilqr_set_regularization(h_, &lambda, 1) == H1ILQR_OK;
+}
+void iLQR::setRegularization(double lambda) { if (h_) h1ilqr_set_regularization(h_, &lambda, 1); }
+void iLQR::setMaxIterations(int max_iter) { opt_.max_iterations = max_iter; recreate(); }
+void iLQR::setTolerance(double tol) { opt_.tolerance = tol; recreate(); }
+
+bool iLQR::upload_window(const std::vector<Eigen::VectorXd>& x_ref, const std::vector<Eigen::VectorXd>& u_ref,
+                         const std::vector<Eigen::Vector3d>& com_ref) {
+  const int nx = robot_.nx(), nu = robot_.nu();
+  std::vector<double> xr((N_ + 1) * nx), ur(N_ * nu), cr((N_ + 1) * 3), er((N_ + 1) * 6), cv((N_ + 1) * 3, 0.0);
+  std::vector<int> st((N_ + 1) * 2);
+  for (int t = 0; t <= N_; ++t) {
+    for (int i = 0; i < nx; ++i) xr[t * nx + i] = x_ref[t](i);
+    for (int i = 0; i < 3; ++i) cr[t * 3 + i] = com_ref[t](i);
+    // horizon-local lookups, exactly as the reference does (quirk Q6); getEEReference throws past the table
+    for (int e = 0; e < 2; ++e) {
+      st[t * 2 + e] = robot_.isStance(e, t) ? 1 : 0;
+      Eigen::Vector3d p = robot_.getEEReference(t, e);
+      for (int i = 0; i < 3; ++i) er[t * 6 + e * 3 + i] = p(i);
+    }
+    if (robot_.getCoMVelWeight() > 0.0) { Eigen::Vector3d v = robot_.getCoMVelReference(t); for (int i = 0; i < 3; ++i) cv[t * 3 + i] = v(i); }
+    if (t < N_) for (int i = 0; i < nu; ++i) ur[t * nu + i] = u_ref[t](i);
+  }
+  H1Weights w = robot_.weights();
+  if (h1ilqr_set_weights(h_, &w) != H1ILQR_OK) return false;
+  return h1ilqr_set_reference_window(h_, xr.data(), ur.data(), cr.data(), er.data(), st.data(), cv.data(), 1) == H1ILQR_OK;
+}
+
+void iLQR::download_solution() {
+  const int nx = robot_.nx(), nu = robot_.nu();
+  std::vector<double> xb((N_ + 1) * nx), ub(N_ * nu), K(N_ * nu * nx), kf(N_ * nu);
+  h1ilqr_get_trajectory(h_, xb.data(), ub.data());
+  h1ilqr_get_gains(h_, K.data(), kf.data());
+  for (int t = 0; t <= N_; ++t) for (int i = 0; i < nx; ++i) xbar_[t](i) = xb[t * nx + i];
+  for (int t = 0; t < N_; ++t) {
+    for (int i = 0; i < nu; ++i) { ubar_[t](i) = ub[t * nu + i]; kff_[t](i) = kf[t * nu + i]; }
+    for (int j = 0; j < nx; ++j) for (int i = 0; i < nu; ++i) K_[t](i, j) = K[(t * nx + j) * nu + i];
+  }
+}
+
+void iLQR::initializeWithReference(const Eigen::VectorXd& x0, const std::vector<Eigen::VectorXd>& x_ref,
+                                   const std::vector<Eigen::VectorXd>& u_ref, const std::vector<Eigen::Vector3d>& com_ref,
+                                   const std::vector<Eigen::VectorXd>* prev_xbar, const std::vector<Eigen::VectorXd>* prev_ubar) {
+  (void)x_ref; (void)u_ref; (void)com_ref;
+  const int nx = robot_.nx(), nu = robot_.nu();
+  if (prev_xbar && prev_ubar && prev_xbar->size() == xbar_.size() && prev_ubar->size() == ubar_.size()) {
+    // warm start: shift by one knot, roll out the last step (ilqr.cpp:68-81)
+    std::vector<double> xb((N_ + 1) * nx), ub(N_ * nu);
+    for (int t = 0; t < N_; ++t) {
+      const Eigen::VectorXd& u = (*prev_ubar)[t < N_ - 1 ? t + 1 : N_ - 1];
+      for (int i = 0; i < nu; ++i) ub[t * nu + i] = u(i);
+    }
+    for (int i = 0; i < nx; ++i) xb[i] = x0(i);
+    for (int t = 0; t < N_ - 1; ++t) for (int i = 0; i < nx; ++i) xb[(t + 1) * nx + i] = (*prev_xbar)[t + 2](i);
+    h1ilqr_dynamics_step(h_, 1, &xb[(N_ - 1) * nx], &ub[(N_ - 1) * nu], &xb[N_ * nx]);
+    h1ilqr_set_trajectory(h_, xb.data(), ub.data());
+  } else {
+    std::cout << "Initial Guess Strategy: Gravity Compensation" << std::endl;
+    Eigen::VectorXd ug;
+    robot_.computeGravComp(ug);
+    h1ilqr_initialize(h_, x0.data(), nullptr, ug.data(), 1);
+  }
+  download_solution();
+}
+
+bool iLQR::solve(const Eigen::VectorXd& x0, const std::vector<Eigen::VectorXd>& x_ref,
+                 const std::vector<Eigen::VectorXd>& u_ref, const std::vector<Eigen::Vector3d>& com_ref, double& cost_out) {
+  if (x_ref.size() != (size_t)(N_ + 1) || u_ref.size() != (size_t)N_ || com_ref.size() != (size_t)(N_ + 1)) {
+    std::cerr << "Reference size mismatch: x_ref=" << x_ref.size() << " expected=" << N_ + 1 << ", u_ref=" << u_ref.size()
+              << " expected=" << N_ << ", com_ref=" << com_ref.size() << " expected=" << N_ + 1 << std::endl;
+    return false;
+  }
+  if (!robot_.weights_are_diagonal()) throw std::runtime_error("non-diagonal Q/R/Qf are not supported by the GPU solver core");
+  if (!upload_window(x_ref, u_ref, com_ref)) throw std::runtime_error(std::string("iLQR upload: ") + h1ilqr_last_error());
+  int status = 0, iters = 0;
+  int rc = h1ilqr_solve(h_, x0.data(), &cost_out, &iters, &status);
+  if (rc == H1ILQR_ENOTFINITE) std::cout << "Warning: Non-finite gains" << std::endl;
+  else if (rc != H1ILQR_OK) throw std::runtime_error(std::string("iLQR solve: ") + h1ilqr_last_error());
+  download_solution();
+  return true;
+}
+
+H1StageTimes iLQR::lastStageTimes() const {
+  H1StageTimes t;
+  h1ilqr_get_stage_times(h_, &t);
+  return t;
+}
