@@ -114,6 +114,15 @@ int h1ilqr_mpc_step(H1Ilqr* h, const double* x_measured, const double* u_init, i
                     double* u_apply, double* cost_out);
 int h1ilqr_mpc_reset(H1Ilqr* h);
 
+/* Kernel families. The path has two sm_100a implementations of its per-knot / per-rollout stages with identical
+ * semantics (both are parity-tested against the oracle): COOPERATIVE = one warp per unit (lowest latency, used for
+ * a single MPC instance, the reference's use case), BATCHED = one thread per unit (highest throughput, used when
+ * many independent instances are resident). AUTO (default) chooses by batch*N. There is no CPU path in either. */
+#define H1ILQR_KERNELS_AUTO 0
+#define H1ILQR_KERNELS_COOPERATIVE 1
+#define H1ILQR_KERNELS_BATCHED 2
+int h1ilqr_set_kernel_policy(H1Ilqr* h, int policy);
+
 /* ---- granular stages (used by the parity tests and by the iLQR shim class) ---- */
 /* iLQR::forwardRolloutNominal (ilqr.cpp:119-124): xbar[t+1] = f_D(xbar[t], ubar[t]) from xbar[0]=x0. */
 int h1ilqr_rollout_nominal(H1Ilqr* h, const double* x0);

@@ -47,6 +47,7 @@ struct DynModel {
   int base_child_slot[NB];   // index of body b among the base's children (only valid when parent[b] == 0)
   int n_base_children;
   int pad_;
+  int nchild[NB];            // number of child bodies (branch bodies keep their state in the sequential walks)
 };
 
 // Same tree for the cost (URDF / Pinocchio-semantics) model; only what the cost kernel reads.

@@ -380,6 +380,27 @@ H1_DEV void ph_back(int lane, int lev, const DynModel& md, DynWarp& w) {
   w.acc[k] = a;
 }
 
+// q_next = normalize(normalize(q) * exp(h * wn / 2)) for the body-frame angular velocity wn (quaternion w,x,y,z)
+template <class T> H1_DEV void quat_step(const T* q, const T* wn, double h, T* qo) {
+  T qu[4];
+  quat_normalize(q, qu);
+  const T ph[3] = {h * wn[0], h * wn[1], h * wn[2]};
+  const T ang = sqrt_t(ph[0] * ph[0] + ph[1] * ph[1] + ph[2] * ph[2]);
+  T e[4];
+  if (ang < 1e-10) { e[0] = T(1.0); e[1] = 0.5 * ph[0]; e[2] = 0.5 * ph[1]; e[3] = 0.5 * ph[2]; }
+  else {
+    T s, c;
+    sincos_t(0.5 * ang, &s, &c);
+    const T sc = s / ang;
+    e[0] = c; e[1] = sc * ph[0]; e[2] = sc * ph[1]; e[3] = sc * ph[2];
+  }
+  const T pq[4] = {qu[0] * e[0] - qu[1] * e[1] - qu[2] * e[2] - qu[3] * e[3],
+                   qu[0] * e[1] + qu[1] * e[0] + qu[2] * e[3] - qu[3] * e[2],
+                   qu[0] * e[2] - qu[1] * e[3] + qu[2] * e[0] + qu[3] * e[1],
+                   qu[0] * e[3] + qu[1] * e[2] - qu[2] * e[1] + qu[3] * e[0]};
+  quat_normalize(pq, qo);
+}
+
 // ---- phase: integrate and store x_next (T = double) or its tangent (T = Dual, stores .d) ----
 H1_HD void store_out(double* p, double a) { *p = a; }
 H1_HD void store_out(double* p, const Dual& a) { *p = a.d; }
@@ -391,24 +412,9 @@ template <class T, class W> H1_DEV void ph_integrate(int lane, const DynModel& m
   if (lane < 3) store_out(&xn[lane], w.q[lane] + h * vn);
   else if (lane >= 6) store_out(&xn[lane + 1], w.q[lane + 1] + h * vn);
   else if (lane == 3) {
-    T qu[4];
-    quat_normalize(&w.q[3], qu);
-    const T ph[3] = {h * (w.v[3] + h * w.acc[3]), h * (w.v[4] + h * w.acc[4]), h * (w.v[5] + h * w.acc[5])};
-    const T ang = sqrt_t(ph[0] * ph[0] + ph[1] * ph[1] + ph[2] * ph[2]);
-    T e[4];
-    if (ang < 1e-10) { e[0] = T(1.0); e[1] = 0.5 * ph[0]; e[2] = 0.5 * ph[1]; e[3] = 0.5 * ph[2]; }
-    else {
-      T s, c;
-      sincos_t(0.5 * ang, &s, &c);
-      const T sc = s / ang;
-      e[0] = c; e[1] = sc * ph[0]; e[2] = sc * ph[1]; e[3] = sc * ph[2];
-    }
-    const T pq[4] = {qu[0] * e[0] - qu[1] * e[1] - qu[2] * e[2] - qu[3] * e[3],
-                     qu[0] * e[1] + qu[1] * e[0] + qu[2] * e[3] - qu[3] * e[2],
-                     qu[0] * e[2] - qu[1] * e[3] + qu[2] * e[0] + qu[3] * e[1],
-                     qu[0] * e[3] + qu[1] * e[2] - qu[2] * e[1] + qu[3] * e[0]};
+    const T wn[3] = {w.v[3] + h * w.acc[3], w.v[4] + h * w.acc[4], w.v[5] + h * w.acc[5]};
     T qo[4];
-    quat_normalize(pq, qo);
+    quat_step(&w.q[3], wn, h, qo);
     store_out(&xn[3], qo[0]); store_out(&xn[4], qo[1]); store_out(&xn[5], qo[2]); store_out(&xn[6], qo[3]);
   }
 }

@@ -2,6 +2,7 @@
 // forward-difference linearization, and kinematic queries.
 #pragma once
 #include "h1_cost_eval.cuh"
+#include "h1_lin_dirs.cuh"
 
 namespace h1 {
 
@@ -169,6 +170,44 @@ k_linearize_analytic(const DynModel* gmd, int N, const int* __restrict__ active,
   double* Bk = Bm + ((size_t)inst * N + t) * NX * NU;
   for (int e = warp; e < NX + NU; e += LINA_WARPS)
     dyn_tangent_id_warp(*md, ws[warp], *pf, xs, xs + NX, e, e < NX ? Ak + e * NX : Bk + (e - NX) * NX);
+}
+
+// ---- analytic linearization, one THREAD per column of [A_k | B_k] (h1_lin_dirs.cuh). Threads are packed
+//      (knot, direction) -> global thread id, so warps are full regardless of the direction count; the three
+//      direction classes are separate instantiations (launches) with their own register budgets.
+//      MODE 0: the 26 q columns, 1: the 25 v columns, 2: the 19 control columns. ----
+constexpr int LIND_THREADS = 128;
+template <int MODE>
+__global__ void __launch_bounds__(LIND_THREADS)
+k_linearize_dirs(const DynModel* gmd, long nknots, int N, const int* __restrict__ active,
+                 const double* __restrict__ xbar, const double* __restrict__ ubar,
+                 const PrimalFactor* __restrict__ pf_g, double* __restrict__ A, double* __restrict__ Bm) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const DynModel* md;
+  stage_model(smem, gmd, &md);
+  constexpr int ND = MODE == 0 ? NQ : (MODE == 1 ? NV : NU);
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long knot = g / ND;
+  const int dir = (int)(g - knot * ND);
+  if (knot >= nknots) return;
+  const long inst = knot / N;
+  const int t = (int)(knot - inst * N);
+  if (active && !active[inst]) return;
+  const double* x = xbar + ((size_t)inst * (N + 1) + t) * NX;
+  const PrimalFactor* pf = pf_g + knot;
+  double tv[NV];
+  int seed;
+  if (MODE == 0) { seed = dir; id_tangent_seq<Dual, Dual>(*md, x, pf->a, seed, tv); }
+  else if (MODE == 1) { seed = NQ + dir; id_tangent_seq<double, Dual>(*md, x, pf->a, seed, tv); }
+  else {
+    seed = NX + dir;
+    const double uj = ubar[(size_t)knot * NU + dir];
+    for (int j = 0; j < NV; ++j) tv[j] = 0.0;
+    tv[6 + dir] = (uj < md->ctrl_lo[dir] || uj > md->ctrl_hi[dir]) ? 0.0 : 1.0;   // clamped torque: no sensitivity
+  }
+  tangent_solve_seq(*md, &pf->Lm[0][0], pf->D, tv);
+  double* col = (MODE == 2) ? Bm + (size_t)knot * NX * NU + (size_t)dir * NX : A + (size_t)knot * NX * NX + (size_t)seed * NX;
+  integrate_tangent_seq(*md, x, pf->a, seed, tv, col);
 }
 
 }  // namespace h1

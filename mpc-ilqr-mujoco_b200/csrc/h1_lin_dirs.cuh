@@ -1,0 +1,260 @@
+// Direction-per-thread analytic linearization of f_D (iLQR::computeLinearization,
+// /root/reference/src/ilqr/ilqr.cpp:126-131; replaces RobotUtils::linearizeDynamicsFD,
+// /root/reference/src/common/robot_utils.cpp:120-160, by exact tangents).
+//
+// The warp-cooperative tangent pass of h1_dyn.cuh keeps 25 of 32 lanes busy in its widest phase and far fewer
+// in the tree recursions. For batched solves the 70 columns of [A_k | B_k] of every knot are independent, so
+// here ONE THREAD owns ONE column and walks the whole kinematic tree sequentially in DFS order; all 32 lanes
+// of a warp execute the same instruction stream on different directions (no divergence, no shuffles, no
+// shared-memory exchange). With the primal acceleration a held fixed (inverse-dynamics form, see h1_dyn.cuh)
+//     t = -d g / d(direction),   g = ID(q, v, a) + (armature + h D) a + D v - tau - sum_i J_i^T F_i ,
+//     Mhat adot = t   (two sparse triangular solves with the factor kept by the nominal rollout),
+// followed by the tangent of the integrator. Everything is expressed about the base origin in world-aligned
+// axes, so subtree wrenches are plain sums: with C_k the cumulative wrench over bodies 1..k (DFS order),
+// the subtree wrench of body b is C_{end(b)} - C_{b-1}, and no per-body storage is needed.
+// Three instantiations keep the work per direction class minimal:
+//   q directions (26): kinematics and velocities carry tangents       -> walk<Dual, Dual>
+//   v directions (25): kinematics are plain doubles                    -> walk<double, Dual>
+//   u directions (19): t is a unit vector (or 0 when the torque is clamped), solve + integrate only.
+// The functions contain no CUDA intrinsics and also compile as plain C++ (tests/emul).
+#pragma once
+#include "h1_dyn.cuh"
+
+namespace h1 {
+
+constexpr int SEQ_MAXSAVE = 3;  // body states are kept for branch bodies (more than one child) of depth < SEQ_MAXSAVE
+
+template <class TA, class TB, class TO> H1_DEV void cross_m(const TA* a, const TB* b, TO* o) {
+  TO x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+// spatial inertia (TI) applied to a motion vector (TM) -> momentum (TM)
+template <class TI, class TM> H1_DEV void spi_apply_m(const TI* I, const TM* V, TM* P) {
+  const TI m = I[0]; const TI* h = I + 1; const TI* J = I + 4;
+  TM hv[3], hw[3];
+  cross_m(h, V + 3, hv); cross_m(h, V, hw);
+  P[0] = J[0] * V[0] + J[3] * V[1] + J[4] * V[2] + hv[0];
+  P[1] = J[3] * V[0] + J[1] * V[1] + J[5] * V[2] + hv[1];
+  P[2] = J[4] * V[0] + J[5] * V[1] + J[2] * V[2] + hv[2];
+  P[3] = m * V[3] - hw[0];
+  P[4] = m * V[4] - hw[1];
+  P[5] = m * V[5] - hw[2];
+}
+// spatial inertia of body b about the base origin in world-aligned axes: m, h(3), I(6: xx yy zz xy xz yz)
+template <class TK> H1_DEV void body_inertia_seq(const DynModel& md, int b, const TK* R, const TK* r, TK* I) {
+  const double* ip = md.ipos[b];
+  TK c[3] = {r[0] + R[0] * ip[0] + R[1] * ip[1] + R[2] * ip[2],
+             r[1] + R[3] * ip[0] + R[4] * ip[1] + R[5] * ip[2],
+             r[2] + R[6] * ip[0] + R[7] * ip[1] + R[8] * ip[2]};
+  const double* J = md.inertia[b];
+  TK Tm[9];
+  for (int i = 0; i < 3; ++i) {
+    Tm[3 * i + 0] = R[3 * i] * J[0] + R[3 * i + 1] * J[3] + R[3 * i + 2] * J[4];
+    Tm[3 * i + 1] = R[3 * i] * J[3] + R[3 * i + 1] * J[1] + R[3 * i + 2] * J[5];
+    Tm[3 * i + 2] = R[3 * i] * J[4] + R[3 * i + 1] * J[5] + R[3 * i + 2] * J[2];
+  }
+  const double m = md.mass[b];
+  const TK cc = dot3(c, c);
+  I[0] = TK(m); I[1] = m * c[0]; I[2] = m * c[1]; I[3] = m * c[2];
+  I[4] = dot3(Tm, R) + m * (cc - c[0] * c[0]);
+  I[5] = dot3(Tm + 3, R + 3) + m * (cc - c[1] * c[1]);
+  I[6] = dot3(Tm + 6, R + 6) + m * (cc - c[2] * c[2]);
+  I[7] = dot3(Tm, R + 3) - m * (c[0] * c[1]);
+  I[8] = dot3(Tm, R + 6) - m * (c[0] * c[2]);
+  I[9] = dot3(Tm + 3, R + 6) - m * (c[1] * c[2]);
+}
+// F = I (Va + Ab) + V x* (I V)
+template <class TK, class TV> H1_DEV void body_wrench_seq(const TK* I, const TV* V, const TV* At, TV* F) {
+  TV Ia[6], Iv[6];
+  spi_apply_m(I, At, Ia);
+  spi_apply_m(I, V, Iv);
+  TV a1[3], a2[3], a3[3];
+  cross_m(V, Iv, a1); cross_m(V + 3, Iv + 3, a2); cross_m(V, Iv + 3, a3);
+  F[0] = Ia[0] + a1[0] + a2[0]; F[1] = Ia[1] + a1[1] + a2[1]; F[2] = Ia[2] + a1[2] + a2[2];
+  F[3] = Ia[3] + a3[0]; F[4] = Ia[4] + a3[1]; F[5] = Ia[5] + a3[2];
+}
+
+template <class TK, class TV> struct SeqState {
+  TK R[9], r[3];
+  TV V[6], At[6];   // spatial velocity; total acceleration Va + bias (gravity folded in)
+};
+
+// Tangent of the inverse-dynamics residual along input direction `seed` (0..25: q entry, 26..50: v entry),
+// t[j] = -d g_j, for the state x (raw, 51 entries) and the fixed primal acceleration a (25 entries).
+template <class TK, class TV>
+H1_DEV void id_tangent_seq(const DynModel& md, const double* __restrict__ x, const double* __restrict__ a, int seed,
+                           double* __restrict__ t) {
+  SeqState<TK, TV> cur, saved[SEQ_MAXSAVE];
+  TK Sst[6][6];      // motion subspaces of the bodies on the current root->body path, by depth
+  TV spst[6];        // S_b . C_{b-1} of the same bodies
+  TK Vab[6];         // J a of the base body (spatial acceleration without bias)
+  {
+    TK qr[4], qn[4];
+    for (int i = 0; i < 4; ++i) qr[i] = seeded<TK>(x[3 + i], seed == 3 + i, 0.0);
+    quat_normalize(qr, qn);
+    quat_to_mat(qn, cur.R);
+  }
+  cur.r[0] = cur.r[1] = cur.r[2] = TK(0.0);
+  {
+    const TV wb[3] = {seeded<TV>(x[NQ + 3], seed == NQ + 3, 0.0), seeded<TV>(x[NQ + 4], seed == NQ + 4, 0.0),
+                      seeded<TV>(x[NQ + 5], seed == NQ + 5, 0.0)};
+    for (int i = 0; i < 3; ++i) {
+      cur.V[i] = cur.R[3 * i] * wb[0] + cur.R[3 * i + 1] * wb[1] + cur.R[3 * i + 2] * wb[2];
+      Vab[i] = cur.R[3 * i] * a[3] + cur.R[3 * i + 1] * a[4] + cur.R[3 * i + 2] * a[5];
+      cur.V[3 + i] = seeded<TV>(x[NQ + i], seed == NQ + i, 0.0);
+      Vab[3 + i] = TK(a[i]);
+    }
+    TV vxw[3];
+    cross_m(cur.V + 3, cur.V, vxw);
+    for (int i = 0; i < 3; ++i) {
+      cur.At[i] = TV(Vab[i]);
+      cur.At[3 + i] = Vab[3 + i] + vxw[i] - md.gravity[i];
+    }
+  }
+  saved[0] = cur;
+  TV F0[6];
+  {
+    TK I[10];
+    body_inertia_seq(md, 0, cur.R, cur.r, I);
+    body_wrench_seq(I, cur.V, cur.At, F0);
+  }
+  const TK qz = seeded<TK>(x[2], seed == 2, 0.0);
+  TV C[6];
+  for (int i = 0; i < 6; ++i) C[i] = TV(0.0);
+#pragma unroll 1
+  for (int b = 1; b < NB; ++b) {
+    const int d = md.depth[b];
+    if (md.parent[b] != b - 1) cur = saved[d - 1];
+    {
+      const double* p = md.pos[b];
+      cur.r[0] += cur.R[0] * p[0] + cur.R[1] * p[1] + cur.R[2] * p[2];
+      cur.r[1] += cur.R[3] * p[0] + cur.R[4] * p[1] + cur.R[5] * p[2];
+      cur.r[2] += cur.R[6] * p[0] + cur.R[7] * p[1] + cur.R[8] * p[2];
+      if (md.has_rfix[b]) {
+        const double* Fx = md.rfix[b];
+        TK Tm[9];
+        for (int i = 0; i < 3; ++i)
+          for (int k = 0; k < 3; ++k)
+            Tm[3 * i + k] = cur.R[3 * i] * Fx[k] + cur.R[3 * i + 1] * Fx[3 + k] + cur.R[3 * i + 2] * Fx[6 + k];
+        for (int i = 0; i < 9; ++i) cur.R[i] = Tm[i];
+      }
+    }
+    TK S[6];
+    {
+      TK sn, cs;
+      sincos_t(seeded<TK>(x[6 + b], seed == 6 + b, 0.0), &sn, &cs);
+      const int ax = md.axis[b];
+      rot_right(cur.R, ax, sn, cs);
+      col_of(cur.R, ax, S);
+      cross_m(cur.r, S, S + 3);
+    }
+    {
+      const TV vj = seeded<TV>(x[NQ + 5 + b], seed == NQ + 5 + b, 0.0);
+      const double aj = a[5 + b];
+      for (int i = 0; i < 6; ++i) cur.V[i] += S[i] * vj;
+      TV c1[3], c2[3], c3[3];
+      cross_m(cur.V, S, c1); cross_m(cur.V, S + 3, c2); cross_m(cur.V + 3, S, c3);
+      for (int i = 0; i < 3; ++i) {
+        cur.At[i] += S[i] * aj + c1[i] * vj;
+        cur.At[3 + i] += S[3 + i] * aj + (c2[i] + c3[i]) * vj;
+      }
+    }
+    if (md.nchild[b] > 1) saved[d] = cur;   // build_dyn_model guarantees d < SEQ_MAXSAVE for branch bodies
+    for (int i = 0; i < 6; ++i) Sst[d][i] = S[i];
+    spst[d] = S[0] * C[0] + S[1] * C[1] + S[2] * C[2] + S[3] * C[3] + S[4] * C[4] + S[5] * C[5];
+    TV F[6];
+    {
+      TK I[10];
+      body_inertia_seq(md, b, cur.R, cur.r, I);
+      body_wrench_seq(I, cur.V, cur.At, F);
+    }
+    for (int f = 0; f < H1_NFOOT; ++f) {
+      if (b != md.foot_body[f]) continue;
+      TK Va[6];
+      for (int i = 0; i < 6; ++i) Va[i] = Vab[i];
+      for (int dd = 1; dd <= d; ++dd) {
+        const double aa = a[5 + md.anc_body[b][dd]];
+        for (int i = 0; i < 6; ++i) Va[i] += Sst[dd][i] * aa;
+      }
+      const double h = md.h;
+#pragma unroll 1
+      for (int c = 0; c < H1_NCP; ++c) {
+        const double* pt = md.foot_pts[f * H1_NCP + c];
+        const TK rho[3] = {cur.r[0] + cur.R[0] * pt[0] + cur.R[1] * pt[1] + cur.R[2] * pt[2],
+                           cur.r[1] + cur.R[3] * pt[0] + cur.R[4] * pt[1] + cur.R[5] * pt[2],
+                           cur.r[2] + cur.R[6] * pt[0] + cur.R[7] * pt[1] + cur.R[8] * pt[2]};
+        TV t1[3]; TK t2[3];
+        cross_m(cur.V, rho, t1);
+        cross_m(Va, rho, t2);
+        const TV pd[3] = {cur.V[3] + t1[0], cur.V[4] + t1[1], cur.V[5] + t1[2]};
+        const TK pa[3] = {Va[3] + t2[0], Va[4] + t2[1], Va[5] + t2[2]};
+        const TK dd_ = -(qz + rho[2]);
+        const TK root = sqrt_t(dd_ * dd_ + md.eps * md.eps);
+        const TK sp = 0.5 * (dd_ + root), al = 0.5 * (1.0 + dd_ / root);
+        TV Fc[3];
+        Fc[0] = -(al * md.bt) * (pd[0] + h * pa[0]);
+        Fc[1] = -(al * md.bt) * (pd[1] + h * pa[1]);
+        Fc[2] = md.kn * sp - al * ((md.bn + h * md.kn) * pd[2] + (h * md.bn + h * h * md.kn) * pa[2]);
+        TV n[3];
+        cross_m(rho, Fc, n);
+        for (int i = 0; i < 3; ++i) { F[i] -= n[i]; F[3 + i] -= Fc[i]; }
+      }
+    }
+    for (int i = 0; i < 6; ++i) C[i] += F[i];
+    // dofs whose subtree ends at this body
+    for (int dd = d; dd >= 1; --dd) {
+      const int bb = md.anc_body[b][dd];
+      if (md.chain_end[bb] != b) break;
+      const TV g = Sst[dd][0] * C[0] + Sst[dd][1] * C[1] + Sst[dd][2] * C[2] + Sst[dd][3] * C[3] + Sst[dd][4] * C[4] +
+                   Sst[dd][5] * C[5] - spst[dd];
+      t[5 + bb] = -(tangent_of(g) + ((seed == NQ + 5 + bb) ? md.damping[5 + bb] : 0.0));
+    }
+  }
+  // base dofs: S_i = e_i (linear) for i < 3, [R_base e_{i-3}; 0] for the body-frame angular dofs
+  for (int i = 0; i < 6; ++i) C[i] += F0[i];
+  for (int i = 0; i < 3; ++i) {
+    t[i] = -(tangent_of(C[3 + i]) + ((seed == NQ + i) ? md.damping[i] : 0.0));
+    const TK* R = saved[0].R;
+    const TV g = R[i] * C[0] + R[3 + i] * C[1] + R[6 + i] * C[2];
+    t[3 + i] = -(tangent_of(g) + ((seed == NQ + 3 + i) ? md.damping[3 + i] : 0.0));
+  }
+}
+
+// Mhat adot = t with the primal factor Mhat = L^T D L (unit-lower rows Lm[k][slot], branch-sparse); in place.
+H1_DEV void tangent_solve_seq(const DynModel& md, const double* __restrict__ Lm, const double* __restrict__ D,
+                              double* __restrict__ t) {
+#pragma unroll 1
+  for (int k = NV - 1; k >= 1; --k) {
+    const int n = md.nlist[k];
+    const double tk = t[k];
+    for (int s = 0; s < n - 1; ++s) t[md.alist[k][s]] -= Lm[k * MAXSLOT + s] * tk;
+  }
+#pragma unroll 1
+  for (int k = 0; k < NV; ++k) {
+    const int n = md.nlist[k];
+    double ad = t[k] / D[k];
+    for (int s = 0; s < n - 1; ++s) ad -= Lm[k * MAXSLOT + s] * t[md.alist[k][s]];
+    t[k] = ad;
+  }
+}
+
+// Column of d x_next / d(input) from adot (tangent of the semi-implicit Euler step + quaternion exponential).
+// seed: 0..50 state entry, >= 51 control. col: 51 entries, stride 1.
+H1_DEV void integrate_tangent_seq(const DynModel& md, const double* __restrict__ x, const double* __restrict__ a,
+                                  int seed, const double* __restrict__ adot, double* __restrict__ col) {
+  const double h = md.h;
+  for (int j = 0; j < NV; ++j) {
+    const double vnd = ((seed == NQ + j) ? 1.0 : 0.0) + h * adot[j];
+    col[NQ + j] = vnd;
+    if (j < 3) col[j] = ((seed == j) ? 1.0 : 0.0) + h * vnd;
+    else if (j >= 6) col[j + 1] = ((seed == j + 1) ? 1.0 : 0.0) + h * vnd;
+  }
+  Dual q[4], wn[3], qo[4];
+  for (int i = 0; i < 4; ++i) q[i] = Dual(x[3 + i], (seed == 3 + i) ? 1.0 : 0.0);
+  for (int i = 0; i < 3; ++i)
+    wn[i] = Dual(x[NQ + 3 + i] + h * a[3 + i], ((seed == NQ + 3 + i) ? 1.0 : 0.0) + h * adot[3 + i]);
+  quat_step(q, wn, h, qo);
+  for (int i = 0; i < 4; ++i) col[3 + i] = qo[i].d;
+}
+
+}  // namespace h1

@@ -45,6 +45,8 @@ struct H1Ilqr {
   cudaEvent_t ev[2] = {nullptr, nullptr};
   int launches = 0;
   size_t smem_lina = 0;
+  int policy = H1ILQR_KERNELS_AUTO;
+  long lin_dirs_min_knots = 64;  // AUTO: B*N at or above which the column-per-thread linearization is used
   size_t smem_dyn4 = 0, smem_lin = 0, smem_cq = 0, smem_ls = 0, smem_ric = 0;
 };
 
@@ -199,6 +201,11 @@ int h1ilqr_set_reference_window(H1Ilqr* h, const double* x_ref, const double* u_
 }
 
 // ---------------- stage launchers (no host sync) ----------------
+static bool use_batched(const H1Ilqr* h, long units, long auto_min_units) {
+  if (h->policy == H1ILQR_KERNELS_COOPERATIVE) return false;
+  if (h->policy == H1ILQR_KERNELS_BATCHED) return true;
+  return units >= auto_min_units;
+}
 static void launch_rollout(H1Ilqr* h, const int* mask, const double* x0_dev, int t_begin, double* cost_out,
                            bool keep_factors = false) {
   const int wpb = 4, blocks = (h->B + wpb - 1) / wpb;
@@ -214,6 +221,16 @@ static void launch_linearize(H1Ilqr* h, const int* mask, bool factors_ready = fa
       const long warps = (long)h->B * h->N;
       k_primal_factor<<<(int)((warps + 3) / 4), 128, h->smem_dyn4, h->stream>>>(h->d_dyn, h->B, h->N, h->xbar, h->ubar, h->pf);
       LAUNCHED();
+    }
+    const long knots = (long)h->B * h->N;
+    if (use_batched(h, knots, h->lin_dirs_min_knots)) {  // one thread per column
+      const size_t sm = ((sizeof(DynModel) + 15) / 16) * 16;
+      auto blocks = [&](int nd) { return (unsigned)((knots * nd + LIND_THREADS - 1) / LIND_THREADS); };
+      k_linearize_dirs<0><<<blocks(NQ), LIND_THREADS, sm, h->stream>>>(h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm);
+      k_linearize_dirs<1><<<blocks(NV), LIND_THREADS, sm, h->stream>>>(h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm);
+      k_linearize_dirs<2><<<blocks(NU), LIND_THREADS, sm, h->stream>>>(h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm);
+      h->launches += 3;
+      return;
     }
     k_linearize_analytic<<<h->B * h->N, LINA_WARPS * 32, h->smem_lina, h->stream>>>(h->d_dyn, h->N, mask, h->xbar, h->ubar,
                                                                                  h->pf, h->A, h->Bm);
@@ -599,6 +616,12 @@ int h1ilqr_get_solve_trace(H1Ilqr* h, double* cost_trace, int* alpha_trace) {
   if (cost_trace) D2H(cost_trace, h->cost_trace, SZ(h->opt.max_iterations) * sizeof(double));
   if (alpha_trace) D2H(alpha_trace, h->alpha_trace, SZ(h->opt.max_iterations * 2) * sizeof(int));
   SYNC(); return 0;
+}
+int h1ilqr_set_kernel_policy(H1Ilqr* h, int policy) {
+  GUARD(h);
+  if (policy < H1ILQR_KERNELS_AUTO || policy > H1ILQR_KERNELS_BATCHED) return set_err(H1ILQR_EARG, "bad kernel policy");
+  h->policy = policy;
+  return 0;
 }
 int h1ilqr_enable_stage_timing(H1Ilqr* h, int enable) { GUARD(h); h->timing = enable != 0; return 0; }
 int h1ilqr_get_stage_times(H1Ilqr* h, H1StageTimes* t) {

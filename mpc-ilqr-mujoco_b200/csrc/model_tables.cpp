@@ -77,6 +77,9 @@ bool build_dyn_model(const H1Model& m, DynModel* d) {
   for (int b = 1; b < NB; ++b)
     if (m.parent[b] == 0) { d->base_child_slot[b] = d->n_base_children++; }
   if (d->n_base_children > 4) return false;
+  for (int b = 1; b < NB; ++b) d->nchild[m.parent[b]]++;
+  for (int b = 1; b < NB; ++b)
+    if (d->nchild[b] > 1 && d->depth[b] >= 3) return false;  // SEQ_MAXSAVE (h1_lin_dirs.cuh)
   return true;
 }
 

@@ -23,9 +23,11 @@ EXPORTS = [
     "h1ilqr_reference_kinematics", "h1ilqr_set_trajectory", "h1ilqr_get_trajectory", "h1ilqr_get_gains",
     "h1ilqr_set_gains", "h1ilqr_get_linearization", "h1ilqr_set_linearization", "h1ilqr_get_cost_quadratics",
     "h1ilqr_set_cost_quadratics", "h1ilqr_get_regularization", "h1ilqr_set_regularization", "h1ilqr_get_solve_trace",
-    "h1ilqr_upload_inputs", "h1ilqr_run_resident_steps", "h1ilqr_measure_fp64_peak", "h1ilqr_enable_stage_timing", "h1ilqr_get_stage_times", "h1ilqr_stream", "h1_default_dynamics_model",
+    "h1ilqr_upload_inputs", "h1ilqr_run_resident_steps", "h1ilqr_measure_fp64_peak", "h1ilqr_enable_stage_timing", "h1ilqr_set_kernel_policy", "h1ilqr_get_stage_times", "h1ilqr_stream", "h1_default_dynamics_model",
     "h1_default_cost_model",
 ]
+
+KERNELS_AUTO, KERNELS_COOPERATIVE, KERNELS_BATCHED = 0, 1, 2
 
 _lib = None
 
@@ -273,6 +275,10 @@ class H1IlqrBatch:
     def get_costs(self):
         """Final cost / iterations / status of the last solve (device -> host)."""
         return self.solve_trace()
+
+    def set_kernel_policy(self, policy):
+        """KERNELS_AUTO (0), KERNELS_COOPERATIVE (1: warp per unit, latency) or KERNELS_BATCHED (2: thread per unit)."""
+        _check(lib().h1ilqr_set_kernel_policy(self._h, C.c_int(int(policy))))
 
     def enable_stage_timing(self, flag=True):
         _check(lib().h1ilqr_enable_stage_timing(self._h, C.c_int(int(flag))))

@@ -2,6 +2,7 @@
 // suite: the phase functions are compiled as plain C++ and the 32 lanes of a phase run one after another.
 // This checks the kernel's index tables / sparse factorisation logic without a GPU; it is not a product path.
 #include "../../mpc-ilqr-mujoco_b200/csrc/h1_dyn.cuh"
+#include "../../mpc-ilqr-mujoco_b200/csrc/h1_lin_dirs.cuh"
 #include "../../mpc-ilqr-mujoco_b200/csrc/model_tables.h"
 
 extern "C" int emul_dyn_step(int n, const double* x, const double* u, double* xn, double* com) {
@@ -43,5 +44,28 @@ extern "C" int emul_dyn_linearize_id(const double* x, const double* u, double* A
   h1::dyn_primal_factor_warp(md, w, x, u, nullptr, pf);
   for (int e = 0; e < h1::NX + h1::NU; ++e)
     h1::dyn_tangent_id_warp(md, wt, pf, x, u, e, e < h1::NX ? A + e * h1::NX : B + (e - h1::NX) * h1::NX);
+  return 0;
+}
+
+// same columns through the direction-per-thread functions (csrc/h1_lin_dirs.cuh, kernel k_linearize_dirs)
+extern "C" int emul_dyn_linearize_dirs(const double* x, const double* u, double* A, double* B) {
+  static h1::DynModel md;
+  static bool init = false;
+  if (!init) { if (!h1::build_dyn_model(*h1_default_dynamics_model(), &md)) return -1; init = true; }
+  static h1::DynWarp w;
+  static h1::PrimalFactor pf;
+  h1::dyn_primal_factor_warp(md, w, x, u, nullptr, pf);
+  for (int e = 0; e < h1::NX + h1::NU; ++e) {
+    double tv[h1::NV];
+    if (e < h1::NQ) h1::id_tangent_seq<h1::Dual, h1::Dual>(md, x, pf.a, e, tv);
+    else if (e < h1::NX) h1::id_tangent_seq<double, h1::Dual>(md, x, pf.a, e, tv);
+    else {
+      const int j = e - h1::NX;
+      for (int k = 0; k < h1::NV; ++k) tv[k] = 0.0;
+      tv[6 + j] = (u[j] < md.ctrl_lo[j] || u[j] > md.ctrl_hi[j]) ? 0.0 : 1.0;
+    }
+    h1::tangent_solve_seq(md, &pf.Lm[0][0], pf.D, tv);
+    h1::integrate_tangent_seq(md, x, pf.a, e, tv, e < h1::NX ? A + e * h1::NX : B + (e - h1::NX) * h1::NX);
+  }
   return 0;
 }

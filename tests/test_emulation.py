@@ -50,6 +50,19 @@ def test_tangent_linearization_matches_oracle_ad(emul, oracle):
         assert np.abs(Be - B).max() <= 1e-10 * np.abs(B).max()
 
 
+def test_direction_per_thread_linearization_matches_oracle_ad(emul, oracle):
+    """csrc/h1_lin_dirs.cuh (one thread per column, sequential DFS walk with cumulative wrenches) against the
+    oracle's forward-mode AD through its dense f_D: 1e-10 relative, incl. clamped torques, raw quaternions."""
+    x, u = states(12, 4)
+    u[::3, 3] = 400.0
+    for i in range(12):
+        A, B = oracle.dyn_linearize_ad(x[i], u[i])
+        Ae = np.empty((51, 51), order="F"); Be = np.empty((51, 19), order="F")
+        assert emul[0].emul_dyn_linearize_dirs(P(x[i]), P(u[i]), P(Ae), P(Be)) == 0
+        assert np.abs(Ae - A).max() <= 1e-10 * np.abs(A).max()
+        assert np.abs(Be - B).max() <= 1e-10 * np.abs(B).max()
+
+
 @pytest.mark.parametrize("tag", ["standing", "walking"])
 def test_cost_quadratics_phases_match_oracle(emul, oracle, tag):
     s, w, win = make_oracle(tag)

@@ -60,11 +60,15 @@ def test_bias_and_reference_kinematics(gpu, oracle):
         assert np.abs(ee[i, 1] - oracle.dyn_body_pos(x[i], 10)).max() < 1e-13
 
 
-def _setup_pair(gpu, tag, N=25, batch=1, t0=0, lin=0):
+POLICIES = [1, 2]  # KERNELS_COOPERATIVE (warp per unit), KERNELS_BATCHED (thread per unit)
+
+
+def _setup_pair(gpu, tag, N=25, batch=1, t0=0, lin=0, policy=0):
     so, w, win = make_oracle(tag, N=N, t0=t0, linearization=lin)
     opt = gpu.default_options()
     opt.linearization = lin
     sg = gpu.H1IlqrBatch(w, N=N, batch=batch, options=opt)
+    sg.set_kernel_policy(policy)
     sg.set_reference_window(*win, shared=True)
     return so, sg, win
 
@@ -102,11 +106,12 @@ def test_linearize_fd_parity(gpu, oracle):
     assert np.abs(A[0] - Ao).max() < 2e-7 and np.abs(B[0] - Bo).max() < 2e-7
 
 
-def test_linearize_analytic_parity(gpu, oracle):
+@pytest.mark.parametrize("policy", POLICIES)
+def test_linearize_analytic_parity(gpu, oracle, policy):
     """Analytic mode (default): exact A_k = df_D/dx, B_k = df_D/du. GPU tangent propagation with a shared
     factorisation vs the oracle's forward-mode AD through its own dense f_D: 1e-9 relative on A and on B
     separately (BASELINE.json), per knot. Includes clamped torques and un-normalised quaternions."""
-    so, sg, win = _setup_pair(gpu, "walking", lin=0)
+    so, sg, win = _setup_pair(gpu, "walking", lin=0, policy=policy)
     x0 = win[0][3].copy()
     x0[3:7] *= 1.02
     rng = np.random.default_rng(16)
@@ -189,12 +194,13 @@ def test_line_search_parity(gpu, oracle):
     assert rel(xg[0], so.get("xbar")) < 1e-9 and rel(ug[0], so.get("ubar")) < 1e-9
 
 
+@pytest.mark.parametrize("policy", POLICIES)
 @pytest.mark.parametrize("tag,lin", [("standing", 0), ("walking", 0), ("standing", 1)])
-def test_solve_parity(gpu, oracle, tag, lin):
+def test_solve_parity(gpu, oracle, tag, lin, policy):
     """Full iLQR::solve: identical accept/reject decisions, per-iteration cost and final x/u within 1e-6
     relative. lin=1 runs the reference's forward-difference linearization on both sides; its FD noise
     (see test_linearize_fd_parity) propagates to ~1e-5 on the controls, hence the looser bound there."""
-    so, sg, win = _setup_pair(gpu, tag, lin=lin)
+    so, sg, win = _setup_pair(gpu, tag, lin=lin, policy=policy)
     x0 = standing_state()
     ug = grav_comp_guess(x0)
     so.initialize(x0, False, ug)
@@ -232,8 +238,10 @@ def test_mpc_closed_loop_parity(gpu, oracle):
     assert np.abs(xg - xo).max() < 1e-6
 
 
-def test_batch_equals_looped_single(gpu, oracle):
-    """Independent instances: a batch must reproduce the per-instance single solves bit for bit."""
+@pytest.mark.parametrize("policy", POLICIES)
+def test_batch_equals_looped_single(gpu, oracle, policy):
+    """Independent instances: a batch must reproduce the per-instance single solves bit for bit (same kernel
+    family on both sides; AUTO would pick the family by batch size)."""
     cfg = Config(); w = cfg.build_weights()
     refs = reference_set("walking")
     win = refs.window(0, 25)
@@ -242,11 +250,13 @@ def test_batch_equals_looped_single(gpu, oracle):
     x0 = perturbed_states(standing_state(), B, seed=0, jnt_range=jr)
     ug = grav_comp_guess(standing_state())
     sb = gpu.H1IlqrBatch(w, N=25, batch=B)
+    sb.set_kernel_policy(policy)
     sb.set_reference_window(*win, shared=True)
     sb.initialize(x0, None, ug)
     cb, ib, _ = sb.solve(x0)
     xb, ub = sb.get_trajectory()
     s1 = gpu.H1IlqrBatch(w, N=25, batch=1)
+    s1.set_kernel_policy(policy)
     s1.set_reference_window(*win, shared=True)
     for i in range(B):
         s1.set_regularization(1e-6)
@@ -260,6 +270,38 @@ def test_batch_equals_looped_single(gpu, oracle):
     so.initialize(x0[0], False, ug)
     co = so.solve(x0[0])
     assert abs(cb[0] - co) / abs(co) < 1e-6
+
+
+def test_kernel_families_agree(gpu, oracle):
+    """COOPERATIVE and BATCHED kernels compute the same numbers (different operation order only): stage by stage
+    on a 37-instance walking batch with per-instance windows."""
+    w = Config().build_weights()
+    refs = reference_set("walking")
+    B = 37
+    wins = [refs.window(3 * i, 25) for i in range(B)]
+    win = tuple(np.stack([wi[k] for wi in wins]) for k in range(6))
+    jr = np.array(gpu.default_dynamics_model().jnt_range)
+    x0 = np.stack([wi[0][0] for wi in wins]) + (perturbed_states(standing_state(), B, seed=3, jnt_range=jr) - standing_state())
+    x0[:, 3:7] /= np.linalg.norm(x0[:, 3:7], axis=1, keepdims=True)
+    ug = grav_comp_guess(standing_state())
+    out = []
+    for policy in POLICIES:
+        s = gpu.H1IlqrBatch(w, N=25, batch=B)
+        s.set_kernel_policy(policy)
+        s.set_reference_window(*win, shared=False)
+        s.initialize(x0, None, ug)
+        s.rollout_nominal(x0); s.linearize(); s.cost_quadratics(); s.backward_pass()
+        ok, c, a = s.line_search(x0)
+        out.append((s.get_linearization(), s.get_cost_quadratics(), s.get_gains(), s.get_trajectory(), c, a))
+    (A1, B1), cq1, (K1, k1), (x1, u1), c1, a1 = out[0]
+    (A2, B2), cq2, (K2, k2), (x2, u2), c2, a2 = out[1]
+    for i in range(B):
+        for t in range(25):
+            assert rel(A2[i, t], A1[i, t]) < 1e-10 and rel(B2[i, t], B1[i, t]) < 1e-10, (i, t)
+    for p, q in zip(cq1, cq2):
+        assert rel(q, p) < 1e-10
+    assert rel(K2, K1) < 1e-7 and rel(k2, k1) < 1e-7
+    assert (a1 == a2).all() and rel(c2, c1) < 1e-9 and rel(x2, x1) < 1e-8 and rel(u2, u1) < 1e-8
 
 
 def test_horizon_sweep(gpu, oracle):
