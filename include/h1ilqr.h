@@ -171,6 +171,8 @@ int h1ilqr_run_resident_steps(H1Ilqr* h, int steps, int cold_each_step, double* 
 /* sustained fp64 FMA throughput of the device (TFLOP/s), measured with a register-resident DFMA kernel: the
  * FP64 roofline denominator (MEASURED_PEAKS.json carries none). */
 int h1ilqr_measure_fp64_peak(H1Ilqr* h, double* tflops);
+/* same for the fp64 tensor-core path (mma.sync m8n8k4, SASS DMMA) used by the Riccati contractions. */
+int h1ilqr_measure_fp64_mma_peak(H1Ilqr* h, double* tflops);
 
 /* ---- timing of the last h1ilqr_solve, CUDA events on the handle's stream, milliseconds ---- */
 typedef struct H1StageTimes {

@@ -4,8 +4,17 @@
 //   LLT test on Quu (+1e-4 I once on failure, quirk Q9), K = -Quu^-1 Qxu', k = -Quu^-1 Qu (LDLT with
 //   largest-|diagonal| pivoting like Eigen::LDLT), Vx = Qx + K'Quu k + K'Qu + Qxu k,
 //   Vxx = sym(Qxx + K'QuuK + K'Qxu' + Qxu K).
-// The two large products share W = Vxx [A|B] (51x70): [Qxx|Qxu] = A' W, Quu = B' W[:,51:].
-// fp64 FMA register-tiled GEMMs on shared-memory operands (4x4 micro-tiles).
+// Contractions (all on the fp64 tensor cores, mma.sync m8n8k4 = SASS DMMA, operands in shared memory):
+//   G1  W = Vxx [A|B]                       51x70x51      (W is shared by the next two)
+//   G2  [Qxx|Qxu] = A' W                    51x70x51
+//   G3  Quu = B' W[:,51:]                   19x19x51
+//   G4  G = Quu K + 2 Qxu'                  19x51x19
+//   G5  M = Qxx + K' G                      51x51x19      sym(M) == sym(Qxx + K'QuuK + K'Qxu' + QxuK)
+// (K'Qxu' and QxuK are transposes of each other, so their sum inside the symmetrisation equals sym(2 K'Qxu');
+// no algebraic cancellation is assumed, only the order of additions differs from the reference.)
+// Shared memory per CTA is 107 KB so that TWO instances are resident per SM: while one is in its sequential
+// section (pivoted LDLT, triangular solves) the other one keeps the tensor pipe busy.
+// Leading dimensions are = 4 (mod 8) doubles: every m8n8k4 fragment load is bank-conflict free.
 #pragma once
 #include "h1_common.cuh"
 
@@ -13,57 +22,25 @@ namespace h1 {
 
 constexpr int RIC_THREADS = 256;
 constexpr int NXU = NX + NU;  // 70
-
-// C(m x n) = op(A) * B with op(A) = A^T if TA (A stored k x m) else A (m x k); column-major, shared memory.
-template <bool TA>
-__device__ __forceinline__ void gemm_smem(int m, int n, int k, const double* __restrict__ A, int lda,
-                                          const double* __restrict__ B, int ldb, double* __restrict__ C, int ldc) {
-  const int tm = (m + 3) >> 2, tn = (n + 3) >> 2;
-  for (int tile = threadIdx.x; tile < tm * tn; tile += blockDim.x) {
-    const int ti = tile % tm, tj = tile / tm;
-    const int i0 = ti * 4, j0 = tj * 4;
-    int ri[4], cj[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) { ri[r] = min(i0 + r, m - 1); cj[r] = min(j0 + r, n - 1); }
-    double acc[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
-    for (int kk = 0; kk < k; ++kk) {
-      double a[4], b[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) a[r] = TA ? A[ri[r] * lda + kk] : A[kk * lda + ri[r]];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) b[c] = B[cj[c] * ldb + kk];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (i0 + r < m && j0 + c < n) C[(j0 + c) * ldc + i0 + r] = acc[r][c];
-  }
-}
+constexpr int LDX = 52;       // leading dimension of 51-row operands (row 51 is a zero pad: k runs to 52)
+constexpr int LDU = 20;       // leading dimension of 19-row operands (row 19 is a zero pad: k runs to 20)
 
 struct RiccatiSmem {
-  double Vxx[NX * NX];
-  double AB[NX * NXU];     // [A | B] of the current knot; refilled with the next knot's by cp.async
-  double W[NX * NXU];      // Vxx [A | B]; later reused as scratch (QuuK, Qxu K)
-  double Qx_[NX * NXU];    // [Qxx | Qxu]
-  double Lnext[NX * NX];   // lxx of the next knot (cp.async prefetch)
-  double T1[NX * NX];      // K' Quu K
-  double Quu[NU * NU];
-  double Lf[NU * NU];      // permuted Quu, reduced in place to its Schur complements
-  double Ls[NU * NU];      // unit-lower factor of the permuted LDL^T
-  double Kt[NU * (NX + 1)];// solves: columns 0..50 -> K(:,j), column 51 -> kff
-  double Vx[NX], Qx[NX], Qu[NU], D[NU], tmp[NX];
+  double V[LDX * LDX];        // Vxx (pad row/column zero); from G2 on: Qxx, then M, then the next Vxx
+  double AB[LDX * NXU];       // [A | B] of the current knot, refilled by cp.async after G2/G3
+  double W[LDX * NXU];        // Vxx [A | B]; after G2/G3: G (LDU x 51) followed by the prefetched lxx (51 x 51 dense)
+  double Qxu[LDX * NU];
+  double Kt[LDU * 56];        // solves: columns 0..50 -> K(:,j), column 51 -> kff; pad row 19 stays zero
+  double Quu[LDU * LDU];      // pad row/column 19 stay zero
+  double Lf[NU * NU];         // permuted Quu, reduced in place to its Schur complements
+  double Ls[NU * NU];         // unit-lower factor of the permuted LDL^T
+  double Vx[NX], Qx[NX], Qu[NU], D[NU], tmp[NU];
   int perm[NU];
   int not_pd;
 };
+constexpr int RIC_G_OFF = 0;              // G inside W
+constexpr int RIC_LXX_OFF = LDU * NX;     // prefetched lxx inside W (dense, ld 51)
+static_assert(RIC_LXX_OFF + NX * NX <= LDX * NXU, "lxx prefetch must fit behind G");
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -71,6 +48,36 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
 }
 __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+// D(8x8) += A(8x4) B(4x8) on the fp64 tensor core. Lane l holds A[l/4][l%4], B[l%4][l/4], C[l/4][2(l%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// One warp accumulates an 8 x (8 NT) strip: acc[j] += sum_k A(m0 + g, k) B(k, n0 + 8 j + g'), k < 4 ksteps.
+// fa(row, k) / fb(k, col) return operand elements (they implement padding / clamping).
+template <int NT, class FA, class FB>
+__device__ __forceinline__ void mma_strip(int ksteps, int m0, int n0, FA fa, FB fb, double (&acc)[NT][2]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll 1
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const int k = 4 * ks + t;
+    const double a = fa(m0 + g, k);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) dmma884(acc[j][0], acc[j][1], a, fb(k, n0 + 8 * j + g));
+  }
+}
+
+// Zero-initialised strip + epilogue st(row, col, value) for every element of the 8 x (8 NT) strip.
+template <int NT, class FA, class FB, class ST>
+__device__ __forceinline__ void mma_strip_store(int ksteps, int m0, int n0, FA fa, FB fb, ST st) {
+  double acc[NT][2];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = 0.0;
+  mma_strip<NT>(ksteps, m0, n0, fa, fb, acc);
+  const int lane = threadIdx.x & 31, r = m0 + (lane >> 2), c0 = n0 + 2 * (lane & 3);
+#pragma unroll
+  for (int j = 0; j < NT; ++j) { st(r, c0 + 8 * j, acc[j][0]); st(r, c0 + 8 * j + 1, acc[j][1]); }
 }
 
 // LDL^T of Quu with symmetric pivoting by largest |diagonal| (Eigen::LDLT's selection rule), one warp,
@@ -80,17 +87,17 @@ __device__ __forceinline__ void quu_ldlt(RiccatiSmem& s) {
   const int lane = threadIdx.x;  // warp 0 only
   const int n = NU;
   if (lane < n) {  // rank of |Q_ii| in descending order, ties by index
-    const double di = fabs(s.Quu[lane * n + lane]);
+    const double di = fabs(s.Quu[lane * LDU + lane]);
     int rank = 0;
     for (int j = 0; j < n; ++j) {
-      const double dj = fabs(s.Quu[j * n + j]);
+      const double dj = fabs(s.Quu[j * LDU + j]);
       rank += (dj > di) || (dj == di && j < lane);
     }
     s.perm[rank] = lane;
   }
   if (lane == 0) s.not_pd = 0;
   __syncwarp();
-  for (int e = lane; e < n * n; e += 32) { const int i = e % n, j = e / n; s.Lf[e] = s.Quu[s.perm[j] * n + s.perm[i]]; }
+  for (int e = lane; e < n * n; e += 32) { const int i = e % n, j = e / n; s.Lf[e] = s.Quu[s.perm[j] * LDU + s.perm[i]]; }
   __syncwarp();
   for (int k = 0; k < n; ++k) {
     const double d = s.Lf[k * n + k];
@@ -105,7 +112,7 @@ __device__ __forceinline__ void quu_ldlt(RiccatiSmem& s) {
   }
 }
 
-__global__ void __launch_bounds__(RIC_THREADS)
+__global__ void __launch_bounds__(RIC_THREADS, 2)
 k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambda, const double* __restrict__ A,
            const double* __restrict__ Bm, const double* __restrict__ lx, const double* __restrict__ lu,
            const double* __restrict__ lxx, const double* __restrict__ luu, double* __restrict__ K,
@@ -115,115 +122,192 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
   const int inst = blockIdx.x;
   if (mask && !mask[inst]) return;
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
   const double lam = lambda[inst];
   const double* lxN = lx + ((size_t)inst * (N + 1) + N) * NX;
   const double* lxxN = lxx + ((size_t)inst * (N + 1) + N) * NX * NX;
-  auto prefetch = [&](int t) {  // A_t, B_t -> s.AB ; lxx_t -> s.Lnext  (8-byte async copies)
-    const double* At = A + ((size_t)inst * N + t) * NX * NX;
+  auto prefetch_ab = [&](int t) {  // A_t, B_t -> s.AB (8-byte async copies; global columns are only 8-byte aligned)
+    const double* At = A + ((size_t)inst * N + t) * NX * NX;      // [A_t | B_t] are NOT contiguous in global memory
     const double* Bt = Bm + ((size_t)inst * N + t) * NX * NU;
-    const double* Lt = lxx + ((size_t)inst * (N + 1) + t) * NX * NX;
-    for (int i = tid; i < NX * NX; i += nt) { cp_async8(&s.AB[i], At + i); cp_async8(&s.Lnext[i], Lt + i); }
-    for (int i = tid; i < NX * NU; i += nt) cp_async8(&s.AB[NX * NX + i], Bt + i);
+    for (int i = tid; i < NX * NX; i += nt) { const int c = i / NX, r = i - c * NX; cp_async8(&s.AB[c * LDX + r], At + i); }
+    for (int i = tid; i < NX * NU; i += nt) { const int c = i / NX, r = i - c * NX; cp_async8(&s.AB[(NX + c) * LDX + r], Bt + i); }
   };
-  prefetch(N - 1);
+  // zero pads (never written afterwards) and the terminal value function
+  for (int i = tid; i < LDX * LDX; i += nt) s.V[i] = 0.0;
+  for (int i = tid; i < NXU; i += nt) s.AB[i * LDX + NX] = 0.0;
+  for (int i = tid; i < LDU * 56; i += nt) s.Kt[i] = 0.0;
+  for (int i = tid; i < LDU * LDU; i += nt) s.Quu[i] = 0.0;
+  __syncthreads();
+  prefetch_ab(N - 1);
   for (int i = tid; i < NX; i += nt) s.Vx[i] = lxN[i];
-  for (int i = tid; i < NX * NX; i += nt) s.Vxx[i] = lxxN[i];
+  for (int i = tid; i < NX * NX; i += nt) { const int c = i / NX, r = i - c * NX; s.V[c * LDX + r] = lxxN[i]; }
   bool nonfinite = false;
+  double* const G = s.W + RIC_G_OFF;
+  double* const Lpre = s.W + RIC_LXX_OFF;
   for (int t = N - 1; t >= 0; --t) {
     const double* lxt = lx + ((size_t)inst * (N + 1) + t) * NX;
     const double* lut = lu + ((size_t)inst * N + t) * NU;
     const double* luut = luu + ((size_t)inst * N + t) * NU * NU;
     cp_async_commit_wait_all();
     __syncthreads();
-    // W = Vxx [A|B]
-    gemm_smem<false>(NX, NXU, NX, s.Vxx, NX, s.AB, NX, s.W, NX);
-    // Qx = lx + A'Vx, Qu = lu + B'Vx
-    for (int i = tid; i < NXU; i += nt) {
-      double acc = 0.0;
-      const double* col = s.AB + i * NX;
-      for (int l = 0; l < NX; ++l) acc += col[l] * s.Vx[l];
-      if (i < NX) s.Qx[i] = lxt[i] + acc; else s.Qu[i - NX] = lut[i - NX] + acc;
+    // ---- G1: W = Vxx [A|B] (warps 0..6: one 8-row strip each) | warp 7: Qx = lx + A'Vx, Qu = lu + B'Vx ----
+    if (warp < 7) {
+      mma_strip_store<9>(13, 8 * warp, 0,
+                         [&](int r, int k) { return r < LDX ? s.V[k * LDX + r] : 0.0; },
+                         [&](int k, int c) { return c < NXU ? s.AB[c * LDX + k] : 0.0; },
+                         [&](int r, int c, double v) { if (r < LDX && c < NXU) s.W[c * LDX + r] = v; });   // row 51 of W = 0
+    } else {
+      for (int i = lane; i < NXU; i += 32) {
+        double acc = 0.0;
+        const double* col = s.AB + i * LDX;
+        for (int l = 0; l < NX; ++l) acc += col[l] * s.Vx[l];
+        if (i < NX) s.Qx[i] = lxt[i] + acc; else s.Qu[i - NX] = lut[i - NX] + acc;
+      }
     }
     __syncthreads();
-    // [Qxx | Qxu] = A' W ; Quu = B' W[:, 51:]
-    gemm_smem<true>(NX, NXU, NX, s.AB, NX, s.W, NX, s.Qx_, NX);
-    gemm_smem<true>(NU, NU, NX, s.AB + NX * NX, NX, s.W + NX * NX, NX, s.Quu, NU);
+    // ---- G2: [Qxx | Qxu] = A' W (warps 0..6; Qxx -> s.V, Qxu -> s.Qxu) | G3 (warp 7): Quu = B' W_B + luu + lam I ----
+    if (warp < 7) {
+      mma_strip_store<9>(13, 8 * warp, 0,
+                         [&](int r, int k) { return s.AB[r * LDX + k]; },   // A'(r,k) = A(k,r); rows 51..55: discarded garbage
+                         [&](int k, int c) { return c < NXU ? s.W[c * LDX + k] : 0.0; },
+                         [&](int r, int c, double v) {
+                           if (r >= NX) return;
+                           if (c < NX) s.V[c * LDX + r] = v;
+                           else if (c < NXU) s.Qxu[(c - NX) * LDX + r] = v;
+                         });
+    } else {
+      auto fa = [&](int r, int k) { return s.AB[(NX + min(r, NU - 1)) * LDX + k]; };
+      auto fb = [&](int k, int c) { return s.W[(NX + min(c, NU - 1)) * LDX + k]; };
+#pragma unroll 1
+      for (int mi = 0; mi < 3; ++mi)
+        mma_strip_store<3>(13, 8 * mi, 0, fa, fb, [&](int r, int c, double v) {
+          if (r < NU && c < NU) s.Quu[c * LDU + r] = v + luut[c * NU + r] + ((c == r) ? lam : 0.0);
+        });
+    }
     __syncthreads();
-    for (int i = tid; i < NX * NX; i += nt) s.Qx_[i] += s.Lnext[i];
-    for (int i = tid; i < NU * NU; i += nt) s.Quu[i] += luut[i] + ((i % NU == i / NU) ? lam : 0.0);
-    __syncthreads();
-    if (t > 0) prefetch(t - 1);   // s.AB / s.Lnext are free from here on; overlaps the factorisation and solves
+    // s.AB and s.W are free: prefetch the next knot's [A|B] and this knot's lxx (consumed by the final pass)
+    if (t > 0) prefetch_ab(t - 1);
+    {
+      const double* Lt = lxx + ((size_t)inst * (N + 1) + t) * NX * NX;
+      for (int i = tid; i < NX * NX; i += nt) cp_async8(&Lpre[i], Lt + i);
+    }
     if (tid < 32) {
       quu_ldlt(s);
       if (s.not_pd) {             // Eigen::LLT failed: Quu += 1e-4 I once, no re-check (quirk Q9), refactor
-        for (int i = tid; i < NU; i += 32) s.Quu[i * NU + i] += 1e-4;
+        for (int i = tid; i < NU; i += 32) s.Quu[i * LDU + i] += 1e-4;
         __syncwarp();
         quu_ldlt(s);
       }
     }
     __syncthreads();
-    // solves: rhs r < 51 -> column r of Qxu' (= row r of Qxu), rhs 51 -> Qu ; result negated
+    // ---- solves: rhs r < 51 -> column r of Qxu' (= row r of Qxu), rhs 51 -> Qu ; result negated ----
     if (tid <= NX) {
       const int r = tid;
       double y[NU];
 #pragma unroll
       for (int i = 0; i < NU; ++i) {
         const int pi = s.perm[i];
-        y[i] = (r < NX) ? s.Qx_[(NX + pi) * NX + r] : s.Qu[pi];
+        y[i] = (r < NX) ? s.Qxu[pi * LDX + r] : s.Qu[pi];
       }
 #pragma unroll
-      for (int i = 0; i < NU; ++i)
+      for (int i = 0; i < NU; ++i)        // forward substitution (critical path: one FMA per row)
 #pragma unroll
         for (int c = 0; c < i; ++c) y[i] -= s.Ls[c * NU + i] * y[c];
 #pragma unroll
       for (int i = 0; i < NU; ++i) y[i] = (fabs(s.D[i]) > 2.2250738585072014e-308) ? y[i] / s.D[i] : 0.0;
 #pragma unroll
-      for (int i = NU - 1; i >= 0; --i)
+      for (int i = NU - 1; i >= 0; --i)   // back substitution with L^T
 #pragma unroll
-        for (int c = i + 1; c < NU; ++c) y[i] -= s.Ls[i * NU + c] * y[c];
+        for (int c = NU - 1; c > i; --c) y[i] -= s.Ls[i * NU + c] * y[c];
 #pragma unroll
       for (int i = 0; i < NU; ++i) {
         const double v = -y[i];
         if (!isfinite(v)) nonfinite = true;
-        s.Kt[r * NU + s.perm[i]] = v;
+        s.Kt[r * LDU + s.perm[i]] = v;
       }
     }
     __syncthreads();
-    // write gains (K column-major 19x51 == Kt columns 0..50; kff = column 51)
-    double* Kt_g = K + ((size_t)inst * N + t) * NU * NX;
-    double* kf_g = kff + ((size_t)inst * N + t) * NU;
-    for (int i = tid; i < NU * NX; i += nt) Kt_g[i] = s.Kt[i];
-    for (int i = tid; i < NU; i += nt) kf_g[i] = s.Kt[NX * NU + i];
-    // QuuK (19x51) and Qxu K (51x51) into W scratch, Quu k into tmp
-    double* QuuK = s.W;
-    double* T3 = s.W + NU * NX;
-    gemm_smem<false>(NU, NX, NU, s.Quu, NU, s.Kt, NU, QuuK, NU);
-    gemm_smem<false>(NX, NX, NU, s.Qx_ + NX * NX, NX, s.Kt, NU, T3, NX);
-    if (tid < NU) {
+    // ---- gains to global | G4: G = Quu K + 2 Qxu' (warps 0..6: one 8-column strip each) | warp 7: tmp = Quu k ----
+    {
+      double* Kt_g = K + ((size_t)inst * N + t) * NU * NX;
+      double* kf_g = kff + ((size_t)inst * N + t) * NU;
+      for (int i = tid; i < NU * NX; i += nt) { const int c = i / NU, r = i - c * NU; Kt_g[i] = s.Kt[c * LDU + r]; }
+      for (int i = tid; i < NU; i += nt) kf_g[i] = s.Kt[NX * LDU + i];
+    }
+    if (warp < 7) {
+      const int n0 = 8 * warp;
+      auto fa = [&](int r, int k) { return r < LDU ? s.Quu[k * LDU + r] : 0.0; };
+      auto fb = [&](int k, int c) { return s.Kt[c * LDU + k]; };
+#pragma unroll 1
+      for (int mi = 0; mi < 3; ++mi) {
+        const int r = 8 * mi + g;
+        double acc[1][2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int c = n0 + 2 * t4 + q;
+          acc[0][q] = (r < NU && c < NX) ? 2.0 * s.Qxu[r * LDX + c] : 0.0;
+        }
+        mma_strip<1>(5, 8 * mi, n0, fa, fb, acc);
+        if (r < LDU) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int c = n0 + 2 * t4 + q;
+            if (c < NX) G[c * LDU + r] = acc[0][q];
+          }
+        }
+      }
+    } else if (lane < NU) {
       double acc = 0.0;
-      for (int l = 0; l < NU; ++l) acc += s.Quu[l * NU + tid] * s.Kt[NX * NU + l];
-      s.tmp[tid] = acc;
+      for (int l = 0; l < NU; ++l) acc += s.Quu[l * LDU + lane] * s.Kt[NX * LDU + l];
+      s.tmp[lane] = acc;
     }
     __syncthreads();
-    // Vx = Qx + K'(Quu k) + K'Qu + Qxu k ;  T1 = K' (Quu K)
-    if (tid < NX) {
-      double a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      for (int l = 0; l < NU; ++l) {
-        const double kli = s.Kt[tid * NU + l];
-        a1 += kli * s.tmp[l]; a2 += kli * s.Qu[l]; a3 += s.Qx_[(NX + l) * NX + tid] * s.Kt[NX * NU + l];
+    // ---- G5: M = Qxx + K' G in place in s.V (warps 0..6) | warp 7: Vx = Qx + K'(Quu k) + K'Qu + Qxu k ----
+    if (warp < 7) {
+      const int m0 = 8 * warp;
+      auto fa = [&](int r, int k) { return s.Kt[r * LDU + k]; };       // K'(r,k) = K(k,r); rows 51..55: kff / zeros, discarded
+      auto fb = [&](int k, int c) { return c < NX ? G[c * LDU + k] : 0.0; };
+      const int r = m0 + g;
+      double acc[7][2];
+#pragma unroll
+      for (int j = 0; j < 7; ++j)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int c = 8 * j + 2 * t4 + q;
+          acc[j][q] = (r < NX && c < NX) ? s.V[c * LDX + r] : 0.0;
+        }
+      mma_strip<7>(5, m0, 0, fa, fb, acc);
+      if (r < NX) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int c = 8 * j + 2 * t4 + q;
+            if (c < NX) s.V[c * LDX + r] = acc[j][q];
+          }
       }
-      s.Vx[tid] = s.Qx[tid] + a1 + a2 + a3;
+    } else {
+      for (int i = lane; i < NX; i += 32) {
+        double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        for (int l = 0; l < NU; ++l) {
+          const double kli = s.Kt[i * LDU + l];
+          a1 += kli * s.tmp[l]; a2 += kli * s.Qu[l]; a3 += s.Qxu[l * LDX + i] * s.Kt[NX * LDU + l];
+        }
+        s.Vx[i] = s.Qx[i] + a1 + a2 + a3;
+      }
     }
-    gemm_smem<true>(NX, NX, NU, s.Kt, NU, QuuK, NU, s.T1, NX);
+    cp_async_commit_wait_all();   // lxx_t (and the next [A|B]) have landed
     __syncthreads();
-    // Vxx = sym(Qxx + K'QuuK + (QxuK)' + QxuK)
+    // ---- Vxx = sym(lxx + M), one thread per (i >= j) pair ----
     for (int e = tid; e < NX * NX; e += nt) {
-      const int i = e % NX, j = e / NX, et = i * NX + j;
-      const double tij = s.Qx_[e] + s.T1[e] + T3[et] + T3[e];
-      const double tji = s.Qx_[et] + s.T1[et] + T3[e] + T3[et];
-      s.Vxx[e] = 0.5 * (tij + tji);
+      const int j = e / NX, i = e - j * NX;
+      if (i < j) continue;
+      const double mij = s.V[j * LDX + i] + Lpre[j * NX + i];
+      const double mji = s.V[i * LDX + j] + Lpre[i * NX + j];
+      const double v = 0.5 * (mij + mji);
+      s.V[j * LDX + i] = v; s.V[i * LDX + j] = v;
     }
-    __syncthreads();
+    // (the __syncthreads at the top of the next iteration orders these writes before G1)
   }
   if (nonfinite && status) status[inst] = 1;
 }

@@ -46,7 +46,7 @@ struct H1Ilqr {
   int launches = 0;
   size_t smem_lina = 0;
   int policy = H1ILQR_KERNELS_AUTO;
-  long lin_dirs_min_knots = 64;  // AUTO: B*N at or above which the column-per-thread linearization is used
+  long lin_dirs_min_knots = 0;   // AUTO: B*N at or above which the column-per-thread linearization is used (faster at every size measured)
   size_t smem_dyn4 = 0, smem_lin = 0, smem_cq = 0, smem_ls = 0, smem_ric = 0;
 };
 
@@ -445,6 +445,45 @@ int h1ilqr_measure_fp64_peak(H1Ilqr* h, double* tflops) {
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, e0, e1));
     const double fl = 2.0 * 8.0 * (double)iters * threads * blocks;
+    if (rep > 0) best = fmax(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *tflops = best;
+  return 0;
+}
+
+// fp64 tensor-core peak: mma.sync m8n8k4 (SASS DMMA), 8 independent accumulator chains per warp
+__global__ void k_dmma_peak(double* out, int iters) {
+  double c[8][2];
+  for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x * 1e-9 + i; c[i][1] = 0.5 * i; }
+  const double a = 1.0000001, b = 0.9999999;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                   : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  if (s == 12345.678) out[0] = s;
+}
+int h1ilqr_measure_fp64_mma_peak(H1Ilqr* h, double* tflops) {
+  GUARD(h);
+  if (!tflops) return set_err(H1ILQR_EARG, "null tflops");
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, h->device));
+  const int blocks = prop.multiProcessorCount * 4, threads = 256, iters = 1 << 14;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CU(cudaEventRecord(e0, h->stream));
+    k_dmma_peak<<<blocks, threads, 0, h->stream>>>(h->scratch, iters);
+    CU(cudaEventRecord(e1, h->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 256.0 * 8.0 * (double)iters * (threads / 32) * blocks;   // 8x8x4 FMAs per mma
     if (rep > 0) best = fmax(best, fl / (ms * 1e-3) / 1e12);
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);

@@ -272,6 +272,11 @@ class H1IlqrBatch:
         _check(lib().h1ilqr_measure_fp64_peak(self._h, C.byref(t)))
         return t.value
 
+    def measure_fp64_mma_peak(self):
+        t = C.c_double()
+        _check(lib().h1ilqr_measure_fp64_mma_peak(self._h, C.byref(t)))
+        return t.value
+
     def get_costs(self):
         """Final cost / iterations / status of the last solve (device -> host)."""
         return self.solve_trace()
