@@ -32,11 +32,9 @@ struct RiccatiSmem {
   double Qxu[LDX * NU];
   double Kt[LDU * 56];        // solves: columns 0..50 -> K(:,j), column 51 -> kff; pad row 19 stays zero
   double Quu[LDU * LDU];      // pad row/column 19 stay zero
-  double Lf[NU * NU];         // permuted Quu, reduced in place to its Schur complements
   double Ls[NU * NU];         // unit-lower factor of the permuted LDL^T
   double Vx[NX], Qx[NX], Qu[NU], D[NU], tmp[NU];
   int perm[NU];
-  int not_pd;
 };
 constexpr int RIC_G_OFF = 0;              // G inside W
 constexpr int RIC_LXX_OFF = LDU * NX;     // prefetched lxx inside W (dense, ld 51)
@@ -80,12 +78,13 @@ __device__ __forceinline__ void mma_strip_store(int ksteps, int m0, int n0, FA f
   for (int j = 0; j < NT; ++j) { st(r, c0 + 8 * j, acc[j][0]); st(r, c0 + 8 * j + 1, acc[j][1]); }
 }
 
-// LDL^T of Quu with symmetric pivoting by largest |diagonal| (Eigen::LDLT's selection rule), one warp,
-// right-looking: after step k, row i holds the Schur complement. Sets not_pd when a pivot is <= 0, which for
-// a symmetric matrix is equivalent to Eigen::LLT reporting failure (Sylvester's law of inertia).
-__device__ __forceinline__ void quu_ldlt(RiccatiSmem& s) {
-  const int lane = threadIdx.x;  // warp 0 only
-  const int n = NU;
+// LDL^T of Quu with symmetric pivoting by largest |diagonal| (Eigen::LDLT's selection rule), ONE warp, right-
+// looking, register resident: lane i holds row i of the permuted matrix (lower triangle), column k of the
+// current Schur complement is broadcast with shuffles. Writes perm, D, Ls (unit-lower factor). Returns true when
+// a pivot is <= 0, which for a symmetric matrix is equivalent to Eigen::LLT reporting failure (Sylvester).
+__device__ __forceinline__ bool quu_ldlt(RiccatiSmem& s) {
+  const int lane = threadIdx.x & 31;
+  constexpr int n = NU;
   if (lane < n) {  // rank of |Q_ii| in descending order, ties by index
     const double di = fabs(s.Quu[lane * LDU + lane]);
     int rank = 0;
@@ -95,21 +94,31 @@ __device__ __forceinline__ void quu_ldlt(RiccatiSmem& s) {
     }
     s.perm[rank] = lane;
   }
-  if (lane == 0) s.not_pd = 0;
   __syncwarp();
-  for (int e = lane; e < n * n; e += 32) { const int i = e % n, j = e / n; s.Lf[e] = s.Quu[s.perm[j] * LDU + s.perm[i]]; }
-  __syncwarp();
+  const int li = min(lane, n - 1);
+  const int pr = s.perm[li];
+  double p[n];
+#pragma unroll
+  for (int c = 0; c < n; ++c) p[c] = s.Quu[s.perm[c] * LDU + pr];
+  bool not_pd = false;
+#pragma unroll
   for (int k = 0; k < n; ++k) {
-    const double d = s.Lf[k * n + k];
-    if (lane == 0) { s.D[k] = d; if (!(d > 0.0)) s.not_pd = 1; }
-    if (lane > k && lane < n) {
-      const double pik = s.Lf[k * n + lane];                       // P(i,k)
-      const double lik = (fabs(d) > 0.0) ? pik / d : 0.0;
-      for (int c = k + 1; c <= lane; ++c) s.Lf[c * n + lane] -= lik * s.Lf[k * n + c];   // P(i,c) -= l_ik P(c,k)
-      s.Ls[k * n + lane] = lik;   // separate array: column k of Lf is still being read by the other lanes
+    const double d = __shfl_sync(0xffffffffu, p[k], k);
+    if (!(d > 0.0)) not_pd = true;
+    if (lane == 0) s.D[k] = d;
+    const double pik = p[k];                                           // P(i,k) of this lane's row
+    const double lik = (fabs(d) > 0.0) ? pik / d : 0.0;
+#pragma unroll
+    for (int c = 1; c < n; ++c) {
+      if (c <= k) continue;                                            // (constant trip counts: both loops unroll fully)
+      const double pck = __shfl_sync(0xffffffffu, pik, c);             // P(c,k)
+      const double upd = p[c] - lik * pck;                             // P(i,c) -= l_ik P(c,k)
+      p[c] = (c <= lane) ? upd : p[c];                                 // select form keeps p[] in registers
     }
-    __syncwarp();
+    if (lane > k && lane < n) s.Ls[k * n + lane] = lik;
   }
+  __syncwarp();
+  return not_pd;
 }
 
 __global__ void __launch_bounds__(RIC_THREADS, 2)
@@ -165,7 +174,18 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
       }
     }
     __syncthreads();
-    // ---- G2: [Qxx | Qxu] = A' W (warps 0..6; Qxx -> s.V, Qxu -> s.Qxu) | G3 (warp 7): Quu = B' W_B + luu + lam I ----
+    // ---- G3: Quu = B' W_B + luu + lam I, 9 tiles over the 8 warps (first, so that its factorisation overlaps G2) ----
+    {
+      auto fa = [&](int r, int k) { return s.AB[(NX + min(r, NU - 1)) * LDX + k]; };
+      auto fb = [&](int k, int c) { return s.W[(NX + min(c, NU - 1)) * LDX + k]; };
+#pragma unroll 1
+      for (int tile = warp; tile < 9; tile += 8)
+        mma_strip_store<1>(13, 8 * (tile / 3), 8 * (tile % 3), fa, fb, [&](int r, int c, double v) {
+          if (r < NU && c < NU) s.Quu[c * LDU + r] = v + luut[c * NU + r] + ((c == r) ? lam : 0.0);
+        });
+    }
+    __syncthreads();
+    // ---- G2: [Qxx | Qxu] = A' W (warps 0..6; Qxx -> s.V, Qxu -> s.Qxu) | warp 7: pivoted LDL^T of Quu ----
     if (warp < 7) {
       mma_strip_store<9>(13, 8 * warp, 0,
                          [&](int r, int k) { return s.AB[r * LDX + k]; },   // A'(r,k) = A(k,r); rows 51..55: discarded garbage
@@ -176,13 +196,11 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
                            else if (c < NXU) s.Qxu[(c - NX) * LDX + r] = v;
                          });
     } else {
-      auto fa = [&](int r, int k) { return s.AB[(NX + min(r, NU - 1)) * LDX + k]; };
-      auto fb = [&](int k, int c) { return s.W[(NX + min(c, NU - 1)) * LDX + k]; };
-#pragma unroll 1
-      for (int mi = 0; mi < 3; ++mi)
-        mma_strip_store<3>(13, 8 * mi, 0, fa, fb, [&](int r, int c, double v) {
-          if (r < NU && c < NU) s.Quu[c * LDU + r] = v + luut[c * NU + r] + ((c == r) ? lam : 0.0);
-        });
+      if (quu_ldlt(s)) {          // Eigen::LLT failed: Quu += 1e-4 I once, no re-check (quirk Q9), refactor
+        for (int i = lane; i < NU; i += 32) s.Quu[i * LDU + i] += 1e-4;
+        __syncwarp();
+        quu_ldlt(s);
+      }
     }
     __syncthreads();
     // s.AB and s.W are free: prefetch the next knot's [A|B] and this knot's lxx (consumed by the final pass)
@@ -191,39 +209,50 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
       const double* Lt = lxx + ((size_t)inst * (N + 1) + t) * NX * NX;
       for (int i = tid; i < NX * NX; i += nt) cp_async8(&Lpre[i], Lt + i);
     }
-    if (tid < 32) {
-      quu_ldlt(s);
-      if (s.not_pd) {             // Eigen::LLT failed: Quu += 1e-4 I once, no re-check (quirk Q9), refactor
-        for (int i = tid; i < NU; i += 32) s.Quu[i * LDU + i] += 1e-4;
-        __syncwarp();
-        quu_ldlt(s);
-      }
-    }
-    __syncthreads();
-    // ---- solves: rhs r < 51 -> column r of Qxu' (= row r of Qxu), rhs 51 -> Qu ; result negated ----
-    if (tid <= NX) {
-      const int r = tid;
-      double y[NU];
+    // ---- solves, 4 threads per right-hand side (rows i = q, q+4, ...): rhs r < 51 -> row r of Qxu, rhs 51 -> Qu;
+    //      column-oriented substitutions, the finished entry is broadcast inside the 4-lane group; result negated.
+    //      Per row the updates are applied in the same order as a row-oriented substitution. ----
+    if (warp < 7) {
+      const int q = tid & 3, r = min(tid >> 2, NX);
+      const bool valid = (tid >> 2) <= NX;
+      double y[5];
 #pragma unroll
-      for (int i = 0; i < NU; ++i) {
-        const int pi = s.perm[i];
-        y[i] = (r < NX) ? s.Qxu[pi * LDX + r] : s.Qu[pi];
+      for (int m = 0; m < 5; ++m) {
+        const int i = q + 4 * m;
+        const int pi = s.perm[min(i, NU - 1)];
+        y[m] = (i < NU) ? ((r < NX) ? s.Qxu[pi * LDX + r] : s.Qu[pi]) : 0.0;
       }
 #pragma unroll
-      for (int i = 0; i < NU; ++i)        // forward substitution (critical path: one FMA per row)
+      for (int c = 0; c < NU - 1; ++c) {        // forward substitution with the unit-lower L
+        const double yc = __shfl_sync(0xffffffffu, y[c >> 2], c & 3, 4);
 #pragma unroll
-        for (int c = 0; c < i; ++c) y[i] -= s.Ls[c * NU + i] * y[c];
+        for (int m = 0; m < 5; ++m) {
+          const int i = q + 4 * m;
+          if (4 * m + 3 > c && i > c && i < NU) y[m] -= s.Ls[c * NU + i] * yc;
+        }
+      }
 #pragma unroll
-      for (int i = 0; i < NU; ++i) y[i] = (fabs(s.D[i]) > 2.2250738585072014e-308) ? y[i] / s.D[i] : 0.0;
+      for (int m = 0; m < 5; ++m) {
+        const int i = min(q + 4 * m, NU - 1);
+        y[m] = (fabs(s.D[i]) > 2.2250738585072014e-308) ? y[m] / s.D[i] : 0.0;
+      }
 #pragma unroll
-      for (int i = NU - 1; i >= 0; --i)   // back substitution with L^T
+      for (int c = NU - 1; c >= 1; --c) {       // back substitution with L^T
+        const double xc = __shfl_sync(0xffffffffu, y[c >> 2], c & 3, 4);
 #pragma unroll
-        for (int c = NU - 1; c > i; --c) y[i] -= s.Ls[i * NU + c] * y[c];
+        for (int m = 0; m < 5; ++m) {
+          const int i = q + 4 * m;
+          if (4 * m < c && i < c) y[m] -= s.Ls[i * NU + c] * xc;
+        }
+      }
 #pragma unroll
-      for (int i = 0; i < NU; ++i) {
-        const double v = -y[i];
-        if (!isfinite(v)) nonfinite = true;
-        s.Kt[r * LDU + s.perm[i]] = v;
+      for (int m = 0; m < 5; ++m) {
+        const int i = q + 4 * m;
+        if (valid && i < NU) {
+          const double v = -y[m];
+          if (!isfinite(v)) nonfinite = true;
+          s.Kt[r * LDU + s.perm[i]] = v;
+        }
       }
     }
     __syncthreads();
