@@ -23,7 +23,7 @@ EXPORTS = [
     "h1ilqr_reference_kinematics", "h1ilqr_set_trajectory", "h1ilqr_get_trajectory", "h1ilqr_get_gains",
     "h1ilqr_set_gains", "h1ilqr_get_linearization", "h1ilqr_set_linearization", "h1ilqr_get_cost_quadratics",
     "h1ilqr_set_cost_quadratics", "h1ilqr_get_regularization", "h1ilqr_set_regularization", "h1ilqr_get_solve_trace",
-    "h1ilqr_upload_inputs", "h1ilqr_run_resident_steps", "h1ilqr_measure_fp64_peak", "h1ilqr_enable_stage_timing", "h1ilqr_set_kernel_policy", "h1ilqr_get_stage_times", "h1ilqr_stream", "h1_default_dynamics_model",
+    "h1ilqr_upload_inputs", "h1ilqr_run_resident_steps", "h1ilqr_measure_fp64_peak", "h1ilqr_measure_fp64_mma_peak", "h1ilqr_enable_stage_timing", "h1ilqr_set_kernel_policy", "h1ilqr_get_stage_times", "h1ilqr_stream", "h1_default_dynamics_model",
     "h1_default_cost_model",
 ]
 
