@@ -48,6 +48,7 @@ struct DynModel {
   int n_base_children;
   int pad_;
   int nchild[NB];            // number of child bodies (branch bodies keep their state in the sequential walks)
+  int seq_ok;                // 1: the tree has H1's chain structure the thread-sequential f_D (h1_dyn_seq.cuh) is specialised for
 };
 
 // Same tree for the cost (URDF / Pinocchio-semantics) model; only what the cost kernel reads.

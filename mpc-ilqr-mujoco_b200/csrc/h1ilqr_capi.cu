@@ -3,6 +3,7 @@
 // There is no CPU fallback anywhere in this library: every entry point runs CUDA kernels on the handle's
 // device or returns H1ILQR_ECUDA.
 #include "h1_kernels_solve.cuh"
+#include "h1_kernels_seq.cuh"
 #include "h1_riccati.cuh"
 #include "model_tables.h"
 #include <cuda_runtime.h>
@@ -46,6 +47,9 @@ struct H1Ilqr {
   int launches = 0;
   size_t smem_lina = 0;
   int policy = H1ILQR_KERNELS_AUTO;
+  int seq_min_batch = 64;   // AUTO: batch at or above which rollouts / line searches run one THREAD per f_D evaluation (h1_dyn_seq.cuh)
+  size_t smem_seq = 0;
+  bool seq_ok = false;      // the model has the chain structure the thread-sequential f_D is specialised for
   long lin_dirs_min_knots = 0;   // AUTO: B*N at or above which the column-per-thread linearization is used (faster at every size measured)
   size_t smem_dyn4 = 0, smem_lin = 0, smem_cq = 0, smem_ls = 0, smem_ric = 0;
 };
@@ -109,6 +113,7 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
       !build_cost_model(cost_model ? *cost_model : *h1_default_cost_model(), &cm)) {
     delete h; return set_err(H1ILQR_EARG, "model is not a DFS-ordered H1-like tree");
   }
+  h->seq_ok = dm.seq_ok != 0;
 #define CUH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(H1ILQR_ECUDA, #call, e_); h1ilqr_destroy(h); return H1ILQR_ECUDA; } } while (0)
   CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CUH(cudaEventCreate(&h->ev[0])); CUH(cudaEventCreate(&h->ev[1]));
@@ -149,6 +154,7 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   h->smem_cq = cml + CQ_WARPS * sizeof(CostWarp);
   h->smem_ls = mdl + H1ILQR_NALPHA * sizeof(DynWarp) + (H1ILQR_NALPHA + H1ILQR_NALPHA * (NX + NU)) * sizeof(double);
   h->smem_ric = sizeof(RiccatiSmem);
+  h->smem_seq = mdl;
   CUH(cudaFuncSetAttribute(k_dyn_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
   CUH(cudaFuncSetAttribute(k_dyn_query, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
   CUH(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
@@ -208,6 +214,13 @@ static bool use_batched(const H1Ilqr* h, long units, long auto_min_units) {
 }
 static void launch_rollout(H1Ilqr* h, const int* mask, const double* x0_dev, int t_begin, double* cost_out,
                            bool keep_factors = false) {
+  if (h->seq_ok && use_batched(h, h->B, h->seq_min_batch)) {   // one thread per instance
+    k_rollout_seq<<<(h->B + SEQ_ROLL_THREADS - 1) / SEQ_ROLL_THREADS, SEQ_ROLL_THREADS, h->smem_seq, h->stream>>>(
+        h->d_dyn, h->d_w, ref_table(h), h->B, h->N, t_begin, mask, x0_dev, h->xbar, h->ubar, cost_out,
+        keep_factors ? h->pf : nullptr);
+    LAUNCHED();
+    return;
+  }
   const int wpb = 4, blocks = (h->B + wpb - 1) / wpb;
   k_rollout<<<blocks, wpb * 32, h->smem_dyn4, h->stream>>>(h->d_dyn, h->d_w, ref_table(h), h->B, h->N, t_begin, mask,
                                                           x0_dev, h->xbar, h->ubar, cost_out,
@@ -255,6 +268,14 @@ static void launch_backward(H1Ilqr* h, const int* mask) {
   LAUNCHED();
 }
 static void launch_line_search(H1Ilqr* h, const int* mask) {
+  if (h->seq_ok && use_batched(h, h->B, h->seq_min_batch)) {   // one thread per (instance, candidate)
+    const long threads = (long)h->B * H1ILQR_NALPHA;
+    k_line_search_seq<<<(unsigned)((threads + SEQ_THREADS - 1) / SEQ_THREADS), SEQ_THREADS, h->smem_seq, h->stream>>>(
+        h->d_dyn, h->d_w, h->d_opt, ref_table(h), h->B, h->N, mask, h->x0, h->nominal_cost, h->xbar, h->ubar, h->K, h->kff,
+        h->xnew, h->unew, h->ls_ok, h->ls_cost, h->ls_alpha);
+    LAUNCHED();
+    return;
+  }
   k_line_search<<<h->B, H1ILQR_NALPHA * 32, h->smem_ls, h->stream>>>(h->d_dyn, h->d_w, h->d_opt, ref_table(h), h->N, mask,
                                                                     h->x0, h->nominal_cost, h->xbar, h->ubar, h->K, h->kff,
                                                                     h->xnew, h->unew, h->ls_ok, h->ls_cost, h->ls_alpha);

@@ -80,6 +80,18 @@ bool build_dyn_model(const H1Model& m, DynModel* d) {
   for (int b = 1; b < NB; ++b) d->nchild[m.parent[b]]++;
   for (int b = 1; b < NB; ++b)
     if (d->nchild[b] > 1 && d->depth[b] >= 3) return false;  // SEQ_MAXSAVE (h1_lin_dirs.cuh)
+  // thread-sequential f_D (h1_dyn_seq.cuh): specialised for base + two 5-hinge leg chains ending in the feet
+  // (bodies 1-5, 6-10) + torso (11) + two 4-hinge arm chains below the torso (12-15, 16-19)
+  {
+    bool ok = d->foot_body[0] == 5 && d->foot_body[1] == 10;
+    for (int b = 1; b < NB && ok; ++b) {
+      int want = b - 1;
+      if (b == 1 || b == 6 || b == 11) want = 0;
+      if (b == 12 || b == 16) want = 11;
+      ok = m.parent[b] == want;
+    }
+    d->seq_ok = ok ? 1 : 0;
+  }
   return true;
 }
 

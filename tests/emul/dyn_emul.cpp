@@ -3,7 +3,9 @@
 // This checks the kernel's index tables / sparse factorisation logic without a GPU; it is not a product path.
 #include "../../mpc-ilqr-mujoco_b200/csrc/h1_dyn.cuh"
 #include "../../mpc-ilqr-mujoco_b200/csrc/h1_lin_dirs.cuh"
+#include "../../mpc-ilqr-mujoco_b200/csrc/h1_dyn_seq.cuh"
 #include "../../mpc-ilqr-mujoco_b200/csrc/model_tables.h"
+#include <cstring>
 
 extern "C" int emul_dyn_step(int n, const double* x, const double* u, double* xn, double* com) {
   static h1::DynModel md;
@@ -67,5 +69,32 @@ extern "C" int emul_dyn_linearize_dirs(const double* x, const double* u, double*
     h1::tangent_solve_seq(md, &pf.Lm[0][0], pf.D, tv);
     h1::integrate_tangent_seq(md, x, pf.a, e, tv, e < h1::NX ? A + e * h1::NX : B + (e - h1::NX) * h1::NX);
   }
+  return 0;
+}
+
+// thread-sequential f_D (csrc/h1_dyn_seq.cuh, kernels k_rollout_seq / k_line_search_seq); also returns the factor
+// it would hand to the linearization kernels next to the warp-cooperative one, for comparison
+extern "C" int emul_dyn_step_seq(int n, const double* x, const double* u, double* xn, double* com, double* fac_seq,
+                                 double* fac_warp) {
+  static h1::DynModel md;
+  static bool init = false;
+  if (!init) { if (!h1::build_dyn_model(*h1_default_dynamics_model(), &md)) return -1; init = true; }
+  static h1::DynWarp w;
+  const int nf = sizeof(h1::PrimalFactor) / sizeof(double);
+  for (int i = 0; i < n; ++i) {
+    h1::PrimalFactor pf, pw;
+    std::memset(&pf, 0, sizeof(pf)); std::memset(&pw, 0, sizeof(pw));
+    h1::dyn_step_seq(md, x + i * h1::NX, u + i * h1::NU, xn + i * h1::NX, &pf, com + 3 * i);
+    h1::dyn_primal_factor_warp(md, w, x + i * h1::NX, u + i * h1::NU, nullptr, pw);
+    std::memcpy(fac_seq + (size_t)i * nf, &pf, sizeof(pf));
+    std::memcpy(fac_warp + (size_t)i * nf, &pw, sizeof(pw));
+  }
+  return 0;
+}
+extern "C" int emul_dyn_com_seq(int n, const double* x, double* com) {
+  static h1::DynModel md;
+  static bool init = false;
+  if (!init) { if (!h1::build_dyn_model(*h1_default_dynamics_model(), &md)) return -1; init = true; }
+  for (int i = 0; i < n; ++i) h1::dyn_com_seq(md, x + i * h1::NX, com + 3 * i);
   return 0;
 }

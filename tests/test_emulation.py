@@ -39,6 +39,26 @@ def test_lane_parallel_dynamics_matches_dense_oracle(emul, oracle):
     assert max(np.abs(com[i] - oracle.dyn_com(x[i])).max() for i in range(64)) < 1e-14
 
 
+def test_thread_sequential_dynamics_matches_dense_oracle(emul, oracle):
+    """csrc/h1_dyn_seq.cuh (one thread per f_D: single DFS walk, contact folded into the foot bodies' spatial
+    inertia / wrench, compact in-place L'DL) against the dense oracle, incl. clamped torques, feet in deep contact
+    and in the air; its factor equals the warp-cooperative one (what the linearization kernels consume)."""
+    x, u = states(96, 7)
+    u[::5, 2] = 500.0; u[1::5, 7] = -500.0
+    x[::4, 2] -= 0.08          # soles well inside the ground
+    x[1::4, 2] += 0.3          # airborne
+    xe = np.empty_like(x); com = np.empty((96, 3))
+    nf = 25 * 11 + 50
+    fs = np.zeros((96, nf)); fw = np.zeros((96, nf))
+    assert emul[0].emul_dyn_step_seq(96, P(x), P(u), P(xe), P(com), P(fs), P(fw)) == 0
+    assert np.abs(xe - oracle.dyn_step(x, u)).max() < 2e-12
+    assert max(np.abs(com[i] - oracle.dyn_com(x[i])).max() for i in range(96)) < 1e-14
+    assert np.abs(fs - fw).max() <= 1e-11 * np.abs(fw).max()
+    com2 = np.empty((96, 3))
+    assert emul[0].emul_dyn_com_seq(96, P(x), P(com2)) == 0
+    assert np.abs(com2 - com).max() < 1e-14
+
+
 def test_tangent_linearization_matches_oracle_ad(emul, oracle):
     x, u = states(12, 2)
     u[::3, 3] = 400.0

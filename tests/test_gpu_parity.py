@@ -354,8 +354,9 @@ def test_against_committed_golden_vectors(gpu):
 def test_full_size_batch_properties(gpu):
     """BASELINE-size batch (1024 standing instances, config 3): size-independent properties — every instance's
     accepted costs are non-increasing, every trajectory is dynamically consistent (a fresh rollout of the
-    returned controls reproduces the returned states bit for bit), identical instances give identical
-    results, and nothing is non-finite."""
+    returned controls reproduces the returned states: bit for bit with the warp-cooperative kernels, to rounding
+    with the thread-sequential ones, whose rollout and line-search kernels inline the same f_D source but may
+    contract multiply-adds differently), identical instances give identical results, nothing is non-finite."""
     w = Config().build_weights()
     B = 1024
     s = gpu.H1IlqrBatch(w, N=25, batch=B)
@@ -376,5 +377,13 @@ def test_full_size_batch_properties(gpu):
     assert (xg[0] == xg[1]).all() and cost[0] == cost[1]
     s.rollout_nominal(x0)
     xr, _ = s.get_trajectory()
-    assert (xr == xg).all()
+    assert np.abs(xr - xg).max() < 1e-12
+    sc = gpu.H1IlqrBatch(w, N=25, batch=64)
+    sc.set_kernel_policy(1)
+    sc.set_reference_window(*refs.window(0, 25), shared=True)
+    sc.initialize(x0[:64], None, ug)
+    sc.solve(x0[:64])
+    xc, _ = sc.get_trajectory()
+    sc.rollout_nominal(x0[:64])
+    assert (sc.get_trajectory()[0] == xc).all()
     assert np.abs(np.linalg.norm(xg[:, 1:, 3:7], axis=2) - 1).max() < 1e-12
