@@ -10,7 +10,9 @@ the walking reference from window row t0_i = i mod 374 with a perturbed initial 
   value        : solves/s with inputs resident in HBM (CUDA events on the solver's stream, max over ranks)
   e2e          : the same through the public C-ABI call h1ilqr_mpc_step with HOST buffers (pinned staging,
                  H2D of x_measured + reference windows and D2H of u_apply + cost inside the timed region)
-  roofline     : dominant kernel (linearization) against the measured HBM peak and the measured fp64 FMA peak
+  roofline     : dominant stage (analytic linearization, k_linearize_dirs<0|1|2>) against the measured HBM peak and
+                 the live-measured fp64 FMA peak; flop counts are EXECUTED fp64 operations per knot taken from ncu
+                 (profiles/), not an estimate
   cpu_baseline : the CPU oracle (a port: the reference itself cannot be built here) on this box's host cores
 `--impl reference` times that CPU oracle as the reference arm.
 """
@@ -38,7 +40,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("H1_BENCH_BATCH", "2048")), help="instances per GPU")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("H1_BENCH_BATCH", "8192")), help="instances per GPU")
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("H1_BENCH_CPU_SAMPLE", "48")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -264,9 +266,12 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         knots = float(it_s.sum()) * N_HORIZON               # linearized knots in that solve
         lin_s = tm["linearize_ms"] * 1e-3
-        alg_bytes = knots * (51 * 51 + 51 * 19 + 51 + 19) * 8.0   # A_k, B_k written; x_k, u_k read
+        # algorithmic bytes per linearized knot: A_k, B_k written; x_k, u_k and the Mhat factor (L, D, a) read
+        alg_bytes = knots * ((51 * 51 + 51 * 19 + 51 + 19) * 8.0 + FACTOR_BYTES_PER_KNOT)
         alg_flops = knots * FLOPS_PER_LINEARIZED_KNOT
         achieved = alg_bytes / lin_s / 1e9
+        bwd_passes = float(it_s.sum()) * N_HORIZON          # lower bound: second attempts add passes
+        dmma_peak = solver.measure_fp64_mma_peak()
         stage = {k: tm[k] for k in ("rollout_ms", "linearize_ms", "cost_quadratics_ms", "backward_ms", "line_search_ms")}
         # single-instance latency (BASELINE metric part 1): H1 iLQR solve ms per MPC step, N=25, one instance
         s1 = gpu.H1IlqrBatch(w, N=N_HORIZON, batch=1, device=local)
@@ -293,11 +298,21 @@ def main():
                     "api": "h1ilqr_set_reference_window + h1ilqr_mpc_step (host buffers, pinned staging)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "k_linearize_analytic", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback",
+            "roofline": {"kernel": "k_linearize_dirs<0|1|2> (analytic linearization, one thread per column of [A|B])",
+                         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": TRAFFIC_BYTES_PER_LINEARIZED_KNOT * B * N_HORIZON,
+                         "traffic_note": "ncu --set full dram read+write of the three launches of one iteration, scaled to this batch (profiles/)",
+                         "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback",
                          "share_of_step": tm["linearize_ms"] / max(tm["total_ms"], 1e-9),
+                         "note": "the stage is fp64-pipe bound, not HBM bound: see fp64",
                          "fp64": {"achieved_tflops": alg_flops / lin_s / 1e12, "peak_tflops": fp64_peak,
-                                  "frac": alg_flops / lin_s / 1e12 / max(fp64_peak, 1e-9), "peak_source": "measured live (DFMA kernel)"}},
+                                  "frac": alg_flops / lin_s / 1e12 / max(fp64_peak, 1e-9),
+                                  "flops_per_knot": FLOPS_PER_LINEARIZED_KNOT,
+                                  "peak_source": "measured live (DFMA kernel)"}},
+            "roofline_backward": {"kernel": "k_backward (Riccati, DMMA m8n8k4)", "bound": "fp64 tensor",
+                                  "achieved_tflops": bwd_passes * 1.153e6 / (tm["backward_ms"] * 1e-3) / 1e12,
+                                  "peak_tflops": dmma_peak, "peak_source": "measured live (mma.sync m8n8k4 f64 kernel)",
+                                  "note": "achieved is a lower bound (second attempts after a failed line search add passes)"},
             "stage_ms_per_solve": stage,
             "single_instance_ms_per_mpc_step": single_ms,
             "cpu_baseline": cpu,
@@ -308,9 +323,13 @@ def main():
         dist.destroy_process_group()
 
 
-# Algorithmic fp64 flop count of one linearized knot (1 primal f_D incl. factorisation + 70 tangent directions),
-# counted by tools/count_flops (op-counting scalar through the same phase functions); see DESIGN.md.
-FLOPS_PER_LINEARIZED_KNOT = 2.1e6
+# fp64 operations EXECUTED per linearized knot by k_linearize_dirs<0|1|2> (2 per DFMA, 1 per DADD / DMUL), from the
+# smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on counters of profiles/r01e_ncu_top_kernels.txt:
+# q columns 680 k + v columns 404 k + u columns 40 k.
+FLOPS_PER_LINEARIZED_KNOT = 1.12e6
+FACTOR_BYTES_PER_KNOT = (25 * 11 + 25 + 25) * 8.0
+# dram__bytes_read.sum + dram__bytes_write.sum of the same capture, per knot (9.42 GB / (4096 instances x 25 knots))
+TRAFFIC_BYTES_PER_LINEARIZED_KNOT = 92.0e3
 
 if __name__ == "__main__":
     main()

@@ -51,6 +51,13 @@ struct DynModel {
   int seq_ok;                // 1: the tree has H1's chain structure the thread-sequential f_D (h1_dyn_seq.cuh) is specialised for
 };
 
+// Compile-time copy of H1's dof tree (valid when DynModel::seq_ok): slot count of dof k and the dof id in slot s.
+// Base dofs 0-5 form a chain; dofs 6-10 / 11-15 = legs, 16 = torso, 17-20 / 21-24 = arms below the torso.
+constexpr int h1_nlist(int k) { return k < 6 ? k + 1 : (k < 16 ? 7 + (k - 6) % 5 : (k == 16 ? 7 : 8 + (k - 17) % 4)); }
+constexpr int h1_anc(int k, int s) {
+  return s < 6 ? s : (k < 16 ? 6 + 5 * ((k - 6) / 5) + (s - 6) : ((k == 16 || s == 6) ? 16 : 17 + 4 * ((k - 17) / 4) + (s - 7)));
+}
+
 // Same tree for the cost (URDF / Pinocchio-semantics) model; only what the cost kernel reads.
 struct CostModel {
   double pos[NB][3];

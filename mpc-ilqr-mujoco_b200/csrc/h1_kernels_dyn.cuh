@@ -126,8 +126,9 @@ k_linearize_fd(const DynModel* gmd, int N, double eps, const int* __restrict__ a
 
 // ---- factorisation of Mhat at every knot of the current trajectory (granular API path; inside a solve the
 //      nominal rollout produces the same factors as a by-product) ----
-__global__ void k_primal_factor(const DynModel* gmd, int B, int N, const double* __restrict__ xbar,
-                                const double* __restrict__ ubar, PrimalFactor* __restrict__ pf_out) {
+__global__ void k_primal_factor(const DynModel* gmd, int B, int N, const int* __restrict__ active,
+                                const double* __restrict__ xbar, const double* __restrict__ ubar,
+                                PrimalFactor* __restrict__ pf_out) {
   extern __shared__ __align__(16) unsigned char smem[];
   const DynModel* md;
   unsigned char* p = stage_model(smem, gmd, &md);
@@ -135,6 +136,7 @@ __global__ void k_primal_factor(const DynModel* gmd, int B, int N, const double*
   const long k = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= (long)B * N) return;
   const int inst = (int)(k / N), t = (int)(k % N);
+  if (active && !active[inst]) return;
   dyn_primal_factor_warp(*md, w, xbar + ((size_t)inst * (N + 1) + t) * NX, ubar + ((size_t)inst * N + t) * NU, nullptr,
                          pf_out[k]);
 }
@@ -177,7 +179,7 @@ k_linearize_analytic(const DynModel* gmd, int N, const int* __restrict__ active,
 //      direction classes are separate instantiations (launches) with their own register budgets.
 //      MODE 0: the 26 q columns, 1: the 25 v columns, 2: the 19 control columns. ----
 constexpr int LIND_THREADS = 128;
-template <int MODE>
+template <int MODE, bool H1TREE>   // H1TREE: the model has H1's dof tree (DynModel::seq_ok) -> static-index solve
 __global__ void __launch_bounds__(LIND_THREADS)
 k_linearize_dirs(const DynModel* gmd, long nknots, int N, const int* __restrict__ active,
                  const double* __restrict__ xbar, const double* __restrict__ ubar,
@@ -205,7 +207,8 @@ k_linearize_dirs(const DynModel* gmd, long nknots, int N, const int* __restrict_
     for (int j = 0; j < NV; ++j) tv[j] = 0.0;
     tv[6 + dir] = (uj < md->ctrl_lo[dir] || uj > md->ctrl_hi[dir]) ? 0.0 : 1.0;   // clamped torque: no sensitivity
   }
-  tangent_solve_seq(*md, &pf->Lm[0][0], pf->D, tv);
+  if (H1TREE) tangent_solve_h1(&pf->Lm[0][0], pf->D, tv);
+  else tangent_solve_seq(*md, &pf->Lm[0][0], pf->D, tv);
   double* col = (MODE == 2) ? Bm + (size_t)knot * NX * NU + (size_t)dir * NX : A + (size_t)knot * NX * NX + (size_t)seed * NX;
   integrate_tangent_seq(*md, x, pf->a, seed, tv, col);
 }

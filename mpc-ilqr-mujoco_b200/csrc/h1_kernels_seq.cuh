@@ -82,12 +82,31 @@ k_rollout_seq(const DynModel* gmd, const H1Weights* gw, RefTable refs, int B, in
   }
 }
 
+// ---- factorisation of Mhat at every knot of the current trajectory, one thread per (instance, knot): the
+//      knot-parallel replacement of the nominal rollout in iterations >= 1, where the rollout would only
+//      reproduce the trajectory the line search has just accepted (f_D is deterministic) ----
+__global__ void __launch_bounds__(SEQ_ROLL_THREADS)
+k_primal_factor_seq(const DynModel* gmd, int B, int N, const int* __restrict__ active, const double* __restrict__ xbar,
+                    const double* __restrict__ ubar, PrimalFactor* __restrict__ pf_out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const DynModel* md;
+  stage_model(smem, gmd, &md);
+  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= (long)B * N) return;
+  const int inst = (int)(k / N), t = (int)(k - (long)inst * N);
+  if (active && !active[inst]) return;
+  dyn_step_seq(*md, xbar + ((size_t)inst * (N + 1) + t) * NX, ubar + ((size_t)inst * N + t) * NU, nullptr, pf_out + k, nullptr);
+}
+
 // ---- line search, one thread per (instance, alpha candidate); the 8 candidates of an instance sit in 8
 //      adjacent lanes, the first-accept rule is a ballot, the winning trajectory is copied by the whole warp
 //      (iLQR::forwardPassLineSearch, ilqr.cpp:311-361) ----
 constexpr int SEQ_THREADS = 64;
 static_assert(H1ILQR_NALPHA == 8, "candidate groups are 8 lanes wide");
-__global__ void __launch_bounds__(SEQ_THREADS)
+#ifndef H1_SEQ_MINB
+#define H1_SEQ_MINB 4
+#endif
+__global__ void __launch_bounds__(SEQ_THREADS, H1_SEQ_MINB)
 k_line_search_seq(const DynModel* gmd, const H1Weights* gw, const H1SolverOptions* gopt, RefTable refs, int B, int N,
                   const int* __restrict__ mask, const double* __restrict__ x0, const double* __restrict__ baseline,
                   double* __restrict__ xbar, double* __restrict__ ubar, const double* __restrict__ K,

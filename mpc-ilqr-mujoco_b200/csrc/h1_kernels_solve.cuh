@@ -149,7 +149,10 @@ __global__ void k_solve_state(SolveState st, const H1SolverOptions* gopt, int B,
       for (int k = 0; k < maxit; ++k) { st.cost_trace[(size_t)i * maxit + k] = 0.0; st.alpha_trace[((size_t)i * maxit + k) * 2] = -2; st.alpha_trace[((size_t)i * maxit + k) * 2 + 1] = -2; }
     }
     st.second[i] = 0;
-    if (st.active[i]) st.prev_cost[i] = st.cost[i];
+    if (st.active[i]) {
+      st.prev_cost[i] = st.cost[i];
+      if (it > 0) st.nominal_cost[i] = st.cost[i];   // baseline of the line search: cost of the unchanged trajectory
+    }
     return;
   }
   if (!st.active[i]) return;

@@ -238,6 +238,25 @@ H1_DEV void tangent_solve_seq(const DynModel& md, const double* __restrict__ Lm,
   }
 }
 
+// Same solve with H1's dof tree compiled in (DynModel::seq_ok): every index is static, t stays in registers.
+H1_DEV void tangent_solve_h1(const double* __restrict__ Lm, const double* __restrict__ D, double* __restrict__ t) {
+#pragma unroll
+  for (int k = NV - 1; k >= 1; --k) {
+    const double tk = t[k];
+#pragma unroll
+    for (int s = 0; s < MAXSLOT - 1; ++s)
+      if (s < h1_nlist(k) - 1) t[h1_anc(k, s)] -= Lm[k * MAXSLOT + s] * tk;
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double ad = t[k] / D[k];
+#pragma unroll
+    for (int s = 0; s < MAXSLOT - 1; ++s)
+      if (s < h1_nlist(k) - 1) ad -= Lm[k * MAXSLOT + s] * t[h1_anc(k, s)];
+    t[k] = ad;
+  }
+}
+
 // Column of d x_next / d(input) from adot (tangent of the semi-implicit Euler step + quaternion exponential).
 // seed: 0..50 state entry, >= 51 control. col: 51 entries, stride 1.
 H1_DEV void integrate_tangent_seq(const DynModel& md, const double* __restrict__ x, const double* __restrict__ a,

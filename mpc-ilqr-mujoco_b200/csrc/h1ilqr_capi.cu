@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -155,6 +156,9 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   h->smem_ls = mdl + H1ILQR_NALPHA * sizeof(DynWarp) + (H1ILQR_NALPHA + H1ILQR_NALPHA * (NX + NU)) * sizeof(double);
   h->smem_ric = sizeof(RiccatiSmem);
   h->smem_seq = mdl;
+  if (const char* e = getenv("H1_SEQ_SMEM_PAD")) h->smem_seq += (size_t)atoi(e) * 1024;   // experiment: limits resident CTAs
+  CUH(cudaFuncSetAttribute(k_line_search_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_seq));
+  CUH(cudaFuncSetAttribute(k_rollout_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_seq));
   CUH(cudaFuncSetAttribute(k_dyn_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
   CUH(cudaFuncSetAttribute(k_dyn_query, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
   CUH(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
@@ -227,21 +231,34 @@ static void launch_rollout(H1Ilqr* h, const int* mask, const double* x0_dev, int
                                                           keep_factors ? h->pf : nullptr);
   LAUNCHED();
 }
-// `factors_ready`: the nominal rollout that just ran kept the per-knot factorisations of Mhat
+// Mhat factors at every knot of the current trajectory (knot-parallel)
+static void launch_factors(H1Ilqr* h, const int* mask) {
+  const long knots = (long)h->B * h->N;
+  if (h->seq_ok && use_batched(h, h->B, h->seq_min_batch)) {
+    k_primal_factor_seq<<<(unsigned)((knots + SEQ_ROLL_THREADS - 1) / SEQ_ROLL_THREADS), SEQ_ROLL_THREADS, h->smem_seq, h->stream>>>(
+        h->d_dyn, h->B, h->N, mask, h->xbar, h->ubar, h->pf);
+  } else {
+    k_primal_factor<<<(int)((knots + 3) / 4), 128, h->smem_dyn4, h->stream>>>(h->d_dyn, h->B, h->N, mask, h->xbar, h->ubar, h->pf);
+  }
+  LAUNCHED();
+}
+// `factors_ready`: the factorisations of Mhat of the current trajectory are already in h->pf
 static void launch_linearize(H1Ilqr* h, const int* mask, bool factors_ready = false) {
   if (h->opt.linearization != H1ILQR_LIN_FD) {
-    if (!factors_ready) {
-      const long warps = (long)h->B * h->N;
-      k_primal_factor<<<(int)((warps + 3) / 4), 128, h->smem_dyn4, h->stream>>>(h->d_dyn, h->B, h->N, h->xbar, h->ubar, h->pf);
-      LAUNCHED();
-    }
+    if (!factors_ready) launch_factors(h, mask);
     const long knots = (long)h->B * h->N;
     if (use_batched(h, knots, h->lin_dirs_min_knots)) {  // one thread per column
       const size_t sm = ((sizeof(DynModel) + 15) / 16) * 16;
       auto blocks = [&](int nd) { return (unsigned)((knots * nd + LIND_THREADS - 1) / LIND_THREADS); };
-      k_linearize_dirs<0><<<blocks(NQ), LIND_THREADS, sm, h->stream>>>(h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm);
-      k_linearize_dirs<1><<<blocks(NV), LIND_THREADS, sm, h->stream>>>(h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm);
-      k_linearize_dirs<2><<<blocks(NU), LIND_THREADS, sm, h->stream>>>(h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm);
+      if (h->seq_ok) {
+        k_linearize_dirs<0, true><<<blocks(NQ), LIND_THREADS, sm, h->stream>>>(h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm);
+        k_linearize_dirs<1, true><<<blocks(NV), LIND_THREADS, sm, h->stream>>>(h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm);
+        k_linearize_dirs<2, true><<<blocks(NU), LIND_THREADS, sm, h->stream>>>(h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm);
+      } else {
+        k_linearize_dirs<0, false><<<blocks(NQ), LIND_THREADS, sm, h->stream>>>(h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm);
+        k_linearize_dirs<1, false><<<blocks(NV), LIND_THREADS, sm, h->stream>>>(h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm);
+        k_linearize_dirs<2, false><<<blocks(NU), LIND_THREADS, sm, h->stream>>>(h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm);
+      }
       h->launches += 3;
       return;
     }
@@ -313,7 +330,12 @@ static void enqueue_solve(H1Ilqr* h) {
   launch_rollout(h, nullptr, nullptr, h->N, h->cost);  // current_cost = computeTotalCost(xbar, ubar)
   for (int it = 0; it < h->opt.max_iterations; ++it) {
     launch_state(h, it, 0);
-    { StageTimer t(h, &h->times.rollout_ms); launch_rollout(h, h->active, h->x0, 0, h->nominal_cost, analytic); }
+    // iLQR::forwardRolloutNominal (ilqr.cpp:551-563). In iteration 0 the guess is rolled out from x0. In later
+    // iterations xbar/ubar are what the last accepted line-search candidate left (or unchanged after a failed
+    // one): rolling them out again from the same x0 reproduces them (f_D is deterministic), so the sequential
+    // rollout is replaced by the knot-parallel factorisation and the known cost (k_solve_state, phase 0).
+    if (it == 0) { StageTimer t(h, &h->times.rollout_ms); launch_rollout(h, h->active, h->x0, 0, h->nominal_cost, analytic); }
+    else if (analytic) { StageTimer t(h, &h->times.rollout_ms); launch_factors(h, h->active); }
     { StageTimer t(h, &h->times.linearize_ms); launch_linearize(h, h->active, analytic); }
     { StageTimer t(h, &h->times.cost_quadratics_ms); launch_cost_quadratics(h, h->active); }
     { StageTimer t(h, &h->times.backward_ms); launch_backward(h, h->active); }

@@ -90,6 +90,10 @@ bool build_dyn_model(const H1Model& m, DynModel* d) {
       if (b == 12 || b == 16) want = 11;
       ok = m.parent[b] == want;
     }
+    for (int k = 0; k < NV && ok; ++k) {   // the compile-time dof tree (h1_common.cuh) must be this model's
+      ok = d->nlist[k] == h1_nlist(k);
+      for (int sl = 0; sl < d->nlist[k] && ok; ++sl) ok = d->alist[k][sl] == h1_anc(k, sl);
+    }
     d->seq_ok = ok ? 1 : 0;
   }
   return true;

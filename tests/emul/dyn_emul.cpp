@@ -66,7 +66,8 @@ extern "C" int emul_dyn_linearize_dirs(const double* x, const double* u, double*
       for (int k = 0; k < h1::NV; ++k) tv[k] = 0.0;
       tv[6 + j] = (u[j] < md.ctrl_lo[j] || u[j] > md.ctrl_hi[j]) ? 0.0 : 1.0;
     }
-    h1::tangent_solve_seq(md, &pf.Lm[0][0], pf.D, tv);
+    if (md.seq_ok && (e & 1)) h1::tangent_solve_h1(&pf.Lm[0][0], pf.D, tv);   // both solve variants are exercised
+    else h1::tangent_solve_seq(md, &pf.Lm[0][0], pf.D, tv);
     h1::integrate_tangent_seq(md, x, pf.a, e, tv, e < h1::NX ? A + e * h1::NX : B + (e - h1::NX) * h1::NX);
   }
   return 0;
