@@ -103,22 +103,29 @@ k_primal_factor_seq(const DynModel* gmd, int B, int N, const int* __restrict__ a
 //      (iLQR::forwardPassLineSearch, ilqr.cpp:311-361) ----
 constexpr int SEQ_THREADS = 64;
 static_assert(H1ILQR_NALPHA == 8, "candidate groups are 8 lanes wide");
+static_assert(NX % 3 == 0, "feedback loop is unrolled by 3");
 #ifndef H1_SEQ_MINB
 #define H1_SEQ_MINB 4
 #endif
 __global__ void __launch_bounds__(SEQ_THREADS, H1_SEQ_MINB)
 k_line_search_seq(const DynModel* gmd, const H1Weights* gw, const H1SolverOptions* gopt, RefTable refs, int B, int N,
-                  const int* __restrict__ mask, const double* __restrict__ x0, const double* __restrict__ baseline,
+                  const int* __restrict__ mask, const int* __restrict__ list, const int* __restrict__ list_count,
+                  const double* __restrict__ x0, const double* __restrict__ baseline,
                   double* __restrict__ xbar, double* __restrict__ ubar, const double* __restrict__ K,
                   const double* __restrict__ kff, double* __restrict__ xnew, double* __restrict__ unew,
                   int* __restrict__ ls_ok, double* __restrict__ ls_cost, int* __restrict__ ls_alpha) {
   extern __shared__ __align__(16) unsigned char smem[];
+  // `list` (optional): compact list of the instances to search, built on the device by k_solve_state; slot s of
+  // the grid then works on instance list[s] and full warps are formed however sparse the active set is
+  const int nlist = list ? *list_count : B;
+  if ((long)blockIdx.x * blockDim.x >= (long)nlist * H1ILQR_NALPHA) return;
   const DynModel* md;
   stage_model(smem, gmd, &md);
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  const int inst = (int)(g >> 3), cand = (int)(g & 7);
-  const bool act = inst < B && (!mask || mask[inst]);
+  const int slot = (int)(g >> 3), cand = (int)(g & 7);
+  const int inst = list ? (slot < nlist ? list[slot] : B) : slot;
+  const bool act = inst < B && (list || !mask || mask[inst]);
   const int instc = min(inst, B - 1);
   double* xb = xbar + (size_t)instc * (N + 1) * NX;
   double* ub = ubar + (size_t)instc * N * NU;
@@ -135,18 +142,19 @@ k_line_search_seq(const DynModel* gmd, const H1Weights* gw, const H1SolverOption
       const double* Kt = K + ((size_t)inst * N + t) * NU * NX;
       const double* kt = kff + ((size_t)inst * N + t) * NU;
 #pragma unroll
-      for (int i = 0; i < NU; ++i) u[i] = 0.0;
+      for (int i = 0; i < NU; ++i) u[i] = ub[t * NU + i] + alpha * kt[i];
+      // u += K_t (x - xbar_t): three state entries per trip so that 57 loads of K are in flight per thread
 #pragma unroll 1
-      for (int l = 0; l < NX; ++l) {
-        const double dx = xn[t * NX + l] - xb[t * NX + l];
+      for (int l = 0; l < NX; l += 3) {
+        const double dx0 = xn[t * NX + l] - xb[t * NX + l];
+        const double dx1 = xn[t * NX + l + 1] - xb[t * NX + l + 1];
+        const double dx2 = xn[t * NX + l + 2] - xb[t * NX + l + 2];
+        const double* Kl = Kt + l * NU;
 #pragma unroll
-        for (int i = 0; i < NU; ++i) u[i] += Kt[l * NU + i] * dx;
+        for (int i = 0; i < NU; ++i) u[i] += Kl[i] * dx0 + Kl[NU + i] * dx1 + Kl[2 * NU + i] * dx2;
       }
 #pragma unroll
-      for (int i = 0; i < NU; ++i) {
-        u[i] = ub[t * NU + i] + alpha * kt[i] + u[i];
-        un[t * NU + i] = u[i];
-      }
+      for (int i = 0; i < NU; ++i) un[t * NU + i] = u[i];
       dyn_step_seq(*md, xn + t * NX, u, xn + (t + 1) * NX, nullptr, com);
       total += knot_cost_seq(*md, *gw, r, t, xn + t * NX, u, com, false);
     }

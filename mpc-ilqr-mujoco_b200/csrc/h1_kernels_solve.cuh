@@ -136,6 +136,7 @@ struct SolveState {
   int* active; int* second; int* iters; int* status;
   int* ls_ok; double* ls_cost; int* ls_alpha;
   double* cost_trace; int* alpha_trace;
+  int* act_list; int* sec_list; int* list_count;   // compact instance lists for the thread-per-candidate line search
 };
 // phase 0: iteration begin; 1: after first line search; 2: iteration end
 __global__ void k_solve_state(SolveState st, const H1SolverOptions* gopt, int B, int it, int phase) {
@@ -152,6 +153,7 @@ __global__ void k_solve_state(SolveState st, const H1SolverOptions* gopt, int B,
     if (st.active[i]) {
       st.prev_cost[i] = st.cost[i];
       if (it > 0) st.nominal_cost[i] = st.cost[i];   // baseline of the line search: cost of the unchanged trajectory
+      st.act_list[atomicAdd(&st.list_count[0], 1)] = i;   // (both counters are zeroed before the phase-0 launch)
     }
     return;
   }
@@ -161,6 +163,7 @@ __global__ void k_solve_state(SolveState st, const H1SolverOptions* gopt, int B,
     if (!st.ls_ok[i]) {
       st.lambda[i] = fmin(st.lambda[i] * 10.0, o.reg_max);
       st.second[i] = 1;
+      st.sec_list[atomicAdd(&st.list_count[1], 1)] = i;
     }
     return;
   }

@@ -35,6 +35,7 @@ struct H1Ilqr {
   int* stance = nullptr; int ref_shared = 1;
   double *lambda = nullptr, *cost = nullptr, *prev_cost = nullptr, *nominal_cost = nullptr, *ls_cost = nullptr;
   int *active = nullptr, *second = nullptr, *iters = nullptr, *status = nullptr, *ls_ok = nullptr, *ls_alpha = nullptr;
+  int *act_list = nullptr, *sec_list = nullptr, *list_count = nullptr;
   int *has_prev = nullptr, *warm_mask = nullptr, *cold_mask = nullptr, *warm_in = nullptr;
   double* cost_trace = nullptr; int* alpha_trace = nullptr;
   PrimalFactor* pf = nullptr;   // [B][N] factorisation of Mhat at every knot of the nominal trajectory
@@ -138,7 +139,7 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   CUH(dalloc(h, &h->nominal_cost, B)); CUH(dalloc(h, &h->ls_cost, B));
   CUH(dalloc(h, &h->active, B)); CUH(dalloc(h, &h->second, B)); CUH(dalloc(h, &h->iters, B)); CUH(dalloc(h, &h->status, B));
   CUH(dalloc(h, &h->ls_ok, B)); CUH(dalloc(h, &h->ls_alpha, B)); CUH(dalloc(h, &h->has_prev, B));
-  CUH(dalloc(h, &h->warm_mask, B)); CUH(dalloc(h, &h->cold_mask, B)); CUH(dalloc(h, &h->warm_in, B));
+  CUH(dalloc(h, &h->warm_mask, B)); CUH(dalloc(h, &h->act_list, B)); CUH(dalloc(h, &h->sec_list, B)); CUH(dalloc(h, &h->list_count, 2)); CUH(dalloc(h, &h->cold_mask, B)); CUH(dalloc(h, &h->warm_in, B));
   CUH(dalloc(h, &h->pf, B * N));
   CUH(dalloc(h, &h->cost_trace, B * h->opt.max_iterations)); CUH(dalloc(h, &h->alpha_trace, B * h->opt.max_iterations * 2));
   h->scratch_bytes = B * N1 * (NX + NU + NX + NV + 9) * sizeof(double);
@@ -287,8 +288,10 @@ static void launch_backward(H1Ilqr* h, const int* mask) {
 static void launch_line_search(H1Ilqr* h, const int* mask) {
   if (h->seq_ok && use_batched(h, h->B, h->seq_min_batch)) {   // one thread per (instance, candidate)
     const long threads = (long)h->B * H1ILQR_NALPHA;
+    const int* list = (mask && mask == h->active) ? h->act_list : ((mask && mask == h->second) ? h->sec_list : nullptr);
     k_line_search_seq<<<(unsigned)((threads + SEQ_THREADS - 1) / SEQ_THREADS), SEQ_THREADS, h->smem_seq, h->stream>>>(
-        h->d_dyn, h->d_w, h->d_opt, ref_table(h), h->B, h->N, mask, h->x0, h->nominal_cost, h->xbar, h->ubar, h->K, h->kff,
+        h->d_dyn, h->d_w, h->d_opt, ref_table(h), h->B, h->N, mask, list, list ? h->list_count + (mask == h->second ? 1 : 0) : nullptr,
+        h->x0, h->nominal_cost, h->xbar, h->ubar, h->K, h->kff,
         h->xnew, h->unew, h->ls_ok, h->ls_cost, h->ls_alpha);
     LAUNCHED();
     return;
@@ -304,9 +307,11 @@ static SolveState solve_state(H1Ilqr* h) {
   st.active = h->active; st.second = h->second; st.iters = h->iters; st.status = h->status;
   st.ls_ok = h->ls_ok; st.ls_cost = h->ls_cost; st.ls_alpha = h->ls_alpha;
   st.cost_trace = h->cost_trace; st.alpha_trace = h->alpha_trace;
+  st.act_list = h->act_list; st.sec_list = h->sec_list; st.list_count = h->list_count;
   return st;
 }
 static void launch_state(H1Ilqr* h, int it, int phase) {
+  if (phase == 0) cudaMemsetAsync(h->list_count, 0, 2 * sizeof(int), h->stream);
   k_solve_state<<<(h->B + 127) / 128, 128, 0, h->stream>>>(solve_state(h), h->d_opt, h->B, it, phase);
   LAUNCHED();
 }
