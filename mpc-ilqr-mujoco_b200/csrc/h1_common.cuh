@@ -16,6 +16,15 @@ namespace h1 { using std::isfinite; }
 
 namespace h1 {
 
+#if defined(__CUDACC__)
+// D(8x8) += A(8x4) B(4x8) on the fp64 tensor core (SASS DMMA). Lane l holds A[l/4][l%4], B[l%4][l/4],
+// C[l/4][2(l%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+#endif
+
 constexpr int NB = H1_NB, NQ = H1_NQ, NV = H1_NV, NX = H1_NX, NU = H1_NU;
 constexpr int MAXSLOT = 11;  // base 6 + longest hinge chain 5
 constexpr int NCPT = H1_NFOOT * H1_NCP;

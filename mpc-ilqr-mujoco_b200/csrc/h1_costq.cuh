@@ -23,6 +23,7 @@ namespace h1 {
 constexpr int CQ_SETS = 3;     // 0: CoM, 1: left ankle frame, 2: right ankle frame
 constexpr int CQ_ROWS = 20;    // Jacobian rows: per set P(3) then U(3) -> 18, + 2 balance residual rows
 constexpr int CQ_MAXOUTER = 28;
+constexpr int CQ_LD = NX + 1;   // leading dimension of the Jacobian rows: = 4 (mod 8) doubles, conflict-free DMMA fragment loads
 
 struct CostWarp {
   double xt[NX];                 // Pinocchio-ordered state
@@ -32,7 +33,7 @@ struct CostWarp {
   double rj[CQ_SETS][NB][3], uth[CQ_SETS][NB][3], D[CQ_SETS][NB][3];
   double lamP[CQ_SETS][3], lamU[CQ_SETS][3];          // Hessian-contraction multipliers per set
   double R[9], Ra[4][9];
-  double rows[CQ_ROWS][NX];
+  double rows[CQ_ROWS][CQ_LD];
   double gcoef[CQ_ROWS];
   double QQ[4][4], QJ[4][NB], JJ[NB][NB], QV[4][NV], JV[NB][NV];
   double gq[4];                  // upright gradient
@@ -423,22 +424,68 @@ H1_DEV void ph_cq_store(int lane, const DynModel& md, const H1Weights& wt, const
     lx[i] = g;
   }
   const int no = w.n_outer;
+  auto diag_terms = [&](int i, double h) {
+    h += Qd[i];
+    if (i >= 7 && i < NQ) {
+      const double lo = md.jnt_lo[i - 7], hi = md.jnt_hi[i - 7];
+      double gd = 0.0;
+      if (isfinite(lo) && isfinite(hi) && lo < hi) limit_d(x[i], lo, hi, wt.w_joint_limits, &gd, &h);
+    }
+    return h;
+  };
+#if defined(__CUDACC__)
+  // sum_k c_k rows[a_k] (x) rows[b_k] is the product (rows_a diag(c))' rows_b with the term index k as the
+  // contraction dimension: 8 x 8 tiles of the lower triangle on the fp64 tensor core (DMMA m8n8k4), <= 7 k-steps.
+  {
+    constexpr int KS = (CQ_MAXOUTER + 3) / 4;
+    const int g = lane >> 2, t4 = lane & 3, nks = (no + 3) >> 2;
+    const double* ra[KS]; const double* rb[KS]; double cc[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int k = 4 * ks + t4;
+      const bool valid = k < no;
+      ra[ks] = w.rows[valid ? w.outer_a[k] : 0];
+      rb[ks] = w.rows[valid ? w.outer_b[k] : 0];
+      cc[ks] = valid ? w.outer_c[k] : 0.0;
+    }
+#pragma unroll 1
+    for (int it = 0; it < (NX + 7) / 8; ++it) {
+      const int ia = min(8 * it + g, NX - 1);          // rows 51..55 of the last tile are padding (discarded)
+      double af[KS];
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) af[ks] = (ks < nks) ? cc[ks] * ra[ks][ia] : 0.0;
+#pragma unroll 1
+      for (int jt = 0; jt <= it; ++jt) {
+        const int jb = min(8 * jt + g, NX - 1);
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+          if (ks < nks) dmma884(c0, c1, af[ks], rb[ks][jb]);
+        const int i = 8 * it + g;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int j = 8 * jt + 2 * t4 + q;
+          if (i < NX && j <= i) {
+            double h = (q ? c1 : c0) + cq_block(w, i, j);
+            if (i == j) h = diag_terms(i, h);
+            lxx[j * NX + i] = h;
+            lxx[i * NX + j] = h;
+          }
+        }
+      }
+    }
+  }
+#else
   for (int j = 0; j < NX; ++j) {      // lower triangle column by column, mirrored on store
     for (int i = j + lane; i < NX; i += 32) {
       double h = cq_block(w, i, j);
       for (int k = 0; k < no; ++k) h += w.outer_c[k] * w.rows[w.outer_a[k]][i] * w.rows[w.outer_b[k]][j];
-      if (i == j) {
-        h += Qd[i];
-        if (i >= 7 && i < NQ) {
-          const double lo = md.jnt_lo[i - 7], hi = md.jnt_hi[i - 7];
-          double gd = 0.0;
-          if (isfinite(lo) && isfinite(hi) && lo < hi) limit_d(x[i], lo, hi, wt.w_joint_limits, &gd, &h);
-        }
-      }
+      if (i == j) h = diag_terms(i, h);
       lxx[j * NX + i] = h;
       lxx[i * NX + j] = h;
     }
   }
+#endif
   if (!terminal) {
     for (int e = lane; e < NU * NU; e += 32) {
       const int i = e % NU, j = e / NU;

@@ -47,11 +47,6 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
 __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
-// D(8x8) += A(8x4) B(4x8) on the fp64 tensor core. Lane l holds A[l/4][l%4], B[l%4][l/4], C[l/4][2(l%4) + {0,1}].
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
 // One warp accumulates an 8 x (8 NT) strip: acc[j] += sum_k A(m0 + g, k) B(k, n0 + 8 j + g'), k < 4 ksteps.
 // fa(row, k) / fb(k, col) return operand elements (they implement padding / clamping).
 template <int NT, class FA, class FB>
