@@ -324,12 +324,12 @@ def main():
 
 
 # fp64 operations EXECUTED per linearized knot by k_linearize_dirs<0|1|2> (2 per DFMA, 1 per DADD / DMUL), from the
-# smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on counters of profiles/r01e_ncu_top_kernels.txt:
-# q columns 680 k + v columns 404 k + u columns 40 k.
-FLOPS_PER_LINEARIZED_KNOT = 1.12e6
+# smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on counters of profiles/r01f_ncu_top_kernels.txt:
+# q columns 693 k + v columns 413 k + u columns 40 k.
+FLOPS_PER_LINEARIZED_KNOT = 1.15e6
 FACTOR_BYTES_PER_KNOT = (25 * 11 + 25 + 25) * 8.0
-# dram__bytes_read.sum + dram__bytes_write.sum of the same capture, per knot (9.42 GB / (4096 instances x 25 knots))
-TRAFFIC_BYTES_PER_LINEARIZED_KNOT = 92.0e3
+# dram__bytes_read.sum + dram__bytes_write.sum of the same capture, per knot (14.2 GB / (4096 instances x 25 knots))
+TRAFFIC_BYTES_PER_LINEARIZED_KNOT = 139.0e3
 
 if __name__ == "__main__":
     main()
