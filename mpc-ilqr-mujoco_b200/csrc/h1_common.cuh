@@ -57,6 +57,7 @@ struct DynModel {
   int n_base_children;
   int pad_;
   int nchild[NB];            // number of child bodies (branch bodies keep their state in the sequential walks)
+  int dir_order[NB - 1];     // hinged bodies by decreasing subtree size (costliest linearization directions first)
   int seq_ok;                // 1: the tree has H1's chain structure the thread-sequential f_D (h1_dyn_seq.cuh) is specialised for
 };
 

@@ -213,4 +213,103 @@ k_linearize_dirs(const DynModel* gmd, long nknots, int N, const int* __restrict_
   integrate_tangent_seq(*md, x, pf->a, seed, tv, col);
 }
 
+// ---- analytic linearization, one thread per column, DIRECTION-UNIFORM WARPS: a CTA owns LINC_KNOTS = 32
+//      consecutive knots and stages their Mhat factors, states and controls in shared memory once (coalesced);
+//      each of its 8 warps then repeatedly takes the next direction of the class (shared counter, costliest
+//      first) and differentiates the 32 knots along it, one knot per lane. Every lane of a warp therefore runs the
+//      same walk — in particular the sparse subtree walks of the joint directions (id_tangent_sub) — and reads its
+//      knot's factor from shared memory at an odd stride (conflict free). Columns are staged per warp and written
+//      to A_k / B_k as contiguous 408-byte runs.
+//      CLS 0: x, y, z, quaternion (7 columns; x / y are unit vectors, the rest walk every body)
+//          1: hinge angles (19, subtree walks)   2: base velocities (6, every body, plain kinematics)
+//          3: hinge rates (19, subtree walks)    4: controls (19, triangular solves only)
+//      (one launch per class: a single launch over all 70 columns balances the warps better but measured 40 %
+//       slower — the warps of a CTA then run five different code paths and thrash the instruction cache) ----
+constexpr int LINC_WARPS = 8, LINC_KNOTS = 32, LINC_THREADS = LINC_WARPS * 32;
+constexpr int LINC_FS = sizeof(PrimalFactor) / sizeof(double);   // 325 doubles: odd stride
+static_assert(LINC_FS % 2 == 1 && NX % 2 == 1 && NU % 2 == 1, "per-knot strides must be odd (bank-conflict-free lane <-> knot access)");
+__host__ __device__ constexpr int linc_ndirs(int cls) { return cls == 0 ? 7 : cls == 2 ? 6 : 19; }
+constexpr size_t LINC_SMEM_DOUBLES = (size_t)LINC_KNOTS * (LINC_FS + NX + NU) + (size_t)LINC_WARPS * LINC_KNOTS * NX;
+template <int CLS, bool H1TREE>
+__global__ void __launch_bounds__(LINC_THREADS)
+k_linearize_cols(const DynModel* gmd, long nknots, int N, const int* __restrict__ active,
+                 const double* __restrict__ xbar, const double* __restrict__ ubar,
+                 const PrimalFactor* __restrict__ pf_g, double* __restrict__ A, double* __restrict__ Bm) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ int okf[LINC_KNOTS];
+  __shared__ int next_dir;
+  const long knot0 = (long)blockIdx.x * LINC_KNOTS;
+  const int nk = (int)min((long)LINC_KNOTS, nknots - knot0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < LINC_KNOTS) okf[tid] = (tid < nk) && (!active || active[(knot0 + tid) / N]);
+  if (tid == 0) next_dir = 0;
+  const DynModel* md;
+  unsigned char* p = stage_model(smem, gmd, &md);    // (has a __syncthreads)
+  bool any = false;
+  for (int k = 0; k < nk; ++k) any |= okf[k] != 0;
+  if (!any) return;                                   // all 32 knots belong to finished instances
+  double* fac = reinterpret_cast<double*>(p);        // [LINC_KNOTS][LINC_FS]
+  double* xs = fac + LINC_KNOTS * LINC_FS;           // [LINC_KNOTS][NX]
+  double* us = xs + LINC_KNOTS * NX;                 // [LINC_KNOTS][NU]
+  double* tile = us + LINC_KNOTS * NU + warp * LINC_KNOTS * NX;   // this warp's [LINC_KNOTS][NX]
+  {
+    const double* src = reinterpret_cast<const double*>(pf_g + knot0);
+    for (int i = tid; i < nk * LINC_FS; i += LINC_THREADS) fac[i] = src[i];
+    for (int i = tid; i < nk * NX; i += LINC_THREADS) {
+      const int k = i / NX, j = i - k * NX;
+      const long knot = knot0 + k, inst = knot / N;
+      xs[i] = xbar[((size_t)inst * (N + 1) + (knot - inst * N)) * NX + j];
+    }
+    for (int i = tid; i < nk * NU; i += LINC_THREADS) us[i] = ubar[(size_t)knot0 * NU + i];
+  }
+  __syncthreads();
+  const bool ok = lane < nk && okf[lane];
+  const double* x = xs + lane * NX;
+  const PrimalFactor* pf = reinterpret_cast<const PrimalFactor*>(fac + lane * LINC_FS);
+  double* col = tile + lane * NX;
+  while (true) {
+    int d = 0;
+    if (lane == 0) d = atomicAdd(&next_dir, 1);
+    d = __shfl_sync(0xffffffffu, d, 0);
+    if (d >= linc_ndirs(CLS)) break;
+    int seed;
+    constexpr int cls = CLS;
+    if (CLS == 0) seed = 6 - d;                                  // quaternion and z first, the trivial x / y last
+    else if (CLS == 1) seed = 6 + md->dir_order[d];              // hinges by decreasing subtree size
+    else if (CLS == 2) seed = NQ + d;
+    else if (CLS == 3) seed = NQ + 5 + md->dir_order[d];
+    else seed = NX + d;
+    if (ok) {
+      if (cls == 0 && seed < 2) {
+        for (int j = 0; j < NX; ++j) col[j] = (j == seed) ? 1.0 : 0.0;
+      } else {
+        double tv[NV];
+        if (cls == 0) id_tangent_seq<Dual, Dual>(*md, x, pf->a, seed, tv);
+        else if (cls == 1) id_tangent_sub<Dual, Dual>(*md, x, pf->a, seed, seed - 6, tv);
+        else if (cls == 2) id_tangent_seq<double, Dual>(*md, x, pf->a, seed, tv);
+        else if (cls == 3) id_tangent_sub<double, Dual>(*md, x, pf->a, seed, seed - NQ - 5, tv);
+        else {
+          const int j = seed - NX;
+          const double uj = us[lane * NU + j];
+          for (int k = 0; k < NV; ++k) tv[k] = 0.0;
+          tv[6 + j] = (uj < md->ctrl_lo[j] || uj > md->ctrl_hi[j]) ? 0.0 : 1.0;   // clamped torque: no sensitivity
+        }
+        if (H1TREE) tangent_solve_h1(&pf->Lm[0][0], pf->D, tv);
+        else tangent_solve_seq(*md, &pf->Lm[0][0], pf->D, tv);
+        integrate_tangent_seq(*md, x, pf->a, seed, tv, col);
+      }
+    }
+    __syncwarp();
+    for (int k = 0; k < nk; ++k) {
+      if (!okf[k]) continue;
+      const long knot = knot0 + k;
+      double* dst = (seed >= NX) ? Bm + (size_t)knot * NX * NU + (size_t)(seed - NX) * NX
+                               : A + (size_t)knot * NX * NX + (size_t)seed * NX;
+      const double* src = tile + k * NX;
+      for (int j = lane; j < NX; j += 32) dst[j] = src[j];
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace h1

@@ -220,6 +220,152 @@ H1_DEV void id_tangent_seq(const DynModel& md, const double* __restrict__ x, con
   }
 }
 
+// Same tangent for a JOINT direction (angle or rate of the hinge of body bj), exploiting its sparsity: only the
+// bodies of subtree(bj) move with the direction, so only they are walked with dual numbers (3.1 of 19 bodies on
+// average over H1's hinges); the bodies on the path base -> parent(bj) are walked for their kinematics alone and
+// every other body is skipped. t_k is non-zero for the dofs of subtree(bj), for the hinge ancestors of bj and for
+// the base: the latter two see the direction only through the total wrench tangent of subtree(bj).
+// seed = 6 + bj (angle; TK = Dual) or NQ + 5 + bj (rate; TK = double).
+template <class TK, class TV>
+H1_DEV void id_tangent_sub(const DynModel& md, const double* __restrict__ x, const double* __restrict__ a, int seed,
+                           int bj, double* __restrict__ t) {
+  SeqState<TK, TV> cur, saved[SEQ_MAXSAVE];
+  TK Sst[6][6];
+  TV spst[6];
+  TK Vab[6];
+  for (int j = 0; j < NV; ++j) t[j] = 0.0;
+  {
+    TK qr[4], qn[4];
+    for (int i = 0; i < 4; ++i) qr[i] = TK(x[3 + i]);
+    quat_normalize(qr, qn);
+    quat_to_mat(qn, cur.R);
+  }
+  cur.r[0] = cur.r[1] = cur.r[2] = TK(0.0);
+  {
+    for (int i = 0; i < 3; ++i) {
+      cur.V[i] = TV(cur.R[3 * i] * x[NQ + 3] + cur.R[3 * i + 1] * x[NQ + 4] + cur.R[3 * i + 2] * x[NQ + 5]);
+      Vab[i] = cur.R[3 * i] * a[3] + cur.R[3 * i + 1] * a[4] + cur.R[3 * i + 2] * a[5];
+      cur.V[3 + i] = TV(x[NQ + i]);
+      Vab[3 + i] = TK(a[i]);
+    }
+    TV vxw[3];
+    cross_m(cur.V + 3, cur.V, vxw);
+    for (int i = 0; i < 3; ++i) {
+      cur.At[i] = TV(Vab[i]);
+      cur.At[3 + i] = Vab[3 + i] + vxw[i] - md.gravity[i];
+    }
+  }
+  saved[0] = cur;
+  const TK qz = TK(x[2]);
+  const int dj = md.depth[bj], bend = md.chain_end[bj];
+  TV C[6];
+  for (int i = 0; i < 6; ++i) C[i] = TV(0.0);
+  // bodies on the path above bj (kinematics only), then the bodies of subtree(bj) (DFS-contiguous: bj .. bend)
+#pragma unroll 1
+  for (int step = 1 - dj; step <= bend - bj; ++step) {
+    const bool above = step < 0;
+    const int b = above ? md.anc_body[bj][dj + step] : bj + step;
+    const int d = md.depth[b];
+    if (!above && step > 0 && md.parent[b] != b - 1) cur = saved[d - 1];
+    {
+      const double* p = md.pos[b];
+      cur.r[0] += cur.R[0] * p[0] + cur.R[1] * p[1] + cur.R[2] * p[2];
+      cur.r[1] += cur.R[3] * p[0] + cur.R[4] * p[1] + cur.R[5] * p[2];
+      cur.r[2] += cur.R[6] * p[0] + cur.R[7] * p[1] + cur.R[8] * p[2];
+      if (md.has_rfix[b]) {
+        const double* Fx = md.rfix[b];
+        TK Tm[9];
+        for (int i = 0; i < 3; ++i)
+          for (int k = 0; k < 3; ++k)
+            Tm[3 * i + k] = cur.R[3 * i] * Fx[k] + cur.R[3 * i + 1] * Fx[3 + k] + cur.R[3 * i + 2] * Fx[6 + k];
+        for (int i = 0; i < 9; ++i) cur.R[i] = Tm[i];
+      }
+    }
+    TK S[6];
+    {
+      TK sn, cs;
+      sincos_t(seeded<TK>(x[6 + b], seed == 6 + b, 0.0), &sn, &cs);
+      const int ax = md.axis[b];
+      rot_right(cur.R, ax, sn, cs);
+      col_of(cur.R, ax, S);
+      cross_m(cur.r, S, S + 3);
+    }
+    {
+      const TV vj = seeded<TV>(x[NQ + 5 + b], seed == NQ + 5 + b, 0.0);
+      const double aj = a[5 + b];
+      for (int i = 0; i < 6; ++i) cur.V[i] += S[i] * vj;
+      TV c1[3], c2[3], c3[3];
+      cross_m(cur.V, S, c1); cross_m(cur.V, S + 3, c2); cross_m(cur.V + 3, S, c3);
+      for (int i = 0; i < 3; ++i) {
+        cur.At[i] += S[i] * aj + c1[i] * vj;
+        cur.At[3 + i] += S[3 + i] * aj + (c2[i] + c3[i]) * vj;
+      }
+    }
+    for (int i = 0; i < 6; ++i) Sst[d][i] = S[i];
+    if (above) continue;
+    if (md.nchild[b] > 1) saved[d] = cur;
+    spst[d] = S[0] * C[0] + S[1] * C[1] + S[2] * C[2] + S[3] * C[3] + S[4] * C[4] + S[5] * C[5];
+    TV F[6];
+    {
+      TK I[10];
+      body_inertia_seq(md, b, cur.R, cur.r, I);
+      body_wrench_seq(I, cur.V, cur.At, F);
+    }
+    for (int f = 0; f < H1_NFOOT; ++f) {
+      if (b != md.foot_body[f]) continue;
+      TK Va[6];
+      for (int i = 0; i < 6; ++i) Va[i] = Vab[i];
+      for (int dd = 1; dd <= d; ++dd) {
+        const double aa = a[5 + md.anc_body[b][dd]];
+        for (int i = 0; i < 6; ++i) Va[i] += Sst[dd][i] * aa;
+      }
+      const double h = md.h;
+#pragma unroll 1
+      for (int c = 0; c < H1_NCP; ++c) {
+        const double* pt = md.foot_pts[f * H1_NCP + c];
+        const TK rho[3] = {cur.r[0] + cur.R[0] * pt[0] + cur.R[1] * pt[1] + cur.R[2] * pt[2],
+                           cur.r[1] + cur.R[3] * pt[0] + cur.R[4] * pt[1] + cur.R[5] * pt[2],
+                           cur.r[2] + cur.R[6] * pt[0] + cur.R[7] * pt[1] + cur.R[8] * pt[2]};
+        TV t1[3]; TK t2[3];
+        cross_m(cur.V, rho, t1);
+        cross_m(Va, rho, t2);
+        const TV pd[3] = {cur.V[3] + t1[0], cur.V[4] + t1[1], cur.V[5] + t1[2]};
+        const TK pa[3] = {Va[3] + t2[0], Va[4] + t2[1], Va[5] + t2[2]};
+        const TK dd_ = -(qz + rho[2]);
+        const TK root = sqrt_t(dd_ * dd_ + md.eps * md.eps);
+        const TK sp = 0.5 * (dd_ + root), al = 0.5 * (1.0 + dd_ / root);
+        TV Fc[3];
+        Fc[0] = -(al * md.bt) * (pd[0] + h * pa[0]);
+        Fc[1] = -(al * md.bt) * (pd[1] + h * pa[1]);
+        Fc[2] = md.kn * sp - al * ((md.bn + h * md.kn) * pd[2] + (h * md.bn + h * h * md.kn) * pa[2]);
+        TV n[3];
+        cross_m(rho, Fc, n);
+        for (int i = 0; i < 3; ++i) { F[i] -= n[i]; F[3 + i] -= Fc[i]; }
+      }
+    }
+    for (int i = 0; i < 6; ++i) C[i] += F[i];
+    for (int dd = d; dd >= dj; --dd) {   // dofs of subtree(bj) whose subtree ends at this body
+      const int bb = md.anc_body[b][dd];
+      if (md.chain_end[bb] != b) break;
+      const TV g = Sst[dd][0] * C[0] + Sst[dd][1] * C[1] + Sst[dd][2] * C[2] + Sst[dd][3] * C[3] + Sst[dd][4] * C[4] +
+                   Sst[dd][5] * C[5] - spst[dd];
+      t[5 + bb] = -(tangent_of(g) + ((seed == NQ + 5 + bb) ? md.damping[5 + bb] : 0.0));
+    }
+  }
+  // hinge ancestors of bj and the base see the direction through the wrench tangent of subtree(bj) only
+  for (int dd = 1; dd < dj; ++dd) {
+    const TV g = Sst[dd][0] * C[0] + Sst[dd][1] * C[1] + Sst[dd][2] * C[2] + Sst[dd][3] * C[3] + Sst[dd][4] * C[4] +
+                 Sst[dd][5] * C[5];
+    t[5 + md.anc_body[bj][dd]] = -tangent_of(g);
+  }
+  for (int i = 0; i < 3; ++i) {
+    t[i] = -tangent_of(C[3 + i]);
+    const TK* R = saved[0].R;
+    const TV g = R[i] * C[0] + R[3 + i] * C[1] + R[6 + i] * C[2];
+    t[3 + i] = -tangent_of(g);
+  }
+}
+
 // Mhat adot = t with the primal factor Mhat = L^T D L (unit-lower rows Lm[k][slot], branch-sparse); in place.
 H1_DEV void tangent_solve_seq(const DynModel& md, const double* __restrict__ Lm, const double* __restrict__ D,
                               double* __restrict__ t) {
@@ -246,6 +392,7 @@ H1_DEV void tangent_solve_h1(const double* __restrict__ Lm, const double* __rest
 #pragma unroll
     for (int s = 0; s < MAXSLOT - 1; ++s)
       if (s < h1_nlist(k) - 1) t[h1_anc(k, s)] -= Lm[k * MAXSLOT + s] * tk;
+    asm volatile("" ::: "memory");   // keep the loads of row k inside step k (hoisting all 169 of them spills t)
   }
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -254,6 +401,7 @@ H1_DEV void tangent_solve_h1(const double* __restrict__ Lm, const double* __rest
     for (int s = 0; s < MAXSLOT - 1; ++s)
       if (s < h1_nlist(k) - 1) ad -= Lm[k * MAXSLOT + s] * t[h1_anc(k, s)];
     t[k] = ad;
+    asm volatile("" ::: "memory");
   }
 }
 
@@ -274,6 +422,35 @@ H1_DEV void integrate_tangent_seq(const DynModel& md, const double* __restrict__
     wn[i] = Dual(x[NQ + 3 + i] + h * a[3 + i], ((seed == NQ + 3 + i) ? 1.0 : 0.0) + h * adot[3 + i]);
   quat_step(q, wn, h, qo);
   for (int i = 0; i < 4; ++i) col[3 + i] = qo[i].d;
+}
+
+// One exact column of [A | B] (seed: 0..50 state entry, 51..69 control) with the cheapest applicable walk.
+// H1TREE: the model has H1's dof tree (DynModel::seq_ok) -> static-index triangular solves.
+template <bool H1TREE>
+H1_DEV void linearize_column_t(const DynModel& md, const double* __restrict__ x, const double* __restrict__ u,
+                               const PrimalFactor& pf, int seed, double* __restrict__ col) {
+  if (seed < 2) {   // f_D is translation invariant in x and y: the column is the unit vector
+    for (int j = 0; j < NX; ++j) col[j] = (j == seed) ? 1.0 : 0.0;
+    return;
+  }
+  double tv[NV];
+  if (seed < 7) id_tangent_seq<Dual, Dual>(md, x, pf.a, seed, tv);                       // z, quaternion: every body moves
+  else if (seed < NQ) id_tangent_sub<Dual, Dual>(md, x, pf.a, seed, seed - 6, tv);       // hinge angle
+  else if (seed < NQ + 6) id_tangent_seq<double, Dual>(md, x, pf.a, seed, tv);           // base velocity
+  else if (seed < NX) id_tangent_sub<double, Dual>(md, x, pf.a, seed, seed - NQ - 5, tv);  // hinge rate
+  else {
+    const int j = seed - NX;
+    for (int k = 0; k < NV; ++k) tv[k] = 0.0;
+    tv[6 + j] = (u[j] < md.ctrl_lo[j] || u[j] > md.ctrl_hi[j]) ? 0.0 : 1.0;   // clamped torque: no sensitivity
+  }
+  if (H1TREE) tangent_solve_h1(&pf.Lm[0][0], pf.D, tv);
+  else tangent_solve_seq(md, &pf.Lm[0][0], pf.D, tv);
+  integrate_tangent_seq(md, x, pf.a, seed, tv, col);
+}
+H1_DEV void linearize_column(const DynModel& md, const double* x, const double* u, const PrimalFactor& pf, int seed,
+                             double* col) {
+  if (md.seq_ok) linearize_column_t<true>(md, x, u, pf, seed, col);
+  else linearize_column_t<false>(md, x, u, pf, seed, col);
 }
 
 }  // namespace h1

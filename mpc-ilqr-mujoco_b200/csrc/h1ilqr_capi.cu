@@ -50,9 +50,10 @@ struct H1Ilqr {
   size_t smem_lina = 0;
   int policy = H1ILQR_KERNELS_AUTO;
   int seq_min_batch = 64;   // AUTO: batch at or above which rollouts / line searches run one THREAD per f_D evaluation (h1_dyn_seq.cuh)
-  size_t smem_seq = 0;
+  size_t smem_seq = 0, smem_linc = 0;
   bool seq_ok = false;      // the model has the chain structure the thread-sequential f_D is specialised for
-  long lin_dirs_min_knots = 0;   // AUTO: B*N at or above which the column-per-thread linearization is used (faster at every size measured)
+  long lin_cols_min_knots = 148 * 32;   // AUTO: B*N at or above which the direction-uniform linearization (32 knots per CTA) fills the GPU;
+                                        // below it the knot-major thread-per-column kernel (k_linearize_dirs) is the faster one
   size_t smem_dyn4 = 0, smem_lin = 0, smem_cq = 0, smem_ls = 0, smem_ric = 0;
 };
 
@@ -157,6 +158,12 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   h->smem_ls = mdl + H1ILQR_NALPHA * sizeof(DynWarp) + (H1ILQR_NALPHA + H1ILQR_NALPHA * (NX + NU)) * sizeof(double);
   h->smem_ric = sizeof(RiccatiSmem);
   h->smem_seq = mdl;
+  h->smem_linc = mdl + LINC_SMEM_DOUBLES * sizeof(double);
+#define LINC_ATTR(CLS) \
+  CUH(cudaFuncSetAttribute(k_linearize_cols<CLS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_linc)); \
+  CUH(cudaFuncSetAttribute(k_linearize_cols<CLS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_linc));
+  LINC_ATTR(0) LINC_ATTR(1) LINC_ATTR(2) LINC_ATTR(3) LINC_ATTR(4)
+#undef LINC_ATTR
   if (const char* e = getenv("H1_SEQ_SMEM_PAD")) h->smem_seq += (size_t)atoi(e) * 1024;   // experiment: limits resident CTAs
   CUH(cudaFuncSetAttribute(k_line_search_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_seq));
   CUH(cudaFuncSetAttribute(k_rollout_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_seq));
@@ -248,18 +255,25 @@ static void launch_linearize(H1Ilqr* h, const int* mask, bool factors_ready = fa
   if (h->opt.linearization != H1ILQR_LIN_FD) {
     if (!factors_ready) launch_factors(h, mask);
     const long knots = (long)h->B * h->N;
-    if (use_batched(h, knots, h->lin_dirs_min_knots)) {  // one thread per column
+    if (use_batched(h, knots, h->lin_cols_min_knots)) {  // one thread per column, direction-uniform warps
+      const unsigned kb = (unsigned)((knots + LINC_KNOTS - 1) / LINC_KNOTS);
+#define LINC_LAUNCH(CLS, TREE)                                                                                        \
+  k_linearize_cols<CLS, TREE><<<kb, LINC_THREADS, h->smem_linc, h->stream>>>(                                         \
+      h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm)
+      if (h->seq_ok) { LINC_LAUNCH(0, true); LINC_LAUNCH(1, true); LINC_LAUNCH(2, true); LINC_LAUNCH(3, true); LINC_LAUNCH(4, true); }
+      else { LINC_LAUNCH(0, false); LINC_LAUNCH(1, false); LINC_LAUNCH(2, false); LINC_LAUNCH(3, false); LINC_LAUNCH(4, false); }
+      h->launches += 5;
+#undef LINC_LAUNCH
+      return;
+    }
+    if (h->policy == H1ILQR_KERNELS_AUTO) {   // small batches: one thread per column, knot-major (the factor is shared by a warp)
       const size_t sm = ((sizeof(DynModel) + 15) / 16) * 16;
       auto blocks = [&](int nd) { return (unsigned)((knots * nd + LIND_THREADS - 1) / LIND_THREADS); };
-      if (h->seq_ok) {
-        k_linearize_dirs<0, true><<<blocks(NQ), LIND_THREADS, sm, h->stream>>>(h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm);
-        k_linearize_dirs<1, true><<<blocks(NV), LIND_THREADS, sm, h->stream>>>(h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm);
-        k_linearize_dirs<2, true><<<blocks(NU), LIND_THREADS, sm, h->stream>>>(h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm);
-      } else {
-        k_linearize_dirs<0, false><<<blocks(NQ), LIND_THREADS, sm, h->stream>>>(h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm);
-        k_linearize_dirs<1, false><<<blocks(NV), LIND_THREADS, sm, h->stream>>>(h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm);
-        k_linearize_dirs<2, false><<<blocks(NU), LIND_THREADS, sm, h->stream>>>(h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm);
-      }
+#define LIND_LAUNCH(MODE, ND, TREE) \
+  k_linearize_dirs<MODE, TREE><<<blocks(ND), LIND_THREADS, sm, h->stream>>>(h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm)
+      if (h->seq_ok) { LIND_LAUNCH(0, NQ, true); LIND_LAUNCH(1, NV, true); LIND_LAUNCH(2, NU, true); }
+      else { LIND_LAUNCH(0, NQ, false); LIND_LAUNCH(1, NV, false); LIND_LAUNCH(2, NU, false); }
+#undef LIND_LAUNCH
       h->launches += 3;
       return;
     }

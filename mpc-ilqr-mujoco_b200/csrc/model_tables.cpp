@@ -80,6 +80,12 @@ bool build_dyn_model(const H1Model& m, DynModel* d) {
   for (int b = 1; b < NB; ++b) d->nchild[m.parent[b]]++;
   for (int b = 1; b < NB; ++b)
     if (d->nchild[b] > 1 && d->depth[b] >= 3) return false;  // SEQ_MAXSAVE (h1_lin_dirs.cuh)
+  {  // hinged bodies by decreasing subtree size (stable): work order of the direction-uniform linearization
+    int n = 0;
+    for (int sz = NB; sz >= 1; --sz)
+      for (int b = 1; b < NB; ++b)
+        if (d->chain_end[b] - b + 1 == sz) d->dir_order[n++] = b;
+  }
   // thread-sequential f_D (h1_dyn_seq.cuh): specialised for base + two 5-hinge leg chains ending in the feet
   // (bodies 1-5, 6-10) + torso (11) + two 4-hinge arm chains below the torso (12-15, 16-19)
   {

@@ -99,3 +99,19 @@ extern "C" int emul_dyn_com_seq(int n, const double* x, double* com) {
   for (int i = 0; i < n; ++i) h1::dyn_com_seq(md, x + i * h1::NX, com + 3 * i);
   return 0;
 }
+
+// same columns through the sparsity-exploiting path of kernel k_linearize_cols (csrc/h1_lin_dirs.cuh): joint
+// directions walk only subtree(joint) with dual numbers, x / y columns are unit vectors
+extern "C" int emul_dyn_linearize_cols(const double* x, const double* u, double* A, double* B) {
+  static h1::DynModel md;
+  static bool init = false;
+  if (!init) { if (!h1::build_dyn_model(*h1_default_dynamics_model(), &md)) return -1; init = true; }
+  static h1::DynWarp w;
+  static h1::PrimalFactor pf;
+  h1::dyn_primal_factor_warp(md, w, x, u, nullptr, pf);
+  for (int e = 0; e < h1::NX + h1::NU; ++e) {
+    double* col = e < h1::NX ? A + e * h1::NX : B + (e - h1::NX) * h1::NX;
+    h1::linearize_column(md, x, u, pf, e, col);
+  }
+  return 0;
+}

@@ -83,6 +83,21 @@ def test_direction_per_thread_linearization_matches_oracle_ad(emul, oracle):
         assert np.abs(Be - B).max() <= 1e-10 * np.abs(B).max()
 
 
+def test_sparse_column_linearization_matches_oracle_ad(emul, oracle):
+    """kernel k_linearize_cols' per-column function: joint directions walk only subtree(joint) with dual numbers,
+    the x / y columns are unit vectors; against the oracle's forward-mode AD, incl. feet in contact and clamps."""
+    x, u = states(12, 9)
+    u[::3, 3] = 400.0
+    x[::2, 2] -= 0.06
+    for i in range(12):
+        A, B = oracle.dyn_linearize_ad(x[i], u[i])
+        Ae = np.empty((51, 51), order="F"); Be = np.empty((51, 19), order="F")
+        assert emul[0].emul_dyn_linearize_cols(P(x[i]), P(u[i]), P(Ae), P(Be)) == 0
+        assert np.abs(Ae - A).max() <= 1e-10 * np.abs(A).max()
+        assert np.abs(Be - B).max() <= 1e-10 * np.abs(B).max()
+        assert (Ae[:, 0] == np.eye(51)[0]).all() and (Ae[:, 1] == np.eye(51)[1]).all()
+
+
 @pytest.mark.parametrize("tag", ["standing", "walking"])
 def test_cost_quadratics_phases_match_oracle(emul, oracle, tag):
     s, w, win = make_oracle(tag)
