@@ -145,6 +145,10 @@ int h1ilqr_bias_forces(H1Ilqr* h, int n, const double* x, double* bias);
 /* Dynamics-model FK used to precompute references: CoM (subtree_com of the root) and ankle body
  * positions, RobotUtils::loadReferences (robot_utils.cpp:370-403). com [n][3], ee [n][2][3]. */
 int h1ilqr_reference_kinematics(H1Ilqr* h, int n, const double* x, double* com, double* ee);
+/* World positions of the 2 x 4 sole contact points of f_D for arbitrary states, pts [n][8][3] (left foot first).
+ * Input of the contact-schedule generation that replaces get_contacts.py:96-157 (MuJoCo foot-geom contacts with
+ * dist < 1e-3): a foot is in stance when one of its sole points is lower than the threshold. */
+int h1ilqr_sole_points(H1Ilqr* h, int n, const double* x, double* pts);
 
 /* ---- accessors (host copies). Sizes as in the conventions above. Any pointer may be NULL. ---- */
 int h1ilqr_set_trajectory(H1Ilqr* h, const double* xbar, const double* ubar);

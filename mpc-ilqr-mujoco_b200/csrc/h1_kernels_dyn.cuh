@@ -31,10 +31,10 @@ __global__ void k_dyn_step(const DynModel* gmd, int n, const double* __restrict_
   dyn_step_warp(*md, w, x + (size_t)i * NX, u + (size_t)i * NU, xn + (size_t)i * NX);
 }
 
-// ---- bias forces, dynamics-model CoM and ankle positions of arbitrary states (computeGravComp,
-//      loadReferences' per-row FK) ----
+// ---- bias forces, dynamics-model CoM, ankle positions and sole contact points of arbitrary states
+//      (computeGravComp, loadReferences' per-row FK, contact-schedule generation) ----
 __global__ void k_dyn_query(const DynModel* gmd, int n, const double* __restrict__ x, double* __restrict__ bias,
-                            double* __restrict__ com, double* __restrict__ ee) {
+                            double* __restrict__ com, double* __restrict__ ee, double* __restrict__ sole) {
   extern __shared__ __align__(16) unsigned char smem[];
   const DynModel* md;
   unsigned char* p = stage_model(smem, gmd, &md);
@@ -46,6 +46,8 @@ __global__ void k_dyn_query(const DynModel* gmd, int n, const double* __restrict
   if (bias && lane < NV) bias[(size_t)i * NV + lane] = w.biasv[lane];
   if (com && lane < 3) com[(size_t)i * 3 + lane] = w.com[lane];
   if (ee && lane < 6) ee[(size_t)i * 6 + lane] = w.q[lane % 3] + w.footr[lane / 3][lane % 3];
+  if (sole && lane < NCPT)
+    for (int c = 0; c < 3; ++c) sole[((size_t)i * NCPT + lane) * 3 + c] = w.q[c] + w.cp[lane][c];
 }
 
 // ---- nominal rollout xbar[t+1] = f_D(xbar[t], ubar[t]) with the trajectory cost as a by-product

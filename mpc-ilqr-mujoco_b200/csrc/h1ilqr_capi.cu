@@ -49,7 +49,8 @@ struct H1Ilqr {
   int launches = 0;
   size_t smem_lina = 0;
   int policy = H1ILQR_KERNELS_AUTO;
-  int seq_min_batch = 64;   // AUTO: batch at or above which rollouts / line searches run one THREAD per f_D evaluation (h1_dyn_seq.cuh)
+  int seq_min_batch = 768;  // AUTO: batch at or above which rollouts / line searches run one THREAD per f_D evaluation (h1_dyn_seq.cuh);
+                            // measured break-even with the warp-per-evaluation kernels: between 512 and 1024 instances
   size_t smem_seq = 0, smem_linc = 0;
   bool seq_ok = false;      // the model has the chain structure the thread-sequential f_D is specialised for
   long lin_cols_min_knots = 148 * 32;   // AUTO: B*N at or above which the direction-uniform linearization (32 knots per CTA) fills the GPU;
@@ -117,6 +118,7 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
     delete h; return set_err(H1ILQR_EARG, "model is not a DFS-ordered H1-like tree");
   }
   h->seq_ok = dm.seq_ok != 0;
+  if (const char* e = getenv("H1_SEQ_MIN_BATCH")) h->seq_min_batch = atoi(e);   // tuning experiments
 #define CUH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(H1ILQR_ECUDA, #call, e_); h1ilqr_destroy(h); return H1ILQR_ECUDA; } } while (0)
   CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CUH(cudaEventCreate(&h->ev[0])); CUH(cudaEventCreate(&h->ev[1]));
@@ -647,23 +649,30 @@ int h1ilqr_dynamics_step(H1Ilqr* h, int n, const double* x, const double* u, dou
   return 0;
 }
 
-static int query(H1Ilqr* h, int n, const double* x, double* bias, double* com, double* ee) {
+static int query(H1Ilqr* h, int n, const double* x, double* bias, double* com, double* ee, double* sole = nullptr) {
   if (n < 1 || !x) return set_err(H1ILQR_EARG, "bad query arguments");
-  int rc = ensure_scratch(h, (size_t)n * (NX + NV + 9) * sizeof(double));
+  int rc = ensure_scratch(h, (size_t)n * (NX + NV + 9 + 3 * NCPT) * sizeof(double));
   if (rc) return rc;
   double* dx = h->scratch; double* db = dx + (size_t)n * NX; double* dc = db + (size_t)n * NV; double* de = dc + (size_t)n * 3;
+  double* ds = de + (size_t)n * 6;
   H2D(dx, x, (size_t)n * NX * sizeof(double));
   k_dyn_query<<<(n + 3) / 4, 128, h->smem_dyn4, h->stream>>>(h->d_dyn, n, dx, bias ? db : nullptr, com ? dc : nullptr,
-                                                            ee ? de : nullptr);
+                                                            ee ? de : nullptr, sole ? ds : nullptr);
   LAUNCHED();
   if (bias) D2H(bias, db, (size_t)n * NV * sizeof(double));
   if (com) D2H(com, dc, (size_t)n * 3 * sizeof(double));
   if (ee) D2H(ee, de, (size_t)n * 6 * sizeof(double));
+  if (sole) D2H(sole, ds, (size_t)n * 3 * NCPT * sizeof(double));
   SYNC(); CU(cudaGetLastError());
   return 0;
 }
 int h1ilqr_bias_forces(H1Ilqr* h, int n, const double* x, double* bias) { GUARD(h); return query(h, n, x, bias, nullptr, nullptr); }
 int h1ilqr_reference_kinematics(H1Ilqr* h, int n, const double* x, double* com, double* ee) { GUARD(h); return query(h, n, x, nullptr, com, ee); }
+int h1ilqr_sole_points(H1Ilqr* h, int n, const double* x, double* pts) {
+  GUARD(h);
+  if (!pts) return set_err(H1ILQR_EARG, "null pts");
+  return query(h, n, x, nullptr, nullptr, nullptr, pts);
+}
 
 // ---------------- accessors ----------------
 #define COPY_PAIR(fn_get, fn_set, p1, n1, p2, n2)                                              \

@@ -20,7 +20,7 @@ EXPORTS = [
     "h1ilqr_horizon", "h1ilqr_set_weights", "h1ilqr_set_reference_window", "h1ilqr_initialize", "h1ilqr_solve",
     "h1ilqr_mpc_step", "h1ilqr_mpc_reset", "h1ilqr_rollout_nominal", "h1ilqr_linearize", "h1ilqr_cost_quadratics",
     "h1ilqr_backward_pass", "h1ilqr_line_search", "h1ilqr_total_cost", "h1ilqr_dynamics_step", "h1ilqr_bias_forces",
-    "h1ilqr_reference_kinematics", "h1ilqr_set_trajectory", "h1ilqr_get_trajectory", "h1ilqr_get_gains",
+    "h1ilqr_reference_kinematics", "h1ilqr_sole_points", "h1ilqr_set_trajectory", "h1ilqr_get_trajectory", "h1ilqr_get_gains",
     "h1ilqr_set_gains", "h1ilqr_get_linearization", "h1ilqr_set_linearization", "h1ilqr_get_cost_quadratics",
     "h1ilqr_set_cost_quadratics", "h1ilqr_get_regularization", "h1ilqr_set_regularization", "h1ilqr_get_solve_trace",
     "h1ilqr_upload_inputs", "h1ilqr_run_resident_steps", "h1ilqr_measure_fp64_peak", "h1ilqr_measure_fp64_mma_peak", "h1ilqr_enable_stage_timing", "h1ilqr_set_kernel_policy", "h1ilqr_get_stage_times", "h1ilqr_stream", "h1_default_dynamics_model",
@@ -195,6 +195,13 @@ class H1IlqrBatch:
         ee = np.empty((x.shape[0], 2, 3))
         _check(lib().h1ilqr_reference_kinematics(self._h, C.c_int(x.shape[0]), dptr(x), dptr(com), dptr(ee)))
         return com, ee
+
+    def sole_points(self, x):
+        """World positions [n][8][3] of the sole contact points (left foot's four first)."""
+        x = _f(x).reshape(-1, NX)
+        pts = np.empty((x.shape[0], 8, 3))
+        _check(lib().h1ilqr_sole_points(self._h, C.c_int(x.shape[0]), dptr(x), dptr(pts)))
+        return pts
 
     # ---- accessors ----
     def get_trajectory(self):

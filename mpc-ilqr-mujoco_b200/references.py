@@ -51,6 +51,26 @@ def load_contact_csv(path):
     return np.asarray(rows, dtype=np.int32)
 
 
+def contact_schedule_from_states(q, sole_points, threshold=1e-3):
+    """Contact schedule [T][2] (left, right; 1 = stance) of a reference motion q [T][26]: the counterpart of the
+    reference's offline tool (/root/reference/get_contacts.py:96-157), which runs MuJoCo's collision detection on
+    the foot geoms and marks a foot in contact when a contact has dist < 1e-3. Here a foot is in contact when
+    one of its four sole points (the contact points of f_D) is lower than `threshold` above the ground plane.
+    `sole_points(x[n,51]) -> [n][8][3]` is H1IlqrBatch.sole_points (GPU)."""
+    q = np.asarray(q, dtype=np.float64)
+    x = np.hstack([q, np.zeros((q.shape[0], NV))])
+    z = np.asarray(sole_points(x))[:, :, 2].reshape(q.shape[0], 2, 4)
+    return (z.min(axis=2) < threshold).astype(np.int32)
+
+
+def write_contact_csv(path, contact):
+    """Same file format as get_contacts.py writes (pandas to_csv, index=False): header + `int,int` rows."""
+    with open(path, "w") as f:
+        f.write("left_foot,right_foot\n")
+        for l, r in np.asarray(contact, dtype=int):
+            f.write(f"{l},{r}\n")
+
+
 class ReferenceSet:
     """x_ref_full / com_ref_full / ee_pos_ref_full / contact schedule of one reference motion."""
 

@@ -387,3 +387,33 @@ def test_full_size_batch_properties(gpu):
     sc.rollout_nominal(x0[:64])
     assert (sc.get_trajectory()[0] == xc).all()
     assert np.abs(np.linalg.norm(xg[:, 1:, 3:7], axis=2) - 1).max() < 1e-12
+
+
+def test_contact_schedule_generation(gpu, tmp_path):
+    """contact schedule from the sole points of f_D (replaces get_contacts.py's MuJoCo collision
+    query). Known answers: flat standing pose -> all eight points at the same height under the ankles; the
+    standing reference is double support throughout; on the walking reference the schedule agrees with the one the
+    reference ships (generated with MuJoCo mesh-hull contacts) on most rows; the CSV round-trips."""
+    import os
+    from helpers import ROOT
+    from mpc_ilqr_mujoco_b200.references import contact_schedule_from_states, load_contact_csv, write_contact_csv
+    s = gpu.H1IlqrBatch(Config().build_weights(), N=25, batch=1)
+    x0 = standing_state()
+    pts = s.sole_points(x0[None])[0]
+    _, ee = s.reference_kinematics(x0[None])
+    m = gpu.default_dynamics_model()
+    for f in range(2):
+        for c in range(4):
+            want = ee[0, f] + np.array(m.foot_pts[f][c])     # identity orientation, zero joint angles
+            assert np.abs(pts[4 * f + c] - want).max() < 1e-12
+    d = np.load(os.path.join(ROOT, "data", "h1_refs.npz"))
+    cs = contact_schedule_from_states(d["standing_q"], s.sole_points)
+    assert cs.shape == (d["standing_q"].shape[0], 2) and (cs == 1).all()
+    cw = contact_schedule_from_states(d["walking_q"], s.sole_points)    # threshold 1e-3 like get_contacts.py:141
+    shipped = d["walking_contact"][:cw.shape[0]]
+    agree = (cw[:shipped.shape[0]] == shipped).mean()
+    print("walking schedule agreement with the shipped CSV:", agree, "stance fractions", cw.mean(axis=0), shipped.mean(axis=0))
+    assert agree > 0.8
+    p = tmp_path / "contact.csv"
+    write_contact_csv(str(p), cw)
+    assert (load_contact_csv(str(p)) == cw).all()
