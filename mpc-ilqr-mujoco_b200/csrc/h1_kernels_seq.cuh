@@ -132,10 +132,13 @@ k_line_search_seq(const DynModel* gmd, const H1Weights* gw, const H1SolverOption
   double* xn = xnew + ((size_t)instc * H1ILQR_NALPHA + cand) * (N + 1) * NX;
   double* un = unew + ((size_t)instc * H1ILQR_NALPHA + cand) * N * NU;
   double total = 0.0;
+  // the thread's current state lives in shared memory (odd per-thread stride: conflict free); every f_D evaluation
+  // and cost term reads it from there instead of going back to the global trajectory
+  double* xs = reinterpret_cast<double*>(smem + ((sizeof(DynModel) + 15) / 16) * 16) + threadIdx.x * NX;
   if (act) {
     const double alpha = gopt->alphas[cand];
     const RefView r = refs.view(inst);
-    for (int i = 0; i < NX; ++i) xn[i] = x0 ? x0[(size_t)inst * NX + i] : xb[i];
+    for (int i = 0; i < NX; ++i) { const double v = x0 ? x0[(size_t)inst * NX + i] : xb[i]; xs[i] = v; xn[i] = v; }
     double u[NU], com[3];
 #pragma unroll 1
     for (int t = 0; t < N; ++t) {
@@ -146,20 +149,22 @@ k_line_search_seq(const DynModel* gmd, const H1Weights* gw, const H1SolverOption
       // u += K_t (x - xbar_t): three state entries per trip so that 57 loads of K are in flight per thread
 #pragma unroll 1
       for (int l = 0; l < NX; l += 3) {
-        const double dx0 = xn[t * NX + l] - xb[t * NX + l];
-        const double dx1 = xn[t * NX + l + 1] - xb[t * NX + l + 1];
-        const double dx2 = xn[t * NX + l + 2] - xb[t * NX + l + 2];
+        const double dx0 = xs[l] - xb[t * NX + l];
+        const double dx1 = xs[l + 1] - xb[t * NX + l + 1];
+        const double dx2 = xs[l + 2] - xb[t * NX + l + 2];
         const double* Kl = Kt + l * NU;
 #pragma unroll
         for (int i = 0; i < NU; ++i) u[i] += Kl[i] * dx0 + Kl[NU + i] * dx1 + Kl[2 * NU + i] * dx2;
       }
 #pragma unroll
       for (int i = 0; i < NU; ++i) un[t * NU + i] = u[i];
-      dyn_step_seq(*md, xn + t * NX, u, xn + (t + 1) * NX, nullptr, com);
-      total += knot_cost_seq(*md, *gw, r, t, xn + t * NX, u, com, false);
+      double* xnext = xn + (t + 1) * NX;
+      dyn_step_seq(*md, xs, u, xnext, nullptr, com);
+      total += knot_cost_seq(*md, *gw, r, t, xs, u, com, false);
+      for (int i = 0; i < NX; ++i) xs[i] = xnext[i];
     }
-    dyn_com_seq(*md, xn + N * NX, com);
-    total += knot_cost_seq(*md, *gw, r, N, xn + N * NX, nullptr, com, true);
+    dyn_com_seq(*md, xs, com);
+    total += knot_cost_seq(*md, *gw, r, N, xs, nullptr, com, true);
   }
   __syncwarp();
   const double base = act ? baseline[inst] : 0.0;

@@ -5,7 +5,8 @@
 //   largest-|diagonal| pivoting like Eigen::LDLT), Vx = Qx + K'Quu k + K'Qu + Qxu k,
 //   Vxx = sym(Qxx + K'QuuK + K'Qxu' + Qxu K).
 // Contractions (all on the fp64 tensor cores, mma.sync m8n8k4 = SASS DMMA, operands in shared memory):
-//   G1  W = Vxx [A|B]                       51x70x51      (W is shared by the next two)
+//   G1  W = Vxx [A|B]                       51x70x51      (W is shared by the next two; its B block is computed
+//                                                         first so that Quu and its factorisation start early)
 //   G2  [Qxx|Qxu] = A' W                    51x70x51
 //   G3  Quu = B' W[:,51:]                   19x19x51
 //   G4  G = Quu K + 2 Qxu'                  19x51x19
@@ -17,6 +18,7 @@
 // Leading dimensions are = 4 (mod 8) doubles: every m8n8k4 fragment load is bank-conflict free.
 #pragma once
 #include "h1_common.cuh"
+#include <type_traits>
 
 namespace h1 {
 
@@ -154,12 +156,17 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
     const double* luut = luu + ((size_t)inst * N + t) * NU * NU;
     cp_async_commit_wait_all();
     __syncthreads();
-    // ---- G1: W = Vxx [A|B] (warps 0..6: one 8-row strip each) | warp 7: Qx = lx + A'Vx, Qu = lu + B'Vx ----
+    // ---- G1b: W(:, 48..71) = Vxx [A|B](:, 48..71) — the B block, which Quu needs first (warps 0..6: one 8-row
+    //      strip each) | warp 7: Qx = lx + A'Vx, Qu = lu + B'Vx ----
+    auto w_strip = [&](auto nt_tag, int n0) {
+      constexpr int NT = decltype(nt_tag)::value;
+      mma_strip_store<NT>(13, 8 * warp, n0,
+                          [&](int r, int k) { return r < LDX ? s.V[k * LDX + r] : 0.0; },
+                          [&](int k, int c) { return c < NXU ? s.AB[c * LDX + k] : 0.0; },
+                          [&](int r, int c, double v) { if (r < LDX && c < NXU) s.W[c * LDX + r] = v; });   // row 51 of W = 0
+    };
     if (warp < 7) {
-      mma_strip_store<9>(13, 8 * warp, 0,
-                         [&](int r, int k) { return r < LDX ? s.V[k * LDX + r] : 0.0; },
-                         [&](int k, int c) { return c < NXU ? s.AB[c * LDX + k] : 0.0; },
-                         [&](int r, int c, double v) { if (r < LDX && c < NXU) s.W[c * LDX + r] = v; });   // row 51 of W = 0
+      w_strip(std::integral_constant<int, 3>(), 48);
     } else {
       for (int i = lane; i < NXU; i += 32) {
         double acc = 0.0;
@@ -169,7 +176,7 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
       }
     }
     __syncthreads();
-    // ---- G3: Quu = B' W_B + luu + lam I, 9 tiles over the 8 warps (first, so that its factorisation overlaps G2) ----
+    // ---- G3: Quu = B' W_B + luu + lam I, 9 tiles over the 8 warps ----
     {
       auto fa = [&](int r, int k) { return s.AB[(NX + min(r, NU - 1)) * LDX + k]; };
       auto fb = [&](int k, int c) { return s.W[(NX + min(c, NU - 1)) * LDX + k]; };
@@ -180,8 +187,11 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
         });
     }
     __syncthreads();
-    // ---- G2: [Qxx | Qxu] = A' W (warps 0..6; Qxx -> s.V, Qxu -> s.Qxu) | warp 7: pivoted LDL^T of Quu ----
+    // ---- warps 0..6: G1a: W(:, 0..47) = Vxx A(:, 0..47), then G2: [Qxx | Qxu] = A' W (Qxx -> s.V, Qxu -> s.Qxu)
+    //      | warp 7: pivoted LDL^T of Quu, hidden behind both contractions ----
     if (warp < 7) {
+      w_strip(std::integral_constant<int, 6>(), 0);
+      asm volatile("bar.sync 1, 224;" ::: "memory");   // W complete (the seven contraction warps only)
       mma_strip_store<9>(13, 8 * warp, 0,
                          [&](int r, int k) { return s.AB[r * LDX + k]; },   // A'(r,k) = A(k,r); rows 51..55: discarded garbage
                          [&](int k, int c) { return c < NXU ? s.W[c * LDX + k] : 0.0; },

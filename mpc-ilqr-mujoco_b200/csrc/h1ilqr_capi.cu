@@ -51,7 +51,7 @@ struct H1Ilqr {
   int policy = H1ILQR_KERNELS_AUTO;
   int seq_min_batch = 768;  // AUTO: batch at or above which rollouts / line searches run one THREAD per f_D evaluation (h1_dyn_seq.cuh);
                             // measured break-even with the warp-per-evaluation kernels: between 512 and 1024 instances
-  size_t smem_seq = 0, smem_linc = 0;
+  size_t smem_seq = 0, smem_seq_ls = 0, smem_linc = 0;
   bool seq_ok = false;      // the model has the chain structure the thread-sequential f_D is specialised for
   long lin_cols_min_knots = 148 * 32;   // AUTO: B*N at or above which the direction-uniform linearization (32 knots per CTA) fills the GPU;
                                         // below it the knot-major thread-per-column kernel (k_linearize_dirs) is the faster one
@@ -167,7 +167,8 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   LINC_ATTR(0) LINC_ATTR(1) LINC_ATTR(2) LINC_ATTR(3) LINC_ATTR(4)
 #undef LINC_ATTR
   if (const char* e = getenv("H1_SEQ_SMEM_PAD")) h->smem_seq += (size_t)atoi(e) * 1024;   // experiment: limits resident CTAs
-  CUH(cudaFuncSetAttribute(k_line_search_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_seq));
+  h->smem_seq_ls = h->smem_seq + (size_t)SEQ_THREADS * NX * sizeof(double);
+  CUH(cudaFuncSetAttribute(k_line_search_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_seq_ls));
   CUH(cudaFuncSetAttribute(k_rollout_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_seq));
   CUH(cudaFuncSetAttribute(k_dyn_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
   CUH(cudaFuncSetAttribute(k_dyn_query, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
@@ -305,7 +306,7 @@ static void launch_line_search(H1Ilqr* h, const int* mask) {
   if (h->seq_ok && use_batched(h, h->B, h->seq_min_batch)) {   // one thread per (instance, candidate)
     const long threads = (long)h->B * H1ILQR_NALPHA;
     const int* list = (mask && mask == h->active) ? h->act_list : ((mask && mask == h->second) ? h->sec_list : nullptr);
-    k_line_search_seq<<<(unsigned)((threads + SEQ_THREADS - 1) / SEQ_THREADS), SEQ_THREADS, h->smem_seq, h->stream>>>(
+    k_line_search_seq<<<(unsigned)((threads + SEQ_THREADS - 1) / SEQ_THREADS), SEQ_THREADS, h->smem_seq_ls, h->stream>>>(
         h->d_dyn, h->d_w, h->d_opt, ref_table(h), h->B, h->N, mask, list, list ? h->list_count + (mask == h->second ? 1 : 0) : nullptr,
         h->x0, h->nominal_cost, h->xbar, h->ubar, h->K, h->kff,
         h->xnew, h->unew, h->ls_ok, h->ls_cost, h->ls_alpha);
