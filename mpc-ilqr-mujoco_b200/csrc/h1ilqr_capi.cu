@@ -51,7 +51,7 @@ struct H1Ilqr {
   int policy = H1ILQR_KERNELS_AUTO;
   int seq_min_batch = 768;  // AUTO: batch at or above which rollouts / line searches run one THREAD per f_D evaluation (h1_dyn_seq.cuh);
                             // measured break-even with the warp-per-evaluation kernels: between 512 and 1024 instances
-  size_t smem_seq = 0, smem_seq_ls = 0, smem_linc = 0;
+  size_t smem_seq = 0, smem_seq_ls = 0, smem_linc[3] = {0, 0, 0};
   bool seq_ok = false;      // the model has the chain structure the thread-sequential f_D is specialised for
   long lin_cols_min_knots = 148 * 32;   // AUTO: B*N at or above which the direction-uniform linearization (32 knots per CTA) fills the GPU;
                                         // below it the knot-major thread-per-column kernel (k_linearize_dirs) is the faster one
@@ -160,11 +160,11 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   h->smem_ls = mdl + H1ILQR_NALPHA * sizeof(DynWarp) + (H1ILQR_NALPHA + H1ILQR_NALPHA * (NX + NU)) * sizeof(double);
   h->smem_ric = sizeof(RiccatiSmem);
   h->smem_seq = mdl;
-  h->smem_linc = mdl + LINC_SMEM_DOUBLES * sizeof(double);
 #define LINC_ATTR(CLS) \
-  CUH(cudaFuncSetAttribute(k_linearize_cols<CLS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_linc)); \
-  CUH(cudaFuncSetAttribute(k_linearize_cols<CLS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_linc));
-  LINC_ATTR(0) LINC_ATTR(1) LINC_ATTR(2) LINC_ATTR(3) LINC_ATTR(4)
+  h->smem_linc[CLS] = mdl + linc_smem_doubles(CLS) * sizeof(double); \
+  CUH(cudaFuncSetAttribute(k_linearize_cols<CLS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_linc[CLS])); \
+  CUH(cudaFuncSetAttribute(k_linearize_cols<CLS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_linc[CLS]));
+  LINC_ATTR(0) LINC_ATTR(1) LINC_ATTR(2)
 #undef LINC_ATTR
   if (const char* e = getenv("H1_SEQ_SMEM_PAD")) h->smem_seq += (size_t)atoi(e) * 1024;   // experiment: limits resident CTAs
   h->smem_seq_ls = h->smem_seq + (size_t)SEQ_THREADS * NX * sizeof(double);
@@ -261,11 +261,11 @@ static void launch_linearize(H1Ilqr* h, const int* mask, bool factors_ready = fa
     if (use_batched(h, knots, h->lin_cols_min_knots)) {  // one thread per column, direction-uniform warps
       const unsigned kb = (unsigned)((knots + LINC_KNOTS - 1) / LINC_KNOTS);
 #define LINC_LAUNCH(CLS, TREE)                                                                                        \
-  k_linearize_cols<CLS, TREE><<<kb, LINC_THREADS, h->smem_linc, h->stream>>>(                                         \
+  k_linearize_cols<CLS, TREE><<<kb, linc_warps(CLS) * 32, h->smem_linc[CLS], h->stream>>>(                            \
       h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm)
-      if (h->seq_ok) { LINC_LAUNCH(0, true); LINC_LAUNCH(1, true); LINC_LAUNCH(2, true); LINC_LAUNCH(3, true); LINC_LAUNCH(4, true); }
-      else { LINC_LAUNCH(0, false); LINC_LAUNCH(1, false); LINC_LAUNCH(2, false); LINC_LAUNCH(3, false); LINC_LAUNCH(4, false); }
-      h->launches += 5;
+      if (h->seq_ok) { LINC_LAUNCH(0, true); LINC_LAUNCH(1, true); LINC_LAUNCH(2, true); }
+      else { LINC_LAUNCH(0, false); LINC_LAUNCH(1, false); LINC_LAUNCH(2, false); }
+      h->launches += 3;
 #undef LINC_LAUNCH
       return;
     }
