@@ -35,7 +35,8 @@ struct RiccatiSmem {
   double Kt[LDU * 56];        // solves: columns 0..50 -> K(:,j), column 51 -> kff; pad row 19 stays zero
   double Quu[LDU * LDU];      // pad row/column 19 stay zero
   double Ls[NU * NU];         // unit-lower factor of the permuted LDL^T
-  double Vx[NX], Qx[NX], Qu[NU], D[NU], tmp[NU];
+  double Vx[LDX], Qx[NX], Qu[NU], D[NU], tmp[NU];   // Vx[51] is a zero pad (Vx rides along as an extra column of W)
+  double lq[NX + NU + NU * NU + 1];   // lx_t, lu_t, luu_t of the current knot (prefetched with [A|B])
   int perm[NU];
 };
 constexpr int RIC_G_OFF = 0;              // G inside W
@@ -137,6 +138,12 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
     const double* Bt = Bm + ((size_t)inst * N + t) * NX * NU;
     for (int i = tid; i < NX * NX; i += nt) { const int c = i / NX, r = i - c * NX; cp_async8(&s.AB[c * LDX + r], At + i); }
     for (int i = tid; i < NX * NU; i += nt) { const int c = i / NX, r = i - c * NX; cp_async8(&s.AB[(NX + c) * LDX + r], Bt + i); }
+    // the small cost terms of the same knot: read in the epilogues of G2 / G3, where a global load would stall
+    const double* lxt = lx + ((size_t)inst * (N + 1) + t) * NX;
+    const double* lut = lu + ((size_t)inst * N + t) * NU;
+    const double* luut = luu + ((size_t)inst * N + t) * NU * NU;
+    for (int i = tid; i < NX + NU + NU * NU; i += nt)
+      cp_async8(&s.lq[i], i < NX ? lxt + i : (i < NX + NU ? lut + (i - NX) : luut + (i - NX - NU)));
   };
   // zero pads (never written afterwards) and the terminal value function
   for (int i = tid; i < LDX * LDX; i += nt) s.V[i] = 0.0;
@@ -145,19 +152,19 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
   for (int i = tid; i < LDU * LDU; i += nt) s.Quu[i] = 0.0;
   __syncthreads();
   prefetch_ab(N - 1);
-  for (int i = tid; i < NX; i += nt) s.Vx[i] = lxN[i];
+  for (int i = tid; i < LDX; i += nt) s.Vx[i] = (i < NX) ? lxN[i] : 0.0;
   for (int i = tid; i < NX * NX; i += nt) { const int c = i / NX, r = i - c * NX; s.V[c * LDX + r] = lxxN[i]; }
   bool nonfinite = false;
   double* const G = s.W + RIC_G_OFF;
   double* const Lpre = s.W + RIC_LXX_OFF;
   for (int t = N - 1; t >= 0; --t) {
-    const double* lxt = lx + ((size_t)inst * (N + 1) + t) * NX;
-    const double* lut = lu + ((size_t)inst * N + t) * NU;
-    const double* luut = luu + ((size_t)inst * N + t) * NU * NU;
+    const double* lxt = s.lq;
+    const double* lut = s.lq + NX;
+    const double* luut = s.lq + NX + NU;
     cp_async_commit_wait_all();
     __syncthreads();
     // ---- G1b: W(:, 48..71) = Vxx [A|B](:, 48..71) — the B block, which Quu needs first (warps 0..6: one 8-row
-    //      strip each) | warp 7: Qx = lx + A'Vx, Qu = lu + B'Vx ----
+    //      strip each) ----
     auto w_strip = [&](auto nt_tag, int n0) {
       constexpr int NT = decltype(nt_tag)::value;
       mma_strip_store<NT>(13, 8 * warp, n0,
@@ -165,40 +172,36 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
                           [&](int k, int c) { return c < NXU ? s.AB[c * LDX + k] : 0.0; },
                           [&](int r, int c, double v) { if (r < LDX && c < NXU) s.W[c * LDX + r] = v; });   // row 51 of W = 0
     };
-    if (warp < 7) {
-      w_strip(std::integral_constant<int, 3>(), 48);
-    } else {
-      for (int i = lane; i < NXU; i += 32) {
-        double acc = 0.0;
-        const double* col = s.AB + i * LDX;
-        for (int l = 0; l < NX; ++l) acc += col[l] * s.Vx[l];
-        if (i < NX) s.Qx[i] = lxt[i] + acc; else s.Qu[i - NX] = lut[i - NX] + acc;
-      }
-    }
+    if (warp < 7) w_strip(std::integral_constant<int, 3>(), 48);
     __syncthreads();
-    // ---- G3: Quu = B' W_B + luu + lam I, 9 tiles over the 8 warps ----
+    // ---- G3: [Quu | B'Vx] = B' [W_B | Vx] + luu + lam I, 9 tiles over the 8 warps; the spare column 19 of the last
+    //      tile column carries Vx and yields Qu = lu + B'Vx ----
     {
       auto fa = [&](int r, int k) { return s.AB[(NX + min(r, NU - 1)) * LDX + k]; };
-      auto fb = [&](int k, int c) { return s.W[(NX + min(c, NU - 1)) * LDX + k]; };
+      auto fb = [&](int k, int c) { return c < NU ? s.W[(NX + c) * LDX + k] : (c == NU ? s.Vx[k] : 0.0); };
 #pragma unroll 1
       for (int tile = warp; tile < 9; tile += 8)
         mma_strip_store<1>(13, 8 * (tile / 3), 8 * (tile % 3), fa, fb, [&](int r, int c, double v) {
-          if (r < NU && c < NU) s.Quu[c * LDU + r] = v + luut[c * NU + r] + ((c == r) ? lam : 0.0);
+          if (r >= NU) return;
+          if (c < NU) s.Quu[c * LDU + r] = v + luut[c * NU + r] + ((c == r) ? lam : 0.0);
+          else if (c == NU) s.Qu[r] = lut[r] + v;
         });
     }
     __syncthreads();
-    // ---- warps 0..6: G1a: W(:, 0..47) = Vxx A(:, 0..47), then G2: [Qxx | Qxu] = A' W (Qxx -> s.V, Qxu -> s.Qxu)
+    // ---- warps 0..6: G1a: W(:, 0..47) = Vxx A(:, 0..47), then G2: [Qxx | Qxu | A'Vx] = A' [W | Vx] (Qxx -> s.V,
+    //      Qxu -> s.Qxu, the spare column 70 of the last tile carries Vx and yields Qx = lx + A'Vx)
     //      | warp 7: pivoted LDL^T of Quu, hidden behind both contractions ----
     if (warp < 7) {
       w_strip(std::integral_constant<int, 6>(), 0);
       asm volatile("bar.sync 1, 224;" ::: "memory");   // W complete (the seven contraction warps only)
       mma_strip_store<9>(13, 8 * warp, 0,
                          [&](int r, int k) { return s.AB[r * LDX + k]; },   // A'(r,k) = A(k,r); rows 51..55: discarded garbage
-                         [&](int k, int c) { return c < NXU ? s.W[c * LDX + k] : 0.0; },
+                         [&](int k, int c) { return c < NXU ? s.W[c * LDX + k] : (c == NXU ? s.Vx[k] : 0.0); },
                          [&](int r, int c, double v) {
                            if (r >= NX) return;
                            if (c < NX) s.V[c * LDX + r] = v;
                            else if (c < NXU) s.Qxu[(c - NX) * LDX + r] = v;
+                           else if (c == NXU) s.Qx[r] = lxt[r] + v;
                          });
     } else {
       if (quu_ldlt(s)) {          // Eigen::LLT failed: Quu += 1e-4 I once, no re-check (quirk Q9), refactor
