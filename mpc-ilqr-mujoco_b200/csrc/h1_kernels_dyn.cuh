@@ -244,21 +244,34 @@ __host__ __device__ constexpr size_t linc_smem_doubles(int cls) {
 template <int CLS, bool H1TREE>
 __global__ void __launch_bounds__(LINC_THREADS)
 k_linearize_cols(const DynModel* gmd, long nknots, int N, const int* __restrict__ active,
+                 const int* __restrict__ list, const int* __restrict__ list_count,
                  const double* __restrict__ xbar, const double* __restrict__ ubar,
                  const PrimalFactor* __restrict__ pf_g, double* __restrict__ A, double* __restrict__ Bm) {
   extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ int okf[LINC_KNOTS];
+  // `list` (optional): compact list of the active instances built on the device by k_solve_state; slot s of the
+  // grid then works on knot (s % N) of instance list[s / N], so every CTA is full however sparse the active set is.
+  __shared__ long kid[LINC_KNOTS];                    // global knot id (instance * N + t) of each slot, -1: nothing to do
   __shared__ int next_item, rot_done;
   constexpr int NW = linc_warps(CLS);
   const long knot0 = (long)blockIdx.x * LINC_KNOTS;
+  if (list) nknots = min(nknots, (long)(*list_count) * N);
+  if (knot0 >= nknots) return;
   const int nk = (int)min((long)LINC_KNOTS, nknots - knot0);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid < LINC_KNOTS) okf[tid] = (tid < nk) && (!active || active[(knot0 + tid) / N]);
+  if (tid < LINC_KNOTS) {
+    long id = -1;
+    if (tid < nk) {
+      const long sl = knot0 + tid;
+      if (list) id = (long)list[sl / N] * N + sl % N;
+      else if (!active || active[sl / N]) id = sl;
+    }
+    kid[tid] = id;
+  }
   if (tid == 0) { next_item = 0; rot_done = 0; }
   const DynModel* md;
   unsigned char* p = stage_model(smem, gmd, &md);    // (has a __syncthreads)
   bool any = false;
-  for (int k = 0; k < nk; ++k) any |= okf[k] != 0;
+  for (int k = 0; k < nk; ++k) any |= kid[k] >= 0;
   if (!any) return;                                   // all 32 knots belong to finished instances
   double* fac = reinterpret_cast<double*>(p);        // [LINC_KNOTS][LINC_FS]
   double* xs = fac + LINC_KNOTS * LINC_FS;           // [LINC_KNOTS][NX]
@@ -267,28 +280,35 @@ k_linearize_cols(const DynModel* gmd, long nknots, int N, const int* __restrict_
   double* tile = qj + LINC_KNOTS * LINC_QJ + warp * LINC_KNOTS * NX;   // this warp's [LINC_KNOTS][NX]
   double* trot = qj + LINC_KNOTS * LINC_QJ + NW * LINC_KNOTS * NX;     // (CLS 2) [3][LINC_KNOTS][NV]
   {
-    const double* src = reinterpret_cast<const double*>(pf_g + knot0);
     constexpr int DOFF = NV * MAXSLOT;               // PrimalFactor::D
     for (int i = tid; i < nk * LINC_FS; i += NW * 32) {
-      const int j = i % LINC_FS;
-      const double v = src[i];
+      const int k = i / LINC_FS, j = i - k * LINC_FS;
+      const long id = kid[k];
+      if (id < 0) continue;
+      const double v = reinterpret_cast<const double*>(pf_g + id)[j];
       fac[i] = (j >= DOFF && j < DOFF + NV) ? 1.0 / v : v;
     }
     for (int i = tid; i < nk * NX; i += NW * 32) {
       const int k = i / NX, j = i - k * NX;
-      const long knot = knot0 + k, inst = knot / N;
-      xs[i] = xbar[((size_t)inst * (N + 1) + (knot - inst * N)) * NX + j];
+      const long id = kid[k];
+      if (id < 0) continue;
+      const long inst = id / N;
+      xs[i] = xbar[((size_t)inst * (N + 1) + (id - inst * N)) * NX + j];
     }
-    for (int i = tid; i < nk * NU; i += NW * 32) us[i] = ubar[(size_t)knot0 * NU + i];
+    for (int i = tid; i < nk * NU; i += NW * 32) {
+      const int k = i / NU, j = i - k * NU;
+      const long id = kid[k];
+      if (id >= 0) us[i] = ubar[(size_t)id * NU + j];
+    }
   }
   __syncthreads();
   if (tid < LINC_KNOTS * QJ_DIRS) {   // Jacobians of the quaternion update: one (knot, direction) per thread
     const int k = tid / QJ_DIRS, d = tid - k * QJ_DIRS;
-    if (k < nk && okf[k])
+    if (k < nk && kid[k] >= 0)
       quat_step_jac_dir(*md, xs + k * NX, reinterpret_cast<const PrimalFactor*>(fac + k * LINC_FS)->a, d, qj + k * LINC_QJ + 4 * d);
   }
   __syncthreads();
-  const bool ok = lane < nk && okf[lane];
+  const bool ok = lane < nk && kid[lane] >= 0;
   const double* x = xs + lane * NX;
   const PrimalFactor* pf = reinterpret_cast<const PrimalFactor*>(fac + lane * LINC_FS);   // (D holds reciprocals)
   double* col = tile + lane * NX;
@@ -353,15 +373,15 @@ k_linearize_cols(const DynModel* gmd, long nknots, int N, const int* __restrict_
       if (lane == 0) atomicAdd(&rot_done, 1);
       continue;
     }
-    // the 32 columns of this item: contiguous 51-double runs, 2 per lane and knot pair
+    // the 32 columns of this item: contiguous 51-double runs
     {
-      double* dst0 = (seed >= NX) ? Bm + (size_t)knot0 * NX * NU + (size_t)(seed - NX) * NX
-                                  : A + (size_t)knot0 * NX * NX + (size_t)seed * NX;
+      double* dst0 = (seed >= NX) ? Bm + (size_t)(seed - NX) * NX : A + (size_t)seed * NX;
       const size_t kstride = (seed >= NX) ? (size_t)NX * NU : (size_t)NX * NX;
       int k = 0, j = lane;
 #pragma unroll 1
       for (int e = lane; e < nk * NX; e += 32) {
-        if (okf[k]) dst0[(size_t)k * kstride + j] = tile[e];
+        const long id = kid[k];
+        if (id >= 0) dst0[(size_t)id * kstride + j] = tile[e];
         j += 32;
         if (j >= NX) { j -= NX; ++k; }
       }

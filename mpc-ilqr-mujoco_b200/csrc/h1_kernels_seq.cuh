@@ -86,16 +86,22 @@ k_rollout_seq(const DynModel* gmd, const H1Weights* gw, RefTable refs, int B, in
 //      knot-parallel replacement of the nominal rollout in iterations >= 1, where the rollout would only
 //      reproduce the trajectory the line search has just accepted (f_D is deterministic) ----
 __global__ void __launch_bounds__(SEQ_ROLL_THREADS)
-k_primal_factor_seq(const DynModel* gmd, int B, int N, const int* __restrict__ active, const double* __restrict__ xbar,
+k_primal_factor_seq(const DynModel* gmd, int B, int N, const int* __restrict__ active, const int* __restrict__ list,
+                    const int* __restrict__ list_count, const double* __restrict__ xbar,
                     const double* __restrict__ ubar, PrimalFactor* __restrict__ pf_out) {
   extern __shared__ __align__(16) unsigned char smem[];
+  const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  // `list` (optional): compact list of the active instances (k_solve_state): full warps however sparse the set is
+  if (list && (long)blockIdx.x * blockDim.x >= (long)(*list_count) * N) return;
   const DynModel* md;
   stage_model(smem, gmd, &md);
-  const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= (long)B * N) return;
-  const int inst = (int)(k / N), t = (int)(k - (long)inst * N);
-  if (active && !active[inst]) return;
-  dyn_step_seq(*md, xbar + ((size_t)inst * (N + 1) + t) * NX, ubar + ((size_t)inst * N + t) * NU, nullptr, pf_out + k, nullptr);
+  if (s >= (long)B * N) return;
+  int inst = (int)(s / N);
+  const int t = (int)(s - (long)inst * N);
+  if (list) { if (inst >= *list_count) return; inst = list[inst]; }
+  else if (active && !active[inst]) return;
+  dyn_step_seq(*md, xbar + ((size_t)inst * (N + 1) + t) * NX, ubar + ((size_t)inst * N + t) * NU, nullptr,
+               pf_out + (size_t)inst * N + t, nullptr);
 }
 
 // ---- line search, one thread per (instance, alpha candidate); the 8 candidates of an instance sit in 8

@@ -246,8 +246,9 @@ static void launch_rollout(H1Ilqr* h, const int* mask, const double* x0_dev, int
 static void launch_factors(H1Ilqr* h, const int* mask) {
   const long knots = (long)h->B * h->N;
   if (h->seq_ok && use_batched(h, h->B, h->seq_min_batch)) {
+    const int* list = (mask && mask == h->active) ? h->act_list : nullptr;
     k_primal_factor_seq<<<(unsigned)((knots + SEQ_ROLL_THREADS - 1) / SEQ_ROLL_THREADS), SEQ_ROLL_THREADS, h->smem_seq, h->stream>>>(
-        h->d_dyn, h->B, h->N, mask, h->xbar, h->ubar, h->pf);
+        h->d_dyn, h->B, h->N, mask, list, list ? h->list_count : nullptr, h->xbar, h->ubar, h->pf);
   } else {
     k_primal_factor<<<(int)((knots + 3) / 4), 128, h->smem_dyn4, h->stream>>>(h->d_dyn, h->B, h->N, mask, h->xbar, h->ubar, h->pf);
   }
@@ -260,9 +261,10 @@ static void launch_linearize(H1Ilqr* h, const int* mask, bool factors_ready = fa
     const long knots = (long)h->B * h->N;
     if (use_batched(h, knots, h->lin_cols_min_knots)) {  // one thread per column, direction-uniform warps
       const unsigned kb = (unsigned)((knots + LINC_KNOTS - 1) / LINC_KNOTS);
+      const int* list = (mask && mask == h->active) ? h->act_list : nullptr;   // compact active list (k_solve_state)
 #define LINC_LAUNCH(CLS, TREE)                                                                                        \
   k_linearize_cols<CLS, TREE><<<kb, linc_warps(CLS) * 32, h->smem_linc[CLS], h->stream>>>(                            \
-      h->d_dyn, knots, h->N, mask, h->xbar, h->ubar, h->pf, h->A, h->Bm)
+      h->d_dyn, knots, h->N, mask, list, list ? h->list_count : nullptr, h->xbar, h->ubar, h->pf, h->A, h->Bm)
       if (h->seq_ok) { LINC_LAUNCH(0, true); LINC_LAUNCH(1, true); LINC_LAUNCH(2, true); }
       else { LINC_LAUNCH(0, false); LINC_LAUNCH(1, false); LINC_LAUNCH(2, false); }
       h->launches += 3;
