@@ -131,14 +131,35 @@ __global__ void k_init_guess(int B, int N, const double* __restrict__ x0, const 
 }
 
 // ---- per-instance solver state machine of iLQR::solve (ilqr.cpp:547-656), one thread per instance ----
+// The launch sequence is pipelined (h1ilqr_capi.cu, enqueue_solve): instances whose FIRST line search succeeded finish
+// their iteration in phase 1 and their next linearization / cost quadratics start at once (`early` set), while the
+// second attempts (lambda x 10, backward pass, line search) of the others run concurrently on a second stream and
+// finish in phase 2; those that succeed there join late (`late` set). Instances whose two attempts both failed keep
+// their trajectory, so their linearization and cost quadratics of this iteration stay valid (quirk Q10: `continue`).
 struct SolveState {
   double* lambda; double* cost; double* prev_cost; double* nominal_cost;
-  int* active; int* second; int* iters; int* status;
+  int* active; int* second; int* early; int* late; int* iters; int* status;
   int* ls_ok; double* ls_cost; int* ls_alpha;
   double* cost_trace; int* alpha_trace;
-  int* act_list; int* sec_list; int* list_count;   // compact instance lists for the thread-per-candidate line search
+  int* act_list; int* sec_list; int* early_list; int* late_list;
+  int* list_count;   // [4]: active, second, early, late — compact instance lists so that warps / CTAs are full however sparse a set is
 };
-// phase 0: iteration begin; 1: after first line search; 2: iteration end
+// end of an iteration whose line search succeeded (ilqr.cpp:628-645); returns whether the instance stays active
+__device__ __forceinline__ bool solve_state_accept(const SolveState& st, const H1SolverOptions& o, int i, int it) {
+  const int maxit = o.max_iterations;
+  const double cur = st.ls_cost[i];
+  st.iters[i] = it + 1;
+  st.cost[i] = cur;
+  st.lambda[i] = fmax(st.lambda[i] / 2.0, o.reg_min);
+  st.cost_trace[(size_t)i * maxit + it] = cur;
+  bool on = true;
+  if (!isfinite(cur)) { st.status[i] = 1; on = false; }
+  else if (fabs(cur - st.prev_cost[i]) < o.tolerance) on = false;
+  else if (cur > o.divergence_cost) on = false;
+  if (!on) st.active[i] = 0;
+  return on;
+}
+// phase 0: iteration begin; 1: after the first line search; 2: after the second attempts
 __global__ void k_solve_state(SolveState st, const H1SolverOptions* gopt, int B, int it, int phase) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
@@ -153,35 +174,37 @@ __global__ void k_solve_state(SolveState st, const H1SolverOptions* gopt, int B,
     if (st.active[i]) {
       st.prev_cost[i] = st.cost[i];
       if (it > 0) st.nominal_cost[i] = st.cost[i];   // baseline of the line search: cost of the unchanged trajectory
-      st.act_list[atomicAdd(&st.list_count[0], 1)] = i;   // (both counters are zeroed before the phase-0 launch)
+      st.act_list[atomicAdd(&st.list_count[0], 1)] = i;   // (the counter is zeroed before the phase-0 launch)
     }
     return;
   }
-  if (!st.active[i]) return;
   if (phase == 1) {
+    st.early[i] = 0; st.late[i] = 0;
+    if (!st.active[i]) return;
     st.alpha_trace[((size_t)i * maxit + it) * 2] = st.ls_alpha[i];
     if (!st.ls_ok[i]) {
       st.lambda[i] = fmin(st.lambda[i] * 10.0, o.reg_max);
       st.second[i] = 1;
       st.sec_list[atomicAdd(&st.list_count[1], 1)] = i;
+    } else if (solve_state_accept(st, o, i, it)) {
+      st.early[i] = 1;
+      st.early_list[atomicAdd(&st.list_count[2], 1)] = i;
     }
     return;
   }
-  // phase 2
-  if (st.second[i]) st.alpha_trace[((size_t)i * maxit + it) * 2 + 1] = st.ls_alpha[i];
-  st.iters[i] = it + 1;
+  // phase 2: only the instances of the second attempt
+  if (!st.active[i] || !st.second[i]) return;
+  st.alpha_trace[((size_t)i * maxit + it) * 2 + 1] = st.ls_alpha[i];
   if (!st.ls_ok[i]) {  // both attempts failed
+    st.iters[i] = it + 1;
     st.cost_trace[(size_t)i * maxit + it] = st.cost[i];
     if (it > 1) st.active[i] = 0;
     return;              // `continue`: no lambda decrease, no convergence test (quirk Q10)
   }
-  const double cur = st.ls_cost[i];
-  st.cost[i] = cur;
-  st.lambda[i] = fmax(st.lambda[i] / 2.0, o.reg_min);
-  st.cost_trace[(size_t)i * maxit + it] = cur;
-  if (!isfinite(cur)) { st.status[i] = 1; st.active[i] = 0; return; }
-  if (fabs(cur - st.prev_cost[i]) < o.tolerance) st.active[i] = 0;
-  else if (cur > o.divergence_cost) st.active[i] = 0;
+  if (solve_state_accept(st, o, i, it)) {
+    st.late[i] = 1;
+    st.late_list[atomicAdd(&st.list_count[3], 1)] = i;
+  }
 }
 
 // ---- u_apply = ubar[0] + K[0] (x_measured - xbar[0]) and bookkeeping of the previous solution

@@ -26,7 +26,9 @@ static int set_err(int code, const char* what, cudaError_t e = cudaSuccess) {
 
 struct H1Ilqr {
   int B = 0, N = 0, device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;        // every launch goes to `stream` (enqueue_solve swaps in `stream2` for the second attempts)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   H1SolverOptions opt;
   DynModel* d_dyn = nullptr; CostModel* d_cost = nullptr; H1Weights* d_w = nullptr; H1SolverOptions* d_opt = nullptr;
   double *xbar = nullptr, *ubar = nullptr, *K = nullptr, *kff = nullptr, *A = nullptr, *Bm = nullptr;
@@ -37,6 +39,7 @@ struct H1Ilqr {
   double *lambda = nullptr, *cost = nullptr, *prev_cost = nullptr, *nominal_cost = nullptr, *ls_cost = nullptr;
   int *active = nullptr, *second = nullptr, *iters = nullptr, *status = nullptr, *ls_ok = nullptr, *ls_alpha = nullptr;
   int *act_list = nullptr, *sec_list = nullptr, *list_count = nullptr;
+  int *early = nullptr, *late = nullptr, *early_list = nullptr, *late_list = nullptr;
   bool lin_legacy = false;   // H1ILQR_LIN_COLUMNS=1: per-column solves (k_linearize_cols) instead of the dense finish
   int *has_prev = nullptr, *warm_mask = nullptr, *cold_mask = nullptr, *warm_in = nullptr;
   double* cost_trace = nullptr; int* alpha_trace = nullptr;
@@ -94,6 +97,9 @@ void h1ilqr_destroy(H1Ilqr* h) {
   for (void* p : h->allocs) cudaFree(p);
   if (h->pin) cudaFreeHost(h->pin);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -124,7 +130,9 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   if (const char* e = getenv("H1_SEQ_MIN_BATCH")) h->seq_min_batch = atoi(e);   // tuning experiments
 #define CUH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(H1ILQR_ECUDA, #call, e_); h1ilqr_destroy(h); return H1ILQR_ECUDA; } } while (0)
   CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUH(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
   CUH(cudaEventCreate(&h->ev[0])); CUH(cudaEventCreate(&h->ev[1]));
+  CUH(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)); CUH(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   const size_t B = batch, N1 = N + 1;
   CUH(dalloc(h, &h->d_dyn, 1)); CUH(dalloc(h, &h->d_cost, 1)); CUH(dalloc(h, &h->d_w, 1)); CUH(dalloc(h, &h->d_opt, 1));
   CUH(cudaMemcpyAsync(h->d_dyn, &dm, sizeof(dm), cudaMemcpyHostToDevice, h->stream));
@@ -145,7 +153,8 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   CUH(dalloc(h, &h->nominal_cost, B)); CUH(dalloc(h, &h->ls_cost, B));
   CUH(dalloc(h, &h->active, B)); CUH(dalloc(h, &h->second, B)); CUH(dalloc(h, &h->iters, B)); CUH(dalloc(h, &h->status, B));
   CUH(dalloc(h, &h->ls_ok, B)); CUH(dalloc(h, &h->ls_alpha, B)); CUH(dalloc(h, &h->has_prev, B));
-  CUH(dalloc(h, &h->warm_mask, B)); CUH(dalloc(h, &h->act_list, B)); CUH(dalloc(h, &h->sec_list, B)); CUH(dalloc(h, &h->list_count, 2)); CUH(dalloc(h, &h->cold_mask, B)); CUH(dalloc(h, &h->warm_in, B));
+  CUH(dalloc(h, &h->warm_mask, B)); CUH(dalloc(h, &h->act_list, B)); CUH(dalloc(h, &h->sec_list, B)); CUH(dalloc(h, &h->list_count, 4));
+  CUH(dalloc(h, &h->early, B)); CUH(dalloc(h, &h->late, B)); CUH(dalloc(h, &h->early_list, B)); CUH(dalloc(h, &h->late_list, B)); CUH(dalloc(h, &h->cold_mask, B)); CUH(dalloc(h, &h->warm_in, B));
   CUH(dalloc(h, &h->pf, B * N));
   CUH(dalloc(h, &h->cost_trace, B * h->opt.max_iterations)); CUH(dalloc(h, &h->alpha_trace, B * h->opt.max_iterations * 2));
   h->scratch_bytes = B * N1 * (NX + NU + NX + NV + 9) * sizeof(double);
@@ -232,6 +241,16 @@ int h1ilqr_set_reference_window(H1Ilqr* h, const double* x_ref, const double* u_
 }
 
 // ---------------- stage launchers (no host sync) ----------------
+// compact instance list (and its device-side counter) that k_solve_state maintains for one of the solve masks
+static const int* list_for(const H1Ilqr* h, const int* mask, const int** count) {
+  const int* list = nullptr; int slot = 0;
+  if (mask && mask == h->active) { list = h->act_list; slot = 0; }
+  else if (mask && mask == h->second) { list = h->sec_list; slot = 1; }
+  else if (mask && mask == h->early) { list = h->early_list; slot = 2; }
+  else if (mask && mask == h->late) { list = h->late_list; slot = 3; }
+  *count = list ? h->list_count + slot : nullptr;
+  return list;
+}
 static bool use_batched(const H1Ilqr* h, long units, long auto_min_units) {
   if (h->policy == H1ILQR_KERNELS_COOPERATIVE) return false;
   if (h->policy == H1ILQR_KERNELS_BATCHED) return true;
@@ -256,9 +275,9 @@ static void launch_rollout(H1Ilqr* h, const int* mask, const double* x0_dev, int
 static void launch_factors(H1Ilqr* h, const int* mask) {
   const long knots = (long)h->B * h->N;
   if (h->seq_ok && use_batched(h, h->B, h->seq_min_batch)) {
-    const int* list = (mask && mask == h->active) ? h->act_list : nullptr;
+    const int* cnt; const int* list = list_for(h, mask, &cnt);
     k_primal_factor_seq<<<(unsigned)((knots + SEQ_ROLL_THREADS - 1) / SEQ_ROLL_THREADS), SEQ_ROLL_THREADS, h->smem_seq, h->stream>>>(
-        h->d_dyn, h->B, h->N, mask, list, list ? h->list_count : nullptr, h->xbar, h->ubar, h->pf);
+        h->d_dyn, h->B, h->N, mask, list, cnt, h->xbar, h->ubar, h->pf);
   } else {
     k_primal_factor<<<(int)((knots + 3) / 4), 128, h->smem_dyn4, h->stream>>>(h->d_dyn, h->B, h->N, mask, h->xbar, h->ubar, h->pf);
   }
@@ -271,8 +290,7 @@ static void launch_linearize(H1Ilqr* h, const int* mask, bool factors_ready = fa
     const long knots = (long)h->B * h->N;
     if (use_batched(h, knots, h->lin_cols_min_knots)) {  // one thread per column, direction-uniform warps
       const unsigned kb = (unsigned)((knots + LINC_KNOTS - 1) / LINC_KNOTS);
-      const int* list = (mask && mask == h->active) ? h->act_list : nullptr;   // compact active list (k_solve_state)
-      const int* cnt = list ? h->list_count : nullptr;
+      const int* cnt; const int* list = list_for(h, mask, &cnt);   // compact instance list (k_solve_state)
       if (!h->lin_legacy) {   // tangents parked in A_k, then one dense contraction per knot (h1_lin_finish.cuh)
 #define LINT_LAUNCH(CLS) \
   k_linearize_tangents<CLS><<<kb, LINT_THREADS, h->smem_lint, h->stream>>>(h->d_dyn, knots, h->N, mask, list, cnt, h->xbar, h->pf, h->A)
@@ -329,9 +347,9 @@ static void launch_backward(H1Ilqr* h, const int* mask) {
 static void launch_line_search(H1Ilqr* h, const int* mask) {
   if (h->seq_ok && use_batched(h, h->B, h->seq_min_batch)) {   // one thread per (instance, candidate)
     const long threads = (long)h->B * H1ILQR_NALPHA;
-    const int* list = (mask && mask == h->active) ? h->act_list : ((mask && mask == h->second) ? h->sec_list : nullptr);
+    const int* cnt; const int* list = list_for(h, mask, &cnt);
     k_line_search_seq<<<(unsigned)((threads + SEQ_THREADS - 1) / SEQ_THREADS), SEQ_THREADS, h->smem_seq_ls, h->stream>>>(
-        h->d_dyn, h->d_w, h->d_opt, ref_table(h), h->B, h->N, mask, list, list ? h->list_count + (mask == h->second ? 1 : 0) : nullptr,
+        h->d_dyn, h->d_w, h->d_opt, ref_table(h), h->B, h->N, mask, list, cnt,
         h->x0, h->nominal_cost, h->xbar, h->ubar, h->K, h->kff,
         h->xnew, h->unew, h->ls_ok, h->ls_cost, h->ls_alpha);
     LAUNCHED();
@@ -348,11 +366,15 @@ static SolveState solve_state(H1Ilqr* h) {
   st.active = h->active; st.second = h->second; st.iters = h->iters; st.status = h->status;
   st.ls_ok = h->ls_ok; st.ls_cost = h->ls_cost; st.ls_alpha = h->ls_alpha;
   st.cost_trace = h->cost_trace; st.alpha_trace = h->alpha_trace;
-  st.act_list = h->act_list; st.sec_list = h->sec_list; st.list_count = h->list_count;
+  st.act_list = h->act_list; st.sec_list = h->sec_list; st.early_list = h->early_list; st.late_list = h->late_list;
+  st.early = h->early; st.late = h->late; st.list_count = h->list_count;
   return st;
 }
 static void launch_state(H1Ilqr* h, int it, int phase) {
-  if (phase == 0) cudaMemsetAsync(h->list_count, 0, 2 * sizeof(int), h->stream);
+  // counters of the lists this phase builds: 0 -> active; 1 -> second, early; 2 -> late
+  if (phase == 0) cudaMemsetAsync(h->list_count, 0, sizeof(int), h->stream);
+  else if (phase == 1) cudaMemsetAsync(h->list_count + 1, 0, 2 * sizeof(int), h->stream);
+  else cudaMemsetAsync(h->list_count + 3, 0, sizeof(int), h->stream);
   k_solve_state<<<(h->B + 127) / 128, 128, 0, h->stream>>>(solve_state(h), h->d_opt, h->B, it, phase);
   LAUNCHED();
 }
@@ -371,25 +393,50 @@ struct StageTimer {
 };
 
 // The whole iLQR::solve launch sequence, stream-ordered, no host round trips (unless stage timing is on).
+//
+// iLQR::forwardRolloutNominal (ilqr.cpp:551-563): in iteration 0 the guess is rolled out from x0. In later iterations
+// xbar/ubar are what the last accepted line-search candidate left (or unchanged after a failed one): rolling them out
+// again from the same x0 reproduces them (f_D is deterministic), so the sequential rollout is replaced by the
+// knot-parallel factorisation and the known cost (k_solve_state, phase 0).
+//
+// Pipelining: after the first line search of iteration `it` the instances that accepted a candidate are done with the
+// iteration (k_solve_state phase 1), so factorisation + linearization + cost quadratics of iteration it + 1 start
+// for them at once on the main stream, while backward pass + line search of the second attempts — a small, latency-
+// bound set — run on `stream2`. Second attempts that succeed (rare) are linearized after the join; instances whose
+// two attempts both failed keep their trajectory and therefore their A, B, lx, lxx ... of this iteration.
 static void enqueue_solve(H1Ilqr* h) {
   const bool analytic = h->opt.linearization != H1ILQR_LIN_FD;
+  cudaStream_t main_stream = h->stream;
+  auto derivatives = [&](const int* mask) {   // of the current trajectory of the instances in `mask`
+    if (analytic) { StageTimer t(h, &h->times.rollout_ms); launch_factors(h, mask); }
+    { StageTimer t(h, &h->times.linearize_ms); launch_linearize(h, mask, analytic); }
+    { StageTimer t(h, &h->times.cost_quadratics_ms); launch_cost_quadratics(h, mask); }
+  };
   launch_rollout(h, nullptr, nullptr, h->N, h->cost);  // current_cost = computeTotalCost(xbar, ubar)
   for (int it = 0; it < h->opt.max_iterations; ++it) {
     launch_state(h, it, 0);
-    // iLQR::forwardRolloutNominal (ilqr.cpp:551-563). In iteration 0 the guess is rolled out from x0. In later
-    // iterations xbar/ubar are what the last accepted line-search candidate left (or unchanged after a failed
-    // one): rolling them out again from the same x0 reproduces them (f_D is deterministic), so the sequential
-    // rollout is replaced by the knot-parallel factorisation and the known cost (k_solve_state, phase 0).
-    if (it == 0) { StageTimer t(h, &h->times.rollout_ms); launch_rollout(h, h->active, h->x0, 0, h->nominal_cost, analytic); }
-    else if (analytic) { StageTimer t(h, &h->times.rollout_ms); launch_factors(h, h->active); }
-    { StageTimer t(h, &h->times.linearize_ms); launch_linearize(h, h->active, analytic); }
-    { StageTimer t(h, &h->times.cost_quadratics_ms); launch_cost_quadratics(h, h->active); }
+    if (it == 0) {
+      { StageTimer t(h, &h->times.rollout_ms); launch_rollout(h, h->active, h->x0, 0, h->nominal_cost, analytic); }
+      { StageTimer t(h, &h->times.linearize_ms); launch_linearize(h, h->active, analytic); }
+      { StageTimer t(h, &h->times.cost_quadratics_ms); launch_cost_quadratics(h, h->active); }
+    }
     { StageTimer t(h, &h->times.backward_ms); launch_backward(h, h->active); }
     { StageTimer t(h, &h->times.line_search_ms); launch_line_search(h, h->active); }
     launch_state(h, it, 1);
+    const bool more = it + 1 < h->opt.max_iterations;
+    // fork: second attempts on stream2 ...
+    cudaEventRecord(h->ev_fork, main_stream);
+    cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+    h->stream = h->stream2;
     { StageTimer t(h, &h->times.backward_ms); launch_backward(h, h->second); }
     { StageTimer t(h, &h->times.line_search_ms); launch_line_search(h, h->second); }
     launch_state(h, it, 2);
+    cudaEventRecord(h->ev_join, h->stream2);
+    h->stream = main_stream;
+    // ... next iteration's derivatives of the early set on the main stream, then join and the late set
+    if (more) derivatives(h->early);
+    cudaStreamWaitEvent(main_stream, h->ev_join, 0);
+    if (more) derivatives(h->late);
   }
 }
 

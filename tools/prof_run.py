@@ -13,8 +13,13 @@ s = gpu.H1IlqrBatch(w, N=25, batch=B)
 s.set_kernel_policy(int(os.environ.get("H1_POLICY", "0")))
 refs = ReferenceSet(d["walking_q"], d["walking_v"], d["walking_contact"], s.reference_kinematics)
 ug = np.zeros(19); ug[:18] = s.bias_forces(standing_state()[None])[0][7:25]
-s.set_reference_window(*refs.window(0, 25), shared=True)
-x0 = perturbed_states(standing_state(), B, seed=0)
+if os.environ.get("H1_PROF_WORKLOAD", "standing") == "bench":   # the bench.py workload (per-instance walking windows)
+    import bench
+    win, x0 = bench.workload(B, 0, s.reference_kinematics)
+    s.set_reference_window(*win, shared=False)
+else:
+    s.set_reference_window(*refs.window(0, 25), shared=True)
+    x0 = perturbed_states(standing_state(), B, seed=0)
 s.upload_inputs(x0, ug)
 ms = s.run_resident_steps(1, True)
 print("B", B, "ms", ms)
