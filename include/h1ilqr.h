@@ -24,6 +24,7 @@
 
 #include "h1_model.h"
 
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -177,6 +178,13 @@ int h1ilqr_run_resident_steps(H1Ilqr* h, int steps, int cold_each_step, double* 
 int h1ilqr_measure_fp64_peak(H1Ilqr* h, double* tflops);
 /* same for the fp64 tensor-core path (mma.sync m8n8k4, SASS DMMA) used by the Riccati contractions. */
 int h1ilqr_measure_fp64_mma_peak(H1Ilqr* h, double* tflops);
+
+/* Page-lock (pin) a caller-owned host buffer so that the host <-> device copies of h1ilqr_set_reference_window /
+ * h1ilqr_mpc_step / the getters run as direct DMA transfers instead of going through the driver's bounce buffers.
+ * The MPC loop keeps its reference arrays alive across steps (MPC members x_ref_window_ ..., src/ilqr/mpc.hpp:52-60),
+ * so they are registered once. Buffers that are not registered keep working (pageable copies). */
+int h1ilqr_host_register(H1Ilqr* h, const void* host_ptr, size_t bytes);
+int h1ilqr_host_unregister(H1Ilqr* h, const void* host_ptr);
 
 /* ---- timing of the last h1ilqr_solve, CUDA events on the handle's stream, milliseconds ---- */
 typedef struct H1StageTimes {

@@ -507,6 +507,19 @@ static void enqueue_mpc_tail(H1Ilqr* h) {
   LAUNCHED();
 }
 
+int h1ilqr_host_register(H1Ilqr* h, const void* host_ptr, size_t bytes) {
+  GUARD(h);
+  if (!host_ptr || bytes == 0) return set_err(H1ILQR_EARG, "h1ilqr_host_register: null buffer");
+  CU(cudaHostRegister(const_cast<void*>(host_ptr), bytes, cudaHostRegisterDefault));
+  return 0;
+}
+int h1ilqr_host_unregister(H1Ilqr* h, const void* host_ptr) {
+  GUARD(h);
+  if (!host_ptr) return set_err(H1ILQR_EARG, "h1ilqr_host_unregister: null buffer");
+  CU(cudaHostUnregister(const_cast<void*>(host_ptr)));
+  return 0;
+}
+
 int h1ilqr_upload_inputs(H1Ilqr* h, const double* x_measured, const double* u_init, int u_init_shared) {
   GUARD(h);
   if (!x_measured) return set_err(H1ILQR_EARG, "null x_measured");

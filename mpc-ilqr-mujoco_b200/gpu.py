@@ -23,7 +23,7 @@ EXPORTS = [
     "h1ilqr_reference_kinematics", "h1ilqr_sole_points", "h1ilqr_set_trajectory", "h1ilqr_get_trajectory", "h1ilqr_get_gains",
     "h1ilqr_set_gains", "h1ilqr_get_linearization", "h1ilqr_set_linearization", "h1ilqr_get_cost_quadratics",
     "h1ilqr_set_cost_quadratics", "h1ilqr_get_regularization", "h1ilqr_set_regularization", "h1ilqr_get_solve_trace",
-    "h1ilqr_upload_inputs", "h1ilqr_run_resident_steps", "h1ilqr_measure_fp64_peak", "h1ilqr_measure_fp64_mma_peak", "h1ilqr_enable_stage_timing", "h1ilqr_set_kernel_policy", "h1ilqr_get_stage_times", "h1ilqr_stream", "h1_default_dynamics_model",
+    "h1ilqr_upload_inputs", "h1ilqr_host_register", "h1ilqr_host_unregister", "h1ilqr_run_resident_steps", "h1ilqr_measure_fp64_peak", "h1ilqr_measure_fp64_mma_peak", "h1ilqr_enable_stage_timing", "h1ilqr_set_kernel_policy", "h1ilqr_get_stage_times", "h1ilqr_stream", "h1_default_dynamics_model",
     "h1_default_cost_model",
 ]
 
@@ -89,6 +89,7 @@ class H1IlqrBatch:
         self.N, self.B = int(N), int(batch)
         self.opt = options if options is not None else default_options()
         self._h = C.c_void_p()
+        self._pinned = []
         _check(lib().h1ilqr_create(C.byref(dyn_model) if dyn_model is not None else None,
                                    C.byref(cost_model) if cost_model is not None else None, C.byref(self.opt),
                                    C.c_int(self.B), C.c_int(self.N), C.c_int(device), C.byref(self._h)))
@@ -96,6 +97,7 @@ class H1IlqrBatch:
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
+            self.unpin_all()
             lib().h1ilqr_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -116,6 +118,22 @@ class H1IlqrBatch:
         cv = _f(com_vel_ref).reshape(n, N1, 3) if com_vel_ref is not None else None
         _check(lib().h1ilqr_set_reference_window(self._h, dptr(x_ref), dptr(u_ref), dptr(com_ref), dptr(ee_ref),
                                                  iptr(stance), dptr(cv), C.c_int(int(shared))))
+
+    def pin_host(self, *arrays):
+        """Page-lock caller-owned numpy arrays that are handed to set_reference_window / mpc_step every step, so their
+        host <-> device copies are direct DMA transfers. Returns the (contiguous) arrays to keep and pass on."""
+        out = []
+        for a in arrays:
+            a = np.ascontiguousarray(a)
+            _check(lib().h1ilqr_host_register(self._h, C.c_void_p(a.ctypes.data), C.c_size_t(a.nbytes)))
+            self._pinned.append(a)
+            out.append(a)
+        return out if len(out) != 1 else out[0]
+
+    def unpin_all(self):
+        for a in self._pinned:
+            lib().h1ilqr_host_unregister(self._h, C.c_void_p(a.ctypes.data))
+        self._pinned = []
 
     # ---- solver ----
     def initialize(self, x0, warm=None, u_init=None):
