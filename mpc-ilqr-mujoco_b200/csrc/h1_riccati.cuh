@@ -19,6 +19,7 @@
 #pragma once
 #include "h1_common.cuh"
 #include <type_traits>
+#include <cstdio>
 
 namespace h1 {
 
@@ -35,7 +36,7 @@ struct RiccatiSmem {
   double Kt[LDU * 56];        // solves: columns 0..50 -> K(:,j), column 51 -> kff; pad row 19 stays zero
   double Quu[LDU * LDU];      // pad row/column 19 stay zero
   double Ls[NU * NU];         // unit-lower factor of the permuted LDL^T
-  double Vx[LDX], Qx[NX], Qu[NU], D[NU], tmp[NU];   // Vx[51] is a zero pad (Vx rides along as an extra column of W)
+  double Vx[LDX], Qx[NX], Qu[NU], D[NU], Dinv[NU], tmp[NU];   // Vx[51] is a zero pad (Vx rides along as an extra column of W)
   double lq[NX + NU + NU * NU + 1];   // lx_t, lu_t, luu_t of the current knot (prefetched with [A|B])
   int perm[NU];
 };
@@ -76,6 +77,24 @@ __device__ __forceinline__ void mma_strip_store(int ksteps, int m0, int n0, FA f
   for (int j = 0; j < NT; ++j) { st(r, c0 + 8 * j, acc[j][0]); st(r, c0 + 8 * j + 1, acc[j][1]); }
 }
 
+// One 8 x 8 tile whose k loop is split over NS independent accumulator chains (a dependent DMMA costs far more than
+// its issue slot: short contractions that sit on the critical path of a knot are latency bound, not pipe bound).
+template <int KSTEPS, int NS, class FA, class FB>
+__device__ __forceinline__ void mma_tile_split(int m0, int n0, FA fa, FB fb, double& c0, double& c1) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  double acc[NS][2];
+#pragma unroll
+  for (int q = 0; q < NS; ++q) acc[q][0] = acc[q][1] = 0.0;
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+    const int k = 4 * ks + t;
+    dmma884(acc[ks % NS][0], acc[ks % NS][1], fa(m0 + g, k), fb(k, n0 + g));
+  }
+  c0 = 0.0; c1 = 0.0;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) { c0 += acc[q][0]; c1 += acc[q][1]; }
+}
+
 // LDL^T of Quu with symmetric pivoting by largest |diagonal| (Eigen::LDLT's selection rule), ONE warp, right-
 // looking, register resident: lane i holds row i of the permuted matrix (lower triangle), column k of the
 // current Schur complement is broadcast with shuffles. Writes perm, D, Ls (unit-lower factor). Returns true when
@@ -103,9 +122,10 @@ __device__ __forceinline__ bool quu_ldlt(RiccatiSmem& s) {
   for (int k = 0; k < n; ++k) {
     const double d = __shfl_sync(0xffffffffu, p[k], k);
     if (!(d > 0.0)) not_pd = true;
-    if (lane == 0) s.D[k] = d;
+    const double rd = (fabs(d) > 2.2250738585072014e-308) ? 1.0 / d : 0.0;   // one reciprocal per pivot: the division is on
+    if (lane == 0) { s.D[k] = d; s.Dinv[k] = rd; }                          // the critical path of the whole knot
     const double pik = p[k];                                           // P(i,k) of this lane's row
-    const double lik = (fabs(d) > 0.0) ? pik / d : 0.0;
+    const double lik = pik * rd;
 #pragma unroll
     for (int c = 1; c < n; ++c) {
       if (c <= k) continue;                                            // (constant trip counts: both loops unroll fully)
@@ -118,6 +138,18 @@ __device__ __forceinline__ bool quu_ldlt(RiccatiSmem& s) {
   __syncwarp();
   return not_pd;
 }
+
+#ifdef RIC_PROF   // debug build only (make NVCC="nvcc -DRIC_PROF"): per-phase cycles of warp 0 / warp 7 of block 0, printed at kernel end
+#define RP_DECL long long rp_t = clock64(); long long rp_acc[16]; for (int q_ = 0; q_ < 16; ++q_) rp_acc[q_] = 0;
+#define RP_MARK(p) { const long long now_ = clock64(); rp_acc[p] += now_ - rp_t; rp_t = now_; }
+#define RP_SYNC(p) { RP_MARK(2 * (p)); __syncthreads(); { unsigned x_; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(x_) : "r"((unsigned)__cvta_generic_to_shared(&s.perm[0])) : "memory"); rp_acc[15] += x_ & 0; } RP_MARK(2 * (p) + 1); }
+#define RP_PRINT if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 7)) printf("ric warp %d work/wait: top %lld/%lld G1b %lld/%lld G3 %lld/%lld P2 %lld/%lld solve %lld/%lld G4 %lld/%lld G5 %lld/%lld sym %lld\n", warp, rp_acc[0], rp_acc[1], rp_acc[2], rp_acc[3], rp_acc[4], rp_acc[5], rp_acc[6], rp_acc[7], rp_acc[8], rp_acc[9], rp_acc[10], rp_acc[11], rp_acc[12], rp_acc[13], rp_acc[14]);
+#else
+#define RP_DECL
+#define RP_MARK(p)
+#define RP_SYNC(p) __syncthreads();
+#define RP_PRINT
+#endif
 
 __global__ void __launch_bounds__(RIC_THREADS, 2)
 k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambda, const double* __restrict__ A,
@@ -157,12 +189,13 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
   bool nonfinite = false;
   double* const G = s.W + RIC_G_OFF;
   double* const Lpre = s.W + RIC_LXX_OFF;
+  RP_DECL
   for (int t = N - 1; t >= 0; --t) {
     const double* lxt = s.lq;
     const double* lut = s.lq + NX;
     const double* luut = s.lq + NX + NU;
     cp_async_commit_wait_all();
-    __syncthreads();
+    RP_SYNC(0)
     // ---- G1b: W(:, 48..71) = Vxx [A|B](:, 48..71) — the B block, which Quu needs first (warps 0..6: one 8-row
     //      strip each) ----
     auto w_strip = [&](auto nt_tag, int n0) {
@@ -173,21 +206,36 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
                           [&](int r, int c, double v) { if (r < LDX && c < NXU) s.W[c * LDX + r] = v; });   // row 51 of W = 0
     };
     if (warp < 7) w_strip(std::integral_constant<int, 3>(), 48);
-    __syncthreads();
+    RP_SYNC(1)
     // ---- G3: [Quu | B'Vx] = B' [W_B | Vx] + luu + lam I, 9 tiles over the 8 warps; the spare column 19 of the last
     //      tile column carries Vx and yields Qu = lu + B'Vx ----
     {
       auto fa = [&](int r, int k) { return s.AB[(NX + min(r, NU - 1)) * LDX + k]; };
       auto fb = [&](int k, int c) { return c < NU ? s.W[(NX + c) * LDX + k] : (c == NU ? s.Vx[k] : 0.0); };
-#pragma unroll 1
-      for (int tile = warp; tile < 9; tile += 8)
-        mma_strip_store<1>(13, 8 * (tile / 3), 8 * (tile % 3), fa, fb, [&](int r, int c, double v) {
-          if (r >= NU) return;
-          if (c < NU) s.Quu[c * LDU + r] = v + luut[c * NU + r] + ((c == r) ? lam : 0.0);
-          else if (c == NU) s.Qu[r] = lut[r] + v;
-        });
+      // one tile per warp: the 6 tiles of the lower triangle (mirrored into the upper one — LLT / LDLT only read one
+      // triangle, and B'VxxB is symmetric up to rounding) and the two remaining tiles of the column that carries Qu
+      const int mi = warp < 6 ? (warp < 1 ? 0 : (warp < 3 ? 1 : 2)) : warp - 6;
+      const int nj = warp < 6 ? (warp < 1 ? 0 : (warp < 3 ? warp - 1 : warp - 3)) : 2;
+      double c0, c1;
+      mma_tile_split<13, 4>(8 * mi, 8 * nj, fa, fb, c0, c1);
+      const int r = 8 * mi + g;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = 8 * nj + 2 * t4 + q;
+        const double v = q ? c1 : c0;
+        if (r >= NU) continue;
+        if (c < NU) {
+          if (warp < 6) {
+            if (c <= r) {
+              const double e = v + luut[c * NU + r] + ((c == r) ? lam : 0.0);
+              s.Quu[c * LDU + r] = e;
+              s.Quu[r * LDU + c] = e;
+            }
+          }
+        } else if (c == NU) s.Qu[r] = lut[r] + v;
+      }
     }
-    __syncthreads();
+    RP_SYNC(2)
     // ---- warps 0..6: G1a: W(:, 0..47) = Vxx A(:, 0..47), then G2: [Qxx | Qxu | A'Vx] = A' [W | Vx] (Qxx -> s.V,
     //      Qxu -> s.Qxu, the spare column 70 of the last tile carries Vx and yields Qx = lx + A'Vx)
     //      | warp 7: pivoted LDL^T of Quu, hidden behind both contractions ----
@@ -210,7 +258,7 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
         quu_ldlt(s);
       }
     }
-    __syncthreads();
+    RP_SYNC(3)
     // s.AB and s.W are free: prefetch the next knot's [A|B] and this knot's lxx (consumed by the final pass)
     if (t > 0) prefetch_ab(t - 1);
     {
@@ -242,7 +290,7 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
 #pragma unroll
       for (int m = 0; m < 5; ++m) {
         const int i = min(q + 4 * m, NU - 1);
-        y[m] = (fabs(s.D[i]) > 2.2250738585072014e-308) ? y[m] / s.D[i] : 0.0;
+        y[m] *= s.Dinv[i];                      // (0 for a vanishing pivot, as Eigen::LDLT::solve does)
       }
 #pragma unroll
       for (int c = NU - 1; c >= 1; --c) {       // back substitution with L^T
@@ -263,7 +311,7 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
         }
       }
     }
-    __syncthreads();
+    RP_SYNC(4)
     // ---- gains to global | G4: G = Quu K + 2 Qxu' (warps 0..6: one 8-column strip each) | warp 7: tmp = Quu k ----
     {
       double* Kt_g = K + ((size_t)inst * N + t) * NU * NX;
@@ -275,21 +323,29 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
       const int n0 = 8 * warp;
       auto fa = [&](int r, int k) { return r < LDU ? s.Quu[k * LDU + r] : 0.0; };
       auto fb = [&](int k, int c) { return s.Kt[c * LDU + k]; };
-#pragma unroll 1
-      for (int mi = 0; mi < 3; ++mi) {
-        const int r = 8 * mi + g;
-        double acc[1][2];
+      double acc[3][2];
+#pragma unroll
+      for (int mi = 0; mi < 3; ++mi)
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const int c = n0 + 2 * t4 + q;
-          acc[0][q] = (r < NU && c < NX) ? 2.0 * s.Qxu[r * LDX + c] : 0.0;
+          const int r = 8 * mi + g, c = n0 + 2 * t4 + q;
+          acc[mi][q] = (r < NU && c < NX) ? 2.0 * s.Qxu[r * LDX + c] : 0.0;
         }
-        mma_strip<1>(5, 8 * mi, n0, fa, fb, acc);
+#pragma unroll
+      for (int ks = 0; ks < 5; ++ks) {       // the three row tiles are independent chains
+        const int k = 4 * ks + t4;
+        const double b = fb(k, n0 + g);
+#pragma unroll
+        for (int mi = 0; mi < 3; ++mi) dmma884(acc[mi][0], acc[mi][1], fa(8 * mi + g, k), b);
+      }
+#pragma unroll
+      for (int mi = 0; mi < 3; ++mi) {
+        const int r = 8 * mi + g;
         if (r < LDU) {
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             const int c = n0 + 2 * t4 + q;
-            if (c < NX) G[c * LDU + r] = acc[0][q];
+            if (c < NX) G[c * LDU + r] = acc[mi][q];
           }
         }
       }
@@ -298,7 +354,7 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
       for (int l = 0; l < NU; ++l) acc += s.Quu[l * LDU + lane] * s.Kt[NX * LDU + l];
       s.tmp[lane] = acc;
     }
-    __syncthreads();
+    RP_SYNC(5)
     // ---- G5: M = Qxx + K' G in place in s.V (warps 0..6) | warp 7: Vx = Qx + K'(Quu k) + K'Qu + Qxu k ----
     if (warp < 7) {
       const int m0 = 8 * warp;
@@ -334,7 +390,7 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
       }
     }
     cp_async_commit_wait_all();   // lxx_t (and the next [A|B]) have landed
-    __syncthreads();
+    RP_SYNC(6)
     // ---- Vxx = sym(lxx + M), one thread per (i >= j) pair ----
     for (int e = tid; e < NX * NX; e += nt) {
       const int j = e / NX, i = e - j * NX;
@@ -344,8 +400,10 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
       const double v = 0.5 * (mij + mji);
       s.V[j * LDX + i] = v; s.V[i * LDX + j] = v;
     }
+    RP_MARK(14)
     // (the __syncthreads at the top of the next iteration orders these writes before G1)
   }
+  RP_PRINT
   if (nonfinite && status) status[inst] = 1;
 }
 
