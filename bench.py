@@ -8,11 +8,12 @@ instances per GPU (weak scaling; 8192/GPU x 8 GPUs = the 65,536-instance configu
 the walking reference from window row t0_i = i mod 374 with a perturbed initial state.
 
   value        : solves/s with inputs resident in HBM (CUDA events on the solver's stream, max over ranks)
-  e2e          : the same through the public C-ABI call h1ilqr_mpc_step with HOST buffers (pinned staging,
-                 H2D of x_measured + reference windows and D2H of u_apply + cost inside the timed region)
-  roofline     : dominant stage (analytic linearization, k_linearize_dirs<0|1|2>) against the measured HBM peak and
-                 the live-measured fp64 FMA peak; flop counts are EXECUTED fp64 operations per knot taken from ncu
-                 (profiles/), not an estimate
+  e2e          : the same through the public C-ABI call h1ilqr_mpc_step with HOST buffers (page-locked once with
+                 h1ilqr_host_register; H2D of x_measured + reference windows and D2H of u_apply + cost inside the timed region)
+  roofline     : dominant kernel (k_backward, the Riccati pass on the fp64 tensor cores): algorithmic flops per knot x
+                 knot passes / stage time measured live with CUDA events, against the fp64 tensor peak measured live;
+                 its HBM view next to it. `roofline_linearize` does the same for the second stage (executed fp64
+                 operations per knot taken from ncu, profiles/, not an estimate)
   cpu_baseline : the CPU oracle (a port: the reference itself cannot be built here) on this box's host cores
 `--impl reference` times that CPU oracle as the reference arm.
 """
@@ -268,13 +269,13 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        knots = float(it_s.sum()) * N_HORIZON               # linearized knots in that solve
+        _, at_s = solver.solve_trace()
+        first_passes = float((at_s[:, :, 0] != -2).sum())    # instance-iterations (linearization, first backward pass / line search)
+        second_passes = float((at_s[:, :, 1] != -2).sum())   # second attempts after a failed line search
+        knots = first_passes * N_HORIZON                     # linearized knots in that solve
         lin_s = tm["linearize_ms"] * 1e-3
-        # algorithmic bytes per linearized knot: A_k, B_k written; x_k, u_k and the Mhat factor (L, D, a) read
-        alg_bytes = knots * ((51 * 51 + 51 * 19 + 51 + 19) * 8.0 + FACTOR_BYTES_PER_KNOT)
-        alg_flops = knots * FLOPS_PER_LINEARIZED_KNOT
-        achieved = alg_bytes / lin_s / 1e9
-        bwd_passes = float(it_s.sum()) * N_HORIZON          # lower bound: second attempts add passes
+        bwd_s = tm["backward_ms"] * 1e-3
+        bwd_knots = (first_passes + second_passes) * N_HORIZON
         dmma_peak = solver.measure_fp64_mma_peak()
         stage = {k: tm[k] for k in ("rollout_ms", "linearize_ms", "cost_quadratics_ms", "backward_ms", "line_search_ms")}
         # single-instance latency (BASELINE metric part 1): H1 iLQR solve ms per MPC step, N=25, one instance
@@ -302,21 +303,30 @@ def main():
                     "api": "h1ilqr_set_reference_window + h1ilqr_mpc_step (host buffers registered with h1ilqr_host_register)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "k_linearize_dirs<0|1|2> (analytic linearization, one thread per column of [A|B])",
-                         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": TRAFFIC_BYTES_PER_LINEARIZED_KNOT * B * N_HORIZON,
-                         "traffic_note": "ncu --set full dram read+write of the three launches of one iteration, scaled to this batch (profiles/)",
-                         "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback",
-                         "share_of_step": tm["linearize_ms"] / max(tm["total_ms"], 1e-9),
-                         "note": "the stage is fp64-pipe bound, not HBM bound: see fp64",
-                         "fp64": {"achieved_tflops": alg_flops / lin_s / 1e12, "peak_tflops": fp64_peak,
-                                  "frac": alg_flops / lin_s / 1e12 / max(fp64_peak, 1e-9),
-                                  "flops_per_knot": FLOPS_PER_LINEARIZED_KNOT,
-                                  "peak_source": "measured live (DFMA kernel)"}},
-            "roofline_backward": {"kernel": "k_backward (Riccati, DMMA m8n8k4)", "bound": "fp64 tensor",
-                                  "achieved_tflops": bwd_passes * 1.153e6 / (tm["backward_ms"] * 1e-3) / 1e12,
-                                  "peak_tflops": dmma_peak, "peak_source": "measured live (mma.sync m8n8k4 f64 kernel)",
-                                  "note": "achieved is a lower bound (second attempts after a failed line search add passes)"},
+            # dominant kernel of the step: the Riccati backward pass (one CTA per instance, contractions on the fp64 tensor cores)
+            "roofline": {"kernel": "k_backward (Riccati backward pass, five contractions per knot as mma.sync m8n8k4 f64 = SASS DMMA)",
+                         "bound": "tensor", "achieved": bwd_knots * BWD_FLOPS_PER_KNOT / bwd_s / 1e12, "peak": dmma_peak,
+                         "unit": "TFLOP/s", "frac": bwd_knots * BWD_FLOPS_PER_KNOT / bwd_s / 1e12 / max(dmma_peak, 1e-9),
+                         "traffic": BWD_TRAFFIC_BYTES_PER_KNOT * B * N_HORIZON,
+                         "traffic_note": "ncu --set full dram read+write of one full-batch launch (profiles/r01h_ncu_top_kernels.txt: 61.5 KB per knot, "
+                                         "algorithmic 60.7 KB), scaled to this batch",
+                         "peak_source": "fp64 tensor-core peak measured live in this run (mma.sync m8n8k4 f64 probe kernel); MEASURED_PEAKS.json "
+                                        "carries HBM and bf16 figures only, and the bf16 tcgen05 peak does not apply to an fp64 path",
+                         "flops_per_knot": BWD_FLOPS_PER_KNOT, "knot_passes": bwd_knots,
+                         "share_of_step": tm["backward_ms"] / max(tm["total_ms"], 1e-9),
+                         "hbm": {"achieved": bwd_knots * BWD_ALG_BYTES_PER_KNOT / bwd_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": bwd_knots * BWD_ALG_BYTES_PER_KNOT / bwd_s / 1e9 / hbm_peak,
+                                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback"},
+                         "note": "latency bound on the sequential section of a knot (pivoted LDL^T of Quu + 52 triangular solves), see DESIGN.md"},
+            # second stage: analytic linearization = 3 tangent kernels (FMA pipe) + k_linearize_finish (DMMA)
+            "roofline_linearize": {"kernel": "k_linearize_tangents<0|1|2> + k_linearize_finish",
+                                   "bound": "fp64", "achieved_tflops": knots * LIN_FLOPS_PER_KNOT / lin_s / 1e12, "peak_tflops": fp64_peak,
+                                   "frac": knots * LIN_FLOPS_PER_KNOT / lin_s / 1e12 / max(fp64_peak, 1e-9),
+                                   "flops_per_knot": LIN_FLOPS_PER_KNOT, "peak_source": "measured live (DFMA kernel)",
+                                   "hbm": {"achieved": knots * LIN_ALG_BYTES_PER_KNOT / lin_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                           "frac": knots * LIN_ALG_BYTES_PER_KNOT / lin_s / 1e9 / hbm_peak,
+                                           "traffic": LIN_TRAFFIC_BYTES_PER_KNOT * B * N_HORIZON},
+                                   "share_of_step": tm["linearize_ms"] / max(tm["total_ms"], 1e-9)},
             "stage_ms_per_solve": stage,
             "single_instance_ms_per_mpc_step": single_ms,
             "cpu_baseline": cpu,
@@ -327,13 +337,18 @@ def main():
         dist.destroy_process_group()
 
 
-# fp64 operations EXECUTED per linearized knot by k_linearize_dirs<0|1|2> (2 per DFMA, 1 per DADD / DMUL), from the
-# smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on counters of profiles/r01f_ncu_top_kernels.txt:
-# q columns 693 k + v columns 413 k + u columns 40 k.
-FLOPS_PER_LINEARIZED_KNOT = 1.15e6
-FACTOR_BYTES_PER_KNOT = (25 * 11 + 25 + 25) * 8.0
-# dram__bytes_read.sum + dram__bytes_write.sum of the same capture, per knot (14.2 GB / (4096 instances x 25 knots))
-TRAFFIC_BYTES_PER_LINEARIZED_KNOT = 139.0e3
+# ---- per-knot work figures (ncu numbers from profiles/r01h_ncu_top_kernels.txt, 4096 x 25 knots) ----
+# Riccati backward pass: algorithmic flops of one knot (the five contractions with shared products, the
+# factorisation and the solves) and its algorithmic bytes (A, B, lx, lu, lxx, luu read; K, kff written).
+BWD_FLOPS_PER_KNOT = 1.153e6
+BWD_ALG_BYTES_PER_KNOT = 52816.0 + 7904.0
+BWD_TRAFFIC_BYTES_PER_KNOT = (5.499e9 + 0.800e9) / (4096 * 25)      # dram__bytes_read.sum + dram__bytes_write.sum of one launch
+# Linearization: fp64 operations EXECUTED per knot (2 per DFMA, 1 per DADD / DMUL from the smsp__sass_thread_inst_executed_op_*
+# counters: tangent kernels 10.48 + 10.50 + 4.10 GFLOP, finish 2.51 GFLOP, plus 255 DMMA m8n8k4 = 130.6 kflop per knot in finish)
+LIN_FLOPS_PER_KNOT = (10.48e9 + 10.50e9 + 4.10e9 + 2.51e9) / (4096 * 25) + 255 * 512.0
+# algorithmic bytes: A_k, B_k written; x_k, u_k and the factor (L, D, a) read; the parked tangents written and read once
+LIN_ALG_BYTES_PER_KNOT = (51 * 51 + 51 * 19 + 51 + 19) * 8.0 + (25 * 11 + 25 + 25) * 8.0 + 2 * 48 * 25 * 8.0
+LIN_TRAFFIC_BYTES_PER_KNOT = (0.168e9 + 1.140e9 + 0.180e9 + 0.780e9 + 0.116e9 + 0.317e9 + 2.014e9 + 2.869e9) / (4096 * 25)
 
 if __name__ == "__main__":
     main()
