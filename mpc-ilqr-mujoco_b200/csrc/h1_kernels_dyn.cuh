@@ -215,179 +215,4 @@ k_linearize_dirs(const DynModel* gmd, long nknots, int N, const int* __restrict_
   integrate_tangent_seq(*md, x, pf->a, seed, tv, col);
 }
 
-// ---- analytic linearization, one thread per column, DIRECTION-UNIFORM WARPS: a CTA owns LINC_KNOTS = 32
-//      consecutive knots and stages their Mhat factors (with 1 / D), states, controls and the Jacobians of the
-//      quaternion update in shared memory once (coalesced); each of its warps then repeatedly takes the next work
-//      item of the class (shared counter, costliest first) and differentiates the 32 knots along it, one knot per
-//      lane. Every lane of a warp therefore runs the same walk — in particular the sparse subtree walks of the joint
-//      directions (id_tangent_sub) — and reads its knot's factor from shared memory at an odd stride (conflict
-//      free). Columns are staged per warp and written to A_k / B_k as contiguous 408-byte runs.
-//      CLS 0: hinge angles (19 columns, subtree walks on dual kinematics)
-//          1: base angular velocity (3, every body) + hinge rates (19, subtree walks), plain kinematics
-//          2: the light class — base rotations (3 items: rigid-direction tangents, h1_lin_dirs.cuh; kept in shared
-//             memory), z and base linear velocity (4 columns, contact only), controls (19, triangular solves
-//             only), x / y (unit vectors), and last the 4 raw-quaternion columns = combinations of the three
-//             rotation tangents (they wait for the rotation items, which were handed out first).
-//      (one launch per class: a single launch over all 70 columns balances the warps better but measured 40 %
-//       slower — the warps of a CTA then run five different code paths and thrash the instruction cache) ----
-constexpr int LINC_WARPS = 8, LINC_KNOTS = 32, LINC_THREADS = LINC_WARPS * 32;
-constexpr int LINC_LIGHT_WARPS = 7;                               // the light class trades one column tile for the rotation tangents
-constexpr int LINC_FS = sizeof(PrimalFactor) / sizeof(double);   // 325 doubles: odd stride
-constexpr int LINC_QJ = QJ_DIRS * 4 + 1;                          // 29 doubles per knot: odd stride
-static_assert(LINC_FS % 2 == 1 && NX % 2 == 1 && NU % 2 == 1 && NV % 2 == 1, "per-knot strides must be odd (bank-conflict-free lane <-> knot access)");
-__host__ __device__ constexpr int linc_nitems(int cls) { return cls == 0 ? NB - 1 : cls == 1 ? 3 + NB - 1 : 3 + 4 + NU + 2 + 4; }
-__host__ __device__ constexpr int linc_warps(int cls) { return cls == 2 ? LINC_LIGHT_WARPS : LINC_WARPS; }
-__host__ __device__ constexpr size_t linc_smem_doubles(int cls) {
-  return (size_t)LINC_KNOTS * (LINC_FS + NX + NU + LINC_QJ) + (size_t)linc_warps(cls) * LINC_KNOTS * NX +
-         (cls == 2 ? (size_t)3 * LINC_KNOTS * NV : 0);
-}
-template <int CLS, bool H1TREE>
-__global__ void __launch_bounds__(LINC_THREADS)
-k_linearize_cols(const DynModel* gmd, long nknots, int N, const int* __restrict__ active,
-                 const int* __restrict__ list, const int* __restrict__ list_count,
-                 const double* __restrict__ xbar, const double* __restrict__ ubar,
-                 const PrimalFactor* __restrict__ pf_g, double* __restrict__ A, double* __restrict__ Bm) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  // `list` (optional): compact list of the active instances built on the device by k_solve_state; slot s of the
-  // grid then works on knot (s % N) of instance list[s / N], so every CTA is full however sparse the active set is.
-  __shared__ long kid[LINC_KNOTS];                    // global knot id (instance * N + t) of each slot, -1: nothing to do
-  __shared__ int next_item, rot_done;
-  constexpr int NW = linc_warps(CLS);
-  const long knot0 = (long)blockIdx.x * LINC_KNOTS;
-  if (list) nknots = min(nknots, (long)(*list_count) * N);
-  if (knot0 >= nknots) return;
-  const int nk = (int)min((long)LINC_KNOTS, nknots - knot0);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid < LINC_KNOTS) {
-    long id = -1;
-    if (tid < nk) {
-      const long sl = knot0 + tid;
-      if (list) id = (long)list[sl / N] * N + sl % N;
-      else if (!active || active[sl / N]) id = sl;
-    }
-    kid[tid] = id;
-  }
-  if (tid == 0) { next_item = 0; rot_done = 0; }
-  const DynModel* md;
-  unsigned char* p = stage_model(smem, gmd, &md);    // (has a __syncthreads)
-  bool any = false;
-  for (int k = 0; k < nk; ++k) any |= kid[k] >= 0;
-  if (!any) return;                                   // all 32 knots belong to finished instances
-  double* fac = reinterpret_cast<double*>(p);        // [LINC_KNOTS][LINC_FS]
-  double* xs = fac + LINC_KNOTS * LINC_FS;           // [LINC_KNOTS][NX]
-  double* us = xs + LINC_KNOTS * NX;                 // [LINC_KNOTS][NU]
-  double* qj = us + LINC_KNOTS * NU;                 // [LINC_KNOTS][LINC_QJ]
-  double* tile = qj + LINC_KNOTS * LINC_QJ + warp * LINC_KNOTS * NX;   // this warp's [LINC_KNOTS][NX]
-  double* trot = qj + LINC_KNOTS * LINC_QJ + NW * LINC_KNOTS * NX;     // (CLS 2) [3][LINC_KNOTS][NV]
-  {
-    constexpr int DOFF = NV * MAXSLOT;               // PrimalFactor::D
-    for (int i = tid; i < nk * LINC_FS; i += NW * 32) {
-      const int k = i / LINC_FS, j = i - k * LINC_FS;
-      const long id = kid[k];
-      if (id < 0) continue;
-      const double v = reinterpret_cast<const double*>(pf_g + id)[j];
-      fac[i] = (j >= DOFF && j < DOFF + NV) ? 1.0 / v : v;
-    }
-    for (int i = tid; i < nk * NX; i += NW * 32) {
-      const int k = i / NX, j = i - k * NX;
-      const long id = kid[k];
-      if (id < 0) continue;
-      const long inst = id / N;
-      xs[i] = xbar[((size_t)inst * (N + 1) + (id - inst * N)) * NX + j];
-    }
-    for (int i = tid; i < nk * NU; i += NW * 32) {
-      const int k = i / NU, j = i - k * NU;
-      const long id = kid[k];
-      if (id >= 0) us[i] = ubar[(size_t)id * NU + j];
-    }
-  }
-  __syncthreads();
-  if (tid < LINC_KNOTS * QJ_DIRS) {   // Jacobians of the quaternion update: one (knot, direction) per thread
-    const int k = tid / QJ_DIRS, d = tid - k * QJ_DIRS;
-    if (k < nk && kid[k] >= 0)
-      quat_step_jac_dir(*md, xs + k * NX, reinterpret_cast<const PrimalFactor*>(fac + k * LINC_FS)->a, d, qj + k * LINC_QJ + 4 * d);
-  }
-  __syncthreads();
-  const bool ok = lane < nk && kid[lane] >= 0;
-  const double* x = xs + lane * NX;
-  const PrimalFactor* pf = reinterpret_cast<const PrimalFactor*>(fac + lane * LINC_FS);   // (D holds reciprocals)
-  double* col = tile + lane * NX;
-  while (true) {
-    int it = 0;
-    if (lane == 0) it = atomicAdd(&next_item, 1);
-    it = __shfl_sync(0xffffffffu, it, 0);
-    if (it >= linc_nitems(CLS)) break;
-    int seed = -1;                 // output column (0..50 of A, 51..69 -> B); -1: a rotation item (no column)
-    if (CLS == 0) seed = 6 + md->dir_order[it];                          // hinges by decreasing subtree size
-    else if (CLS == 1) seed = it < 3 ? NQ + 3 + it : NQ + 5 + md->dir_order[it - 3];
-    else {
-      if (it < 3) seed = -1;
-      else if (it == 3) seed = 2;
-      else if (it < 7) seed = NQ + it - 4;
-      else if (it < 7 + NU) seed = NX + it - 7;
-      else if (it < 9 + NU) seed = it - 7 - NU;
-      else seed = 3 + it - 9 - NU;
-    }
-    if (CLS == 2 && seed >= 3 && seed < 7) {   // quaternion column: needs the three rotation tangents
-      if (lane == 0) while (atomicAdd(&rot_done, 0) < 3) { }
-      __syncwarp();
-      __threadfence_block();
-    }
-    if (ok) {
-      if (CLS == 2 && seed >= 0 && seed < 2) {
-        for (int j = 0; j < NX; ++j) col[j] = (j == seed) ? 1.0 : 0.0;   // f_D is translation invariant in x and y
-      } else if (CLS == 2 && seed < 0) {
-        double tv[NV];
-        id_tangent_rot(*md, x, pf->a, it, tv);
-        double* dst = trot + ((size_t)it * LINC_KNOTS + lane) * NV;
-        for (int j = 0; j < NV; ++j) dst[j] = tv[j];
-      } else {
-        double tv[NV];
-        if (CLS == 0) id_tangent_sub<Dual, Dual>(*md, x, pf->a, seed, seed - 6, tv);
-        else if (CLS == 1) {
-          if (it < 3) id_tangent_seq<double, Dual>(*md, x, pf->a, seed, tv);
-          else id_tangent_sub<double, Dual>(*md, x, pf->a, seed, seed - NQ - 5, tv);
-        } else if (seed >= NX) {
-          const int j = seed - NX;
-          const double uj = us[lane * NU + j];
-          for (int k = 0; k < NV; ++k) tv[k] = 0.0;
-          tv[6 + j] = (uj < md->ctrl_lo[j] || uj > md->ctrl_hi[j]) ? 0.0 : 1.0;   // clamped torque: no sensitivity
-        } else if (seed >= 3 && seed < 7) {
-          double G[3][4];
-          quat_rot_map(x + 3, G);
-          const double g0 = G[0][seed - 3], g1 = G[1][seed - 3], g2 = G[2][seed - 3];
-          const double* t0 = trot + (size_t)lane * NV;
-          for (int j = 0; j < NV; ++j)
-            tv[j] = g0 * t0[j] + g1 * t0[LINC_KNOTS * NV + j] + g2 * t0[2 * LINC_KNOTS * NV + j];
-        } else {
-          id_tangent_rigid(*md, x, pf->a, seed, tv);
-        }
-        if (H1TREE) tangent_solve_h1<true>(&pf->Lm[0][0], pf->D, tv);
-        else tangent_solve_seq<true>(*md, &pf->Lm[0][0], pf->D, tv);
-        integrate_tangent_pre(*md, seed, tv, qj + lane * LINC_QJ, col);
-      }
-    }
-    __syncwarp();
-    if (CLS == 2 && seed < 0) {    // publish the rotation tangent
-      __threadfence_block();
-      if (lane == 0) atomicAdd(&rot_done, 1);
-      continue;
-    }
-    // the 32 columns of this item: contiguous 51-double runs
-    {
-      double* dst0 = (seed >= NX) ? Bm + (size_t)(seed - NX) * NX : A + (size_t)seed * NX;
-      const size_t kstride = (seed >= NX) ? (size_t)NX * NU : (size_t)NX * NX;
-      int k = 0, j = lane;
-#pragma unroll 1
-      for (int e = lane; e < nk * NX; e += 32) {
-        const long id = kid[k];
-        if (id >= 0) dst0[(size_t)id * kstride + j] = tile[e];
-        j += 32;
-        if (j >= NX) { j -= NX; ++k; }
-      }
-    }
-    __syncwarp();
-  }
-}
-
 }  // namespace h1

@@ -617,7 +617,7 @@ H1_DEV void tangent_solve_seq(const DynModel& md, const double* __restrict__ Lm,
 }
 
 // Same solve with H1's dof tree compiled in (DynModel::seq_ok): every index is static, t stays in registers.
-// DINV: D holds the reciprocals 1 / D_k (staged once per knot by k_linearize_cols) -> no division per column.
+// DINV: D holds the reciprocals 1 / D_k -> no division per column.
 template <bool DINV = false>
 H1_DEV void tangent_solve_h1(const double* __restrict__ Lm, const double* __restrict__ D, double* __restrict__ t) {
 #pragma unroll

@@ -36,6 +36,8 @@ struct RiccatiSmem {
   double Kt[LDU * 56];        // solves: columns 0..50 -> K(:,j), column 51 -> kff; pad row 19 stays zero
   double Quu[LDU * LDU];      // pad row/column 19 stay zero
   double Ls[NU * NU];         // unit-lower factor of the permuted LDL^T
+  double col[2][32];          // column exchange of the LDL^T warp (double buffered)
+  double Li[LDU * LDU];       // its inverse (unit lower), row-major; pad row / column 19 stay zero
   double Vx[LDX], Qx[NX], Qu[NU], D[NU], Dinv[NU], tmp[NU];   // Vx[51] is a zero pad (Vx rides along as an extra column of W)
   double lq[NX + NU + NU * NU + 1];   // lx_t, lu_t, luu_t of the current knot (prefetched with [A|B])
   int perm[NU];
@@ -97,7 +99,7 @@ __device__ __forceinline__ void mma_tile_split(int m0, int n0, FA fa, FB fb, dou
 
 // LDL^T of Quu with symmetric pivoting by largest |diagonal| (Eigen::LDLT's selection rule), ONE warp, right-
 // looking, register resident: lane i holds row i of the permuted matrix (lower triangle), column k of the
-// current Schur complement is broadcast with shuffles. Writes perm, D, Ls (unit-lower factor). Returns true when
+// current Schur complement is exchanged through shared memory. Writes perm, D, Dinv, Ls (unit-lower factor). Returns true when
 // a pivot is <= 0, which for a symmetric matrix is equivalent to Eigen::LLT reporting failure (Sylvester).
 __device__ __forceinline__ bool quu_ldlt(RiccatiSmem& s) {
   const int lane = threadIdx.x & 31;
@@ -120,18 +122,21 @@ __device__ __forceinline__ bool quu_ldlt(RiccatiSmem& s) {
   bool not_pd = false;
 #pragma unroll
   for (int k = 0; k < n; ++k) {
-    const double d = __shfl_sync(0xffffffffu, p[k], k);
+    // column k of the current Schur complement goes through shared memory (one store, broadcast loads): lane c's p[k] is
+    // P(c,k), lane k's is the pivot. Entries p[c] with c > lane are never read again, so they are updated unguarded.
+    double* colk = s.col[k & 1];
+    const double pik = p[k];                                           // P(i,k) of this lane's row
+    colk[lane] = pik;
+    __syncwarp();
+    const double d = colk[k];
     if (!(d > 0.0)) not_pd = true;
     const double rd = (fabs(d) > 2.2250738585072014e-308) ? 1.0 / d : 0.0;   // one reciprocal per pivot: the division is on
     if (lane == 0) { s.D[k] = d; s.Dinv[k] = rd; }                          // the critical path of the whole knot
-    const double pik = p[k];                                           // P(i,k) of this lane's row
     const double lik = pik * rd;
 #pragma unroll
     for (int c = 1; c < n; ++c) {
       if (c <= k) continue;                                            // (constant trip counts: both loops unroll fully)
-      const double pck = __shfl_sync(0xffffffffu, pik, c);             // P(c,k)
-      const double upd = p[c] - lik * pck;                             // P(i,c) -= l_ik P(c,k)
-      p[c] = (c <= lane) ? upd : p[c];                                 // select form keeps p[] in registers
+      p[c] -= lik * colk[c];                                           // P(i,c) -= l_ik P(c,k)
     }
     if (lane > k && lane < n) s.Ls[k * n + lane] = lik;
   }
@@ -140,10 +145,10 @@ __device__ __forceinline__ bool quu_ldlt(RiccatiSmem& s) {
 }
 
 #ifdef RIC_PROF   // debug build only (make NVCC="nvcc -DRIC_PROF"): per-phase cycles of warp 0 / warp 7 of block 0, printed at kernel end
-#define RP_DECL long long rp_t = clock64(); long long rp_acc[16]; for (int q_ = 0; q_ < 16; ++q_) rp_acc[q_] = 0;
+#define RP_DECL long long rp_t = clock64(); long long rp_acc[20]; for (int q_ = 0; q_ < 20; ++q_) rp_acc[q_] = 0;
 #define RP_MARK(p) { const long long now_ = clock64(); rp_acc[p] += now_ - rp_t; rp_t = now_; }
-#define RP_SYNC(p) { RP_MARK(2 * (p)); __syncthreads(); { unsigned x_; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(x_) : "r"((unsigned)__cvta_generic_to_shared(&s.perm[0])) : "memory"); rp_acc[15] += x_ & 0; } RP_MARK(2 * (p) + 1); }
-#define RP_PRINT if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 7)) printf("ric warp %d work/wait: top %lld/%lld G1b %lld/%lld G3 %lld/%lld P2 %lld/%lld solve %lld/%lld G4 %lld/%lld G5 %lld/%lld sym %lld\n", warp, rp_acc[0], rp_acc[1], rp_acc[2], rp_acc[3], rp_acc[4], rp_acc[5], rp_acc[6], rp_acc[7], rp_acc[8], rp_acc[9], rp_acc[10], rp_acc[11], rp_acc[12], rp_acc[13], rp_acc[14]);
+#define RP_SYNC(p) { RP_MARK(2 * (p)); __syncthreads(); { unsigned x_; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(x_) : "r"((unsigned)__cvta_generic_to_shared(&s.perm[0])) : "memory"); rp_acc[19] += x_ & 0; } RP_MARK(2 * (p) + 1); }
+#define RP_PRINT if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 7)) printf("ric warp %d work/wait: top %lld/%lld G1b %lld/%lld G3 %lld/%lld P2 %lld/%lld solve %lld/%lld G4 %lld/%lld G5 %lld/%lld sym %lld Linv %lld/%lld\n", warp, rp_acc[0], rp_acc[1], rp_acc[2], rp_acc[3], rp_acc[4], rp_acc[5], rp_acc[6], rp_acc[7], rp_acc[8], rp_acc[9], rp_acc[10], rp_acc[11], rp_acc[12], rp_acc[13], rp_acc[16], rp_acc[14], rp_acc[15]);
 #else
 #define RP_DECL
 #define RP_MARK(p)
@@ -165,7 +170,7 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
   const double lam = lambda[inst];
   const double* lxN = lx + ((size_t)inst * (N + 1) + N) * NX;
   const double* lxxN = lxx + ((size_t)inst * (N + 1) + N) * NX * NX;
-  auto prefetch_ab = [&](int t) {  // A_t, B_t -> s.AB (8-byte async copies; global columns are only 8-byte aligned)
+  auto prefetch_ab = [&](int t, int tid, int nt) {  // A_t, B_t -> s.AB (8-byte async copies; global columns are only 8-byte aligned)
     const double* At = A + ((size_t)inst * N + t) * NX * NX;      // [A_t | B_t] are NOT contiguous in global memory
     const double* Bt = Bm + ((size_t)inst * N + t) * NX * NU;
     for (int i = tid; i < NX * NX; i += nt) { const int c = i / NX, r = i - c * NX; cp_async8(&s.AB[c * LDX + r], At + i); }
@@ -181,9 +186,9 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
   for (int i = tid; i < LDX * LDX; i += nt) s.V[i] = 0.0;
   for (int i = tid; i < NXU; i += nt) s.AB[i * LDX + NX] = 0.0;
   for (int i = tid; i < LDU * 56; i += nt) s.Kt[i] = 0.0;
-  for (int i = tid; i < LDU * LDU; i += nt) s.Quu[i] = 0.0;
+  for (int i = tid; i < LDU * LDU; i += nt) { s.Quu[i] = 0.0; s.Li[i] = 0.0; }
   __syncthreads();
-  prefetch_ab(N - 1);
+  prefetch_ab(N - 1, tid, nt);
   for (int i = tid; i < LDX; i += nt) s.Vx[i] = (i < NX) ? lxN[i] : 0.0;
   for (int i = tid; i < NX * NX; i += nt) { const int c = i / NX, r = i - c * NX; s.V[c * LDX + r] = lxxN[i]; }
   bool nonfinite = false;
@@ -259,55 +264,85 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
       }
     }
     RP_SYNC(3)
-    // s.AB and s.W are free: prefetch the next knot's [A|B] and this knot's lxx (consumed by the final pass)
-    if (t > 0) prefetch_ab(t - 1);
-    {
-      const double* Lt = lxx + ((size_t)inst * (N + 1) + t) * NX * NX;
-      for (int i = tid; i < NX * NX; i += nt) cp_async8(&Lpre[i], Lt + i);
-    }
-    // ---- solves, 4 threads per right-hand side (rows i = q, q+4, ...): rhs r < 51 -> row r of Qxu, rhs 51 -> Qu;
-    //      column-oriented substitutions, the finished entry is broadcast inside the 4-lane group; result negated.
-    //      Per row the updates are applied in the same order as a row-oriented substitution. ----
+    // ---- warps 0..6: s.AB and s.W are free -> prefetch the next knot's [A|B], lx, lu, luu and this knot's lxx (consumed
+    //      by the final pass) | warp 7: N = L^-1 (unit lower; lane j owns column j, 171 multiply-adds). With N explicit the
+    //      52 pairs of triangular solves of the knot become two small tensor-core contractions instead of 36 dependent
+    //      shuffle / multiply-add steps per right-hand side. (Computing N row by row inside the factorisation loop was
+    //      measured slower: the factorisation, not the contractions beside it, then bounds that phase.) ----
     if (warp < 7) {
-      const int q = tid & 3, r = min(tid >> 2, NX);
-      const bool valid = (tid >> 2) <= NX;
-      double y[5];
+      if (t > 0) prefetch_ab(t - 1, tid, 7 * 32);
+      const double* Lt = lxx + ((size_t)inst * (N + 1) + t) * NX * NX;
+      for (int i = tid; i < NX * NX; i += 7 * 32) cp_async8(&Lpre[i], Lt + i);
+    } else if (lane < LDU) {
+      double x[NU];
 #pragma unroll
-      for (int m = 0; m < 5; ++m) {
-        const int i = q + 4 * m;
-        const int pi = s.perm[min(i, NU - 1)];
-        y[m] = (i < NU) ? ((r < NX) ? s.Qxu[pi * LDX + r] : s.Qu[pi]) : 0.0;
+      for (int i = 0; i < NU; ++i) {
+        double v0 = (i == lane) ? 1.0 : 0.0, v1 = 0.0;
+#pragma unroll
+        for (int m = 0; m < i; ++m) {
+          if (m & 1) v1 -= s.Ls[m * NU + i] * x[m]; else v0 -= s.Ls[m * NU + i] * x[m];
+        }
+        x[i] = v0 + v1;
+        s.Li[i * LDU + lane] = x[i];
       }
+    }
+    RP_SYNC(7)
+    // ---- K = -Quu^-1 Qxu', k = -Quu^-1 Qu with P Quu P' = L D L':  X = P' N' D^-1 N (P R), R = [Qxu' | Qu] (19 x 52).
+    //      Each of the warps 0..6 owns one 8-column tile of R: Y = N (P R), Z = D^-1 Y parked in its own columns of
+    //      s.Kt, X = N' Z; no exchange between warps ----
+    if (warp < 7) {
+      const int n0 = 8 * warp;
+      double acc[3][2];
 #pragma unroll
-      for (int c = 0; c < NU - 1; ++c) {        // forward substitution with the unit-lower L
-        const double yc = __shfl_sync(0xffffffffu, y[c >> 2], c & 3, 4);
+      for (int mi = 0; mi < 3; ++mi) acc[mi][0] = acc[mi][1] = 0.0;
 #pragma unroll
-        for (int m = 0; m < 5; ++m) {
-          const int i = q + 4 * m;
-          if (4 * m + 3 > c && i > c && i < NU) y[m] -= s.Ls[c * NU + i] * yc;
+      for (int ks = 0; ks < 5; ++ks) {
+        const int k = 4 * ks + t4, n = n0 + g;
+        const int pk = s.perm[min(k, NU - 1)];
+        const double b = (k < NU) ? (n < NX ? s.Qxu[pk * LDX + n] : (n == NX ? s.Qu[pk] : 0.0)) : 0.0;
+#pragma unroll
+        for (int mi = 0; mi < 3; ++mi) {
+          const int r = 8 * mi + g;
+          dmma884(acc[mi][0], acc[mi][1], r < LDU ? s.Li[r * LDU + k] : 0.0, b);
         }
       }
 #pragma unroll
-      for (int m = 0; m < 5; ++m) {
-        const int i = min(q + 4 * m, NU - 1);
-        y[m] *= s.Dinv[i];                      // (0 for a vanishing pivot, as Eigen::LDLT::solve does)
-      }
-#pragma unroll
-      for (int c = NU - 1; c >= 1; --c) {       // back substitution with L^T
-        const double xc = __shfl_sync(0xffffffffu, y[c >> 2], c & 3, 4);
-#pragma unroll
-        for (int m = 0; m < 5; ++m) {
-          const int i = q + 4 * m;
-          if (4 * m < c && i < c) y[m] -= s.Ls[i * NU + c] * xc;
+      for (int mi = 0; mi < 3; ++mi) {
+        const int r = 8 * mi + g;
+        if (r < LDU) {
+          const double di = r < NU ? s.Dinv[r] : 0.0;     // (0 for a vanishing pivot, as Eigen::LDLT::solve does)
+          s.Kt[(n0 + 2 * t4) * LDU + r] = di * acc[mi][0];
+          s.Kt[(n0 + 2 * t4 + 1) * LDU + r] = di * acc[mi][1];
         }
       }
+      __syncwarp();
 #pragma unroll
-      for (int m = 0; m < 5; ++m) {
-        const int i = q + 4 * m;
-        if (valid && i < NU) {
-          const double v = -y[m];
-          if (!isfinite(v)) nonfinite = true;
-          s.Kt[r * LDU + s.perm[i]] = v;
+      for (int mi = 0; mi < 3; ++mi) acc[mi][0] = acc[mi][1] = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < 5; ++ks) {
+        const int k = 4 * ks + t4;
+        const double b = s.Kt[(n0 + g) * LDU + k];
+#pragma unroll
+        for (int mi = 0; mi < 3; ++mi) {
+          const int r = 8 * mi + g;
+          dmma884(acc[mi][0], acc[mi][1], r < LDU ? s.Li[k * LDU + r] : 0.0, b);   // N'(r, k) = N(k, r)
+        }
+      }
+      __syncwarp();   // every lane has read Z before its columns are overwritten with the gains
+#pragma unroll
+      for (int mi = 0; mi < 3; ++mi) {
+        const int r = 8 * mi + g;
+        if (r < NU) {
+          const int pr = s.perm[r];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int n = n0 + 2 * t4 + q;
+            if (n <= NX) {
+              const double v = -acc[mi][q];
+              if (!isfinite(v)) nonfinite = true;
+              s.Kt[n * LDU + pr] = v;
+            }
+          }
         }
       }
     }
@@ -400,7 +435,7 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
       const double v = 0.5 * (mij + mji);
       s.V[j * LDX + i] = v; s.V[i * LDX + j] = v;
     }
-    RP_MARK(14)
+    RP_MARK(16)
     // (the __syncthreads at the top of the next iteration orders these writes before G1)
   }
   RP_PRINT

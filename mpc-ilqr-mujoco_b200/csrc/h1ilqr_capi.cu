@@ -40,7 +40,6 @@ struct H1Ilqr {
   int *active = nullptr, *second = nullptr, *iters = nullptr, *status = nullptr, *ls_ok = nullptr, *ls_alpha = nullptr;
   int *act_list = nullptr, *sec_list = nullptr, *list_count = nullptr;
   int *early = nullptr, *late = nullptr, *early_list = nullptr, *late_list = nullptr;
-  bool lin_legacy = false;   // H1ILQR_LIN_COLUMNS=1: per-column solves (k_linearize_cols) instead of the dense finish
   int *has_prev = nullptr, *warm_mask = nullptr, *cold_mask = nullptr, *warm_in = nullptr;
   double* cost_trace = nullptr; int* alpha_trace = nullptr;
   PrimalFactor* pf = nullptr;   // [B][N] factorisation of Mhat at every knot of the nominal trajectory
@@ -56,7 +55,7 @@ struct H1Ilqr {
   int policy = H1ILQR_KERNELS_AUTO;
   int seq_min_batch = 768;  // AUTO: batch at or above which rollouts / line searches run one THREAD per f_D evaluation (h1_dyn_seq.cuh);
                             // measured break-even with the warp-per-evaluation kernels: between 512 and 1024 instances
-  size_t smem_seq = 0, smem_seq_ls = 0, smem_linc[3] = {0, 0, 0}, smem_lint = 0, smem_linf = 0;
+  size_t smem_seq = 0, smem_seq_ls = 0, smem_lint = 0, smem_linf = 0;
   bool seq_ok = false;      // the model has the chain structure the thread-sequential f_D is specialised for
   long lin_cols_min_knots = 148 * 32;   // AUTO: B*N at or above which the direction-uniform linearization (32 knots per CTA) fills the GPU;
                                         // below it the knot-major thread-per-column kernel (k_linearize_dirs) is the faster one
@@ -126,7 +125,6 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
     delete h; return set_err(H1ILQR_EARG, "model is not a DFS-ordered H1-like tree");
   }
   h->seq_ok = dm.seq_ok != 0;
-  { const char* e = std::getenv("H1ILQR_LIN_COLUMNS"); h->lin_legacy = e && std::atoi(e) != 0; }
   if (const char* e = getenv("H1_SEQ_MIN_BATCH")) h->seq_min_batch = atoi(e);   // tuning experiments
 #define CUH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(H1ILQR_ECUDA, #call, e_); h1ilqr_destroy(h); return H1ILQR_ECUDA; } } while (0)
   CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -172,12 +170,6 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   h->smem_ls = mdl + H1ILQR_NALPHA * sizeof(DynWarp) + (H1ILQR_NALPHA + H1ILQR_NALPHA * (NX + NU)) * sizeof(double);
   h->smem_ric = sizeof(RiccatiSmem);
   h->smem_seq = mdl;
-#define LINC_ATTR(CLS) \
-  h->smem_linc[CLS] = mdl + linc_smem_doubles(CLS) * sizeof(double); \
-  CUH(cudaFuncSetAttribute(k_linearize_cols<CLS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_linc[CLS])); \
-  CUH(cudaFuncSetAttribute(k_linearize_cols<CLS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_linc[CLS]));
-  LINC_ATTR(0) LINC_ATTR(1) LINC_ATTR(2)
-#undef LINC_ATTR
   h->smem_lint = mdl + LINT_SMEM_DOUBLES * sizeof(double);
   h->smem_linf = LINF_WARPS * sizeof(LinFinishWarp);
   CUH(cudaFuncSetAttribute(k_linearize_tangents<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_lint));
@@ -289,26 +281,17 @@ static void launch_linearize(H1Ilqr* h, const int* mask, bool factors_ready = fa
     if (!factors_ready) launch_factors(h, mask);
     const long knots = (long)h->B * h->N;
     if (use_batched(h, knots, h->lin_cols_min_knots)) {  // one thread per column, direction-uniform warps
-      const unsigned kb = (unsigned)((knots + LINC_KNOTS - 1) / LINC_KNOTS);
+      const unsigned kb = (unsigned)((knots + LINT_KNOTS - 1) / LINT_KNOTS);
       const int* cnt; const int* list = list_for(h, mask, &cnt);   // compact instance list (k_solve_state)
-      if (!h->lin_legacy) {   // tangents parked in A_k, then one dense contraction per knot (h1_lin_finish.cuh)
+      // tangents parked in A_k, then one dense contraction per knot (h1_lin_finish.cuh)
 #define LINT_LAUNCH(CLS) \
   k_linearize_tangents<CLS><<<kb, LINT_THREADS, h->smem_lint, h->stream>>>(h->d_dyn, knots, h->N, mask, list, cnt, h->xbar, h->pf, h->A)
-        LINT_LAUNCH(0); LINT_LAUNCH(1); LINT_LAUNCH(2);
+      LINT_LAUNCH(0); LINT_LAUNCH(1); LINT_LAUNCH(2);
 #undef LINT_LAUNCH
-        const unsigned fb = (unsigned)((knots + LINF_WARPS - 1) / LINF_WARPS);
-        if (h->seq_ok) k_linearize_finish<true><<<fb, LINF_THREADS, h->smem_linf, h->stream>>>(h->d_dyn, knots, h->N, mask, list, cnt, h->xbar, h->ubar, h->pf, h->A, h->Bm);
-        else k_linearize_finish<false><<<fb, LINF_THREADS, h->smem_linf, h->stream>>>(h->d_dyn, knots, h->N, mask, list, cnt, h->xbar, h->ubar, h->pf, h->A, h->Bm);
-        h->launches += 4;
-        return;
-      }
-#define LINC_LAUNCH(CLS, TREE)                                                                                        \
-  k_linearize_cols<CLS, TREE><<<kb, linc_warps(CLS) * 32, h->smem_linc[CLS], h->stream>>>(                            \
-      h->d_dyn, knots, h->N, mask, list, cnt, h->xbar, h->ubar, h->pf, h->A, h->Bm)
-      if (h->seq_ok) { LINC_LAUNCH(0, true); LINC_LAUNCH(1, true); LINC_LAUNCH(2, true); }
-      else { LINC_LAUNCH(0, false); LINC_LAUNCH(1, false); LINC_LAUNCH(2, false); }
-      h->launches += 3;
-#undef LINC_LAUNCH
+      const unsigned fb = (unsigned)((knots + LINF_WARPS - 1) / LINF_WARPS);
+      if (h->seq_ok) k_linearize_finish<true><<<fb, LINF_THREADS, h->smem_linf, h->stream>>>(h->d_dyn, knots, h->N, mask, list, cnt, h->xbar, h->ubar, h->pf, h->A, h->Bm);
+      else k_linearize_finish<false><<<fb, LINF_THREADS, h->smem_linf, h->stream>>>(h->d_dyn, knots, h->N, mask, list, cnt, h->xbar, h->ubar, h->pf, h->A, h->Bm);
+      h->launches += 4;
       return;
     }
     if (h->policy == H1ILQR_KERNELS_AUTO) {   // small batches: one thread per column, knot-major (the factor is shared by a warp)

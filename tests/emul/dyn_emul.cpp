@@ -100,7 +100,7 @@ extern "C" int emul_dyn_com_seq(int n, const double* x, double* com) {
   return 0;
 }
 
-// same columns through the sparsity-exploiting path of kernel k_linearize_cols (csrc/h1_lin_dirs.cuh): joint
+// same columns through the per-direction tangent functions of kernel k_linearize_tangents (csrc/h1_lin_dirs.cuh): joint
 // directions walk only subtree(joint) with dual numbers, x / y columns are unit vectors
 extern "C" int emul_dyn_linearize_cols(const double* x, const double* u, double* A, double* B) {
   static h1::DynModel md;

@@ -84,7 +84,7 @@ def test_direction_per_thread_linearization_matches_oracle_ad(emul, oracle):
 
 
 def test_sparse_column_linearization_matches_oracle_ad(emul, oracle):
-    """kernel k_linearize_cols' per-column function: joint directions walk only subtree(joint) with dual numbers,
+    """the per-direction tangent functions of k_linearize_tangents (joint directions walk only subtree(joint) with dual numbers, the rigid base directions use the contact-only / rotation-covariance tangents) composed into columns,
     the x / y columns are unit vectors; against the oracle's forward-mode AD, incl. feet in contact and clamps."""
     x, u = states(12, 9)
     u[::3, 3] = 400.0
