@@ -298,7 +298,7 @@ def main():
         single_ms = s1.run_resident_steps(5, True) / 5
         s1.close()
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # (rank 0 at N = 1 only)
             v, threads, secs = cpu_oracle_rate_parallel(args.cpu_sample)
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{args.cpu_sample} instances of the same workload, one cold MPC step each, all host threads ({secs:.1f} s)"}

@@ -417,3 +417,24 @@ def test_contact_schedule_generation(gpu, tmp_path):
     p = tmp_path / "contact.csv"
     write_contact_csv(str(p), cw)
     assert (load_contact_csv(str(p)) == cw).all()
+
+
+def test_registered_host_buffers_give_identical_results(gpu):
+    """h1ilqr_host_register (page-locked caller buffers) changes how the copies run, not what they carry."""
+    w = Config().build_weights()
+    refs = reference_set("walking")
+    B = 4
+    wins = [refs.window(5 * i, 25) for i in range(B)]
+    win = tuple(np.ascontiguousarray(np.stack([wi[k] for wi in wins])) for k in range(6))
+    x0 = np.ascontiguousarray(np.stack([wi[0][0] for wi in wins]))
+    ug = grav_comp_guess(standing_state())
+    out = []
+    for pin in (False, True):
+        s = gpu.H1IlqrBatch(w, N=25, batch=B)
+        a = tuple(s.pin_host(*win)) if pin else win
+        xx = s.pin_host(x0) if pin else x0
+        s.set_reference_window(*a, shared=False)
+        ua, c = s.mpc_step(xx, ug)
+        out.append((ua.copy(), c.copy()))
+        s.close()
+    assert (out[0][0] == out[1][0]).all() and (out[0][1] == out[1][1]).all()
