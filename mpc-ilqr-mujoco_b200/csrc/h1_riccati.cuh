@@ -243,7 +243,8 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
     RP_SYNC(2)
     // ---- warps 0..6: G1a: W(:, 0..47) = Vxx A(:, 0..47), then G2: [Qxx | Qxu | A'Vx] = A' [W | Vx] (Qxx -> s.V,
     //      Qxu -> s.Qxu, the spare column 70 of the last tile carries Vx and yields Qx = lx + A'Vx)
-    //      | warp 7: pivoted LDL^T of Quu, hidden behind both contractions ----
+    //      | warp 7: pivoted LDL^T of Quu, then N = L^-1: the sequential section of the knot, beside both contractions and the
+    //      prefetch (one barrier for the whole phase) ----
     if (warp < 7) {
       w_strip(std::integral_constant<int, 6>(), 0);
       asm volatile("bar.sync 1, 224;" ::: "memory");   // W complete (the seven contraction warps only)
@@ -256,34 +257,33 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
                            else if (c < NXU) s.Qxu[(c - NX) * LDX + r] = v;
                            else if (c == NXU) s.Qx[r] = lxt[r] + v;
                          });
+      // s.AB, s.W and s.lq are free once all seven contraction warps are through G2 -> prefetch the next knot's [A|B], lx,
+      // lu, luu and this knot's lxx (consumed by the final pass) while warp 7 is still in its sequential section
+      asm volatile("bar.sync 1, 224;" ::: "memory");
+      if (t > 0) prefetch_ab(t - 1, tid, 7 * 32);
+      const double* Lt = lxx + ((size_t)inst * (N + 1) + t) * NX * NX;
+      for (int i = tid; i < NX * NX; i += 7 * 32) cp_async8(&Lpre[i], Lt + i);
     } else {
       if (quu_ldlt(s)) {          // Eigen::LLT failed: Quu += 1e-4 I once, no re-check (quirk Q9), refactor
         for (int i = lane; i < NU; i += 32) s.Quu[i * LDU + i] += 1e-4;
         __syncwarp();
         quu_ldlt(s);
       }
-    }
-    RP_SYNC(3)
-    // ---- warps 0..6: s.AB and s.W are free -> prefetch the next knot's [A|B], lx, lu, luu and this knot's lxx (consumed
-    //      by the final pass) | warp 7: N = L^-1 (unit lower; lane j owns column j, 171 multiply-adds). With N explicit the
-    //      52 pairs of triangular solves of the knot become two small tensor-core contractions instead of 36 dependent
-    //      shuffle / multiply-add steps per right-hand side. (Computing N row by row inside the factorisation loop was
-    //      measured slower: the factorisation, not the contractions beside it, then bounds that phase.) ----
-    if (warp < 7) {
-      if (t > 0) prefetch_ab(t - 1, tid, 7 * 32);
-      const double* Lt = lxx + ((size_t)inst * (N + 1) + t) * NX * NX;
-      for (int i = tid; i < NX * NX; i += 7 * 32) cp_async8(&Lpre[i], Lt + i);
-    } else if (lane < LDU) {
-      double x[NU];
+      // N = L^-1 (unit lower; lane j owns column j, 171 multiply-adds). With N explicit the 52 pairs of triangular solves
+      // of the knot become two small tensor-core contractions instead of 36 dependent shuffle / multiply-add steps per
+      // right-hand side. (Computing N row by row inside the factorisation loop was measured slower.)
+      if (lane < LDU) {
+        double x[NU];
 #pragma unroll
-      for (int i = 0; i < NU; ++i) {
-        double v0 = (i == lane) ? 1.0 : 0.0, v1 = 0.0;
+        for (int i = 0; i < NU; ++i) {
+          double v0 = (i == lane) ? 1.0 : 0.0, v1 = 0.0;
 #pragma unroll
-        for (int m = 0; m < i; ++m) {
-          if (m & 1) v1 -= s.Ls[m * NU + i] * x[m]; else v0 -= s.Ls[m * NU + i] * x[m];
+          for (int m = 0; m < i; ++m) {
+            if (m & 1) v1 -= s.Ls[m * NU + i] * x[m]; else v0 -= s.Ls[m * NU + i] * x[m];
+          }
+          x[i] = v0 + v1;
+          s.Li[i * LDU + lane] = x[i];
         }
-        x[i] = v0 + v1;
-        s.Li[i * LDU + lane] = x[i];
       }
     }
     RP_SYNC(7)
