@@ -104,11 +104,13 @@ __device__ __forceinline__ void mma_tile_split(int m0, int n0, FA fa, FB fb, dou
 __device__ __forceinline__ bool quu_ldlt(RiccatiSmem& s) {
   const int lane = threadIdx.x & 31;
   constexpr int n = NU;
-  if (lane < n) {  // rank of |Q_ii| in descending order, ties by index
-    const double di = fabs(s.Quu[lane * LDU + lane]);
+  if (lane < n) {  // rank of |Q_ii| in descending order, ties by index. A NaN diagonal (diverged instance: the reference
+                   // carries non-finite gains on with a warning, ilqr.cpp:290-293) sorts last, so perm is always a permutation
+    auto key = [&](int j) { const double v = fabs(s.Quu[j * LDU + j]); return (v == v) ? v : -1.0; };
+    const double di = key(lane);
     int rank = 0;
     for (int j = 0; j < n; ++j) {
-      const double dj = fabs(s.Quu[j * LDU + j]);
+      const double dj = key(j);
       rank += (dj > di) || (dj == di && j < lane);
     }
     s.perm[rank] = lane;

@@ -438,3 +438,32 @@ def test_registered_host_buffers_give_identical_results(gpu):
         out.append((ua.copy(), c.copy()))
         s.close()
     assert (out[0][0] == out[1][0]).all() and (out[0][1] == out[1][1]).all()
+
+
+def test_backward_pass_survives_non_finite_inputs(gpu):
+    """A diverged instance (non-finite cost quadratics -> NaN on the diagonal of Quu) must neither fault nor disturb its
+    neighbours: the reference carries non-finite gains on with a warning (ilqr.cpp:290-293). Regression test for the pivot
+    ranking of the LDL^T (a NaN diagonal used to leave the permutation uninitialised -> out-of-bounds shared-memory reads,
+    found with compute-sanitizer at N = 200)."""
+    _, sg, win = _setup_pair(gpu, "walking", batch=2)
+    x0 = np.stack([win[0][0], win[0][0]])
+    ug = grav_comp_guess(standing_state())
+    sg.initialize(x0, None, ug)
+    sg.rollout_nominal(x0); sg.linearize(); sg.cost_quadratics()
+    sg.backward_pass()
+    K_ref, k_ref = sg.get_gains()
+    lx, lu, lxx, luu = sg.get_cost_quadratics()
+    luu[1, 20, 3, 3] = np.nan
+    sg.set_cost_quadratics(lx, lu, lxx, luu)
+    sg.backward_pass()
+    K, k = sg.get_gains()
+    assert (K[0] == K_ref[0]).all() and (k[0] == k_ref[0]).all()          # the healthy instance is bit-identical
+    assert not np.isfinite(K[1]).all()                                     # the poisoned one reports it through its gains
+    # and the long-horizon configuration that exposed it runs through the whole solve
+    w = Config().build_weights()
+    s = gpu.H1IlqrBatch(w, N=200, batch=1)
+    refs = reference_set("walking")
+    s.set_reference_window(*refs.window(0, 200), shared=True)
+    xs = perturbed_states(refs.x_ref_full[0], 1, seed=0)
+    s.upload_inputs(xs, ug)
+    assert s.run_resident_steps(1, True) > 0.0
