@@ -49,7 +49,10 @@ __device__ __forceinline__ double knot_cost_seq(const DynModel& md, const H1Weig
 
 // ---- nominal rollout, one thread per instance (iLQR::forwardRolloutNominal + baseline computeTotalCost);
 //      same contract as k_rollout ----
-constexpr int SEQ_ROLL_THREADS = 32;
+#ifndef H1_SEQ_ROLL_THREADS
+#define H1_SEQ_ROLL_THREADS 32
+#endif
+constexpr int SEQ_ROLL_THREADS = H1_SEQ_ROLL_THREADS;   // (128 measured the same: these kernels are latency bound per warp)
 __global__ void __launch_bounds__(SEQ_ROLL_THREADS)
 k_rollout_seq(const DynModel* gmd, const H1Weights* gw, RefTable refs, int B, int N, int t_begin,
               const int* __restrict__ active, const double* __restrict__ x0, double* __restrict__ xbar,
@@ -107,11 +110,14 @@ k_primal_factor_seq(const DynModel* gmd, int B, int N, const int* __restrict__ a
 // ---- line search, one thread per (instance, alpha candidate); the 8 candidates of an instance sit in 8
 //      adjacent lanes, the first-accept rule is a ballot, the winning trajectory is copied by the whole warp
 //      (iLQR::forwardPassLineSearch, ilqr.cpp:311-361) ----
-constexpr int SEQ_THREADS = 64;
+#ifndef H1_SEQ_THREADS
+#define H1_SEQ_THREADS 128
+#endif
+constexpr int SEQ_THREADS = H1_SEQ_THREADS;
 static_assert(H1ILQR_NALPHA == 8, "candidate groups are 8 lanes wide");
 static_assert(NX % 3 == 0, "feedback loop is unrolled by 3");
 #ifndef H1_SEQ_MINB
-#define H1_SEQ_MINB 4
+#define H1_SEQ_MINB 2
 #endif
 __global__ void __launch_bounds__(SEQ_THREADS, H1_SEQ_MINB)
 k_line_search_seq(const DynModel* gmd, const H1Weights* gw, const H1SolverOptions* gopt, RefTable refs, int B, int N,
@@ -141,13 +147,18 @@ k_line_search_seq(const DynModel* gmd, const H1Weights* gw, const H1SolverOption
   // the thread's current state lives in shared memory (odd per-thread stride: conflict free); every f_D evaluation
   // and cost term reads it from there instead of going back to the global trajectory
   double* xs = reinterpret_cast<double*>(smem + ((sizeof(DynModel) + 15) / 16) * 16) + threadIdx.x * NX;
-  if (act) {
-    const double alpha = gopt->alphas[cand];
-    const RefView r = refs.view(inst);
+  // The 4 warps of a CTA walk the knots in step (a barrier per knot): f_D is ~20 k straight-line instructions, far more
+  // than the instruction cache holds, and warps that sit at the same place of it share every fetched line (line search
+  // 80 -> 77 ms per solve at 8192 instances; a second barrier inside the knot or 256-thread CTAs measured no better). CTAs
+  // of 128 threads also leave whole SMs to the derivative kernels that run beside the second attempts.
+  const double alpha = gopt->alphas[cand];
+  const RefView r = refs.view(instc);
+  if (act)
     for (int i = 0; i < NX; ++i) { const double v = x0 ? x0[(size_t)inst * NX + i] : xb[i]; xs[i] = v; xn[i] = v; }
-    double u[NU], com[3];
+  double u[NU], com[3];
 #pragma unroll 1
-    for (int t = 0; t < N; ++t) {
+  for (int t = 0; t < N; ++t) {
+    if (act) {
       const double* Kt = K + ((size_t)inst * N + t) * NU * NX;
       const double* kt = kff + ((size_t)inst * N + t) * NU;
 #pragma unroll
@@ -164,11 +175,18 @@ k_line_search_seq(const DynModel* gmd, const H1Weights* gw, const H1SolverOption
       }
 #pragma unroll
       for (int i = 0; i < NU; ++i) un[t * NU + i] = u[i];
+    }
+    if (act) {
       double* xnext = xn + (t + 1) * NX;
       dyn_step_seq(*md, xs, u, xnext, nullptr, com);
       total += knot_cost_seq(*md, *gw, r, t, xs, u, com, false);
       for (int i = 0; i < NX; ++i) xs[i] = xnext[i];
     }
+#ifndef H1_SEQ_NOSYNC
+    __syncthreads();
+#endif
+  }
+  if (act) {
     dyn_com_seq(*md, xs, com);
     total += knot_cost_seq(*md, *gw, r, N, xs, nullptr, com, true);
   }
