@@ -172,37 +172,34 @@ k_linearize_finish(const DynModel* __restrict__ md, long nknots, int N, const in
   const double h = md->h;
   double* Ak = A + (size_t)id * NX * NX;
   double* Bk = Bm + (size_t)id * NX * NU;
-  // ---- 1. stage: factor, state, parked tangents (columns 0, 1, 6 and the pad rows are zero). Everything is
-  //      fetched with asynchronous copies issued back to back: one memory latency per knot, not one per element ----
+  // ---- 1. stage with asynchronous copies in two groups: (A) factor + state, needed at once; (B) the parked tangents,
+  //      needed only by the contraction of step 4 — their memory latency hides behind N = L^-1 and Mhat^-1.
+  //      Columns 0, 1, 6 and the pad rows of T are zero ----
   {
     const double* src = reinterpret_cast<const double*>(pf_g + id);
     for (int i = lane; i < (int)(sizeof(PrimalFactor) / sizeof(double)); i += 32) lf_cp_async8(&W.Mi[i], src + i);
     const long inst = id / N;
     const double* xg = xbar + ((size_t)inst * (N + 1) + (id - inst * N)) * NX;
     for (int i = lane; i < NX; i += 32) lf_cp_async8(&W.x[i], xg + i);
-    if (lane < LDF) {   // plain loads in batches of 17 columns: 17 independent requests in flight, then 17 stores
-      const bool rowok = lane < NV;
-#pragma unroll 1
-      for (int c0 = 0; c0 < NX; c0 += 17) {
-        double v[17];
-#pragma unroll
-        for (int i = 0; i < 17; ++i) {
-          const int c = c0 + i;                     // (branch-free: always a valid address, the value is selected)
-          const double ld = __ldg(Ak + c * NX + (rowok ? lane : 0));
-          v[i] = (rowok && c >= 2 && c != 6) ? ld : 0.0;
-        }
-#pragma unroll
-        for (int i = 0; i < 17; ++i) W.T[(c0 + i) * LDF + lane] = v[i];
-      }
+    if (lane < 26) lf_cp_async8(&W.J[lane], Ak + NV + lane);                      // parked by k_linearize_tangents<2>
+    if (lane < 14) lf_cp_async8(lane < 2 ? &W.J[26 + lane] : &W.G[lane - 2], Ak + NX + NV + lane);
+    if (lane < NU) lf_cp_async8(&W.umask[lane], ubar + (size_t)id * NU + lane);   // (turned into the clamp mask below)
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    if (lane < NV) {
+#pragma unroll 4
+      for (int c = 2; c < NX; ++c)
+        if (c != 6) lf_cp_async8(&W.T[c * LDF + lane], Ak + c * NX + lane);
+      W.T[lane] = 0.0; W.T[LDF + lane] = 0.0; W.T[6 * LDF + lane] = 0.0;
+    } else if (lane < LDF) {
+      for (int c = 0; c < NX; ++c) W.T[c * LDF + lane] = 0.0;
     }
-    if (lane < 26) W.J[lane] = __ldg(Ak + NV + lane);                  // parked by k_linearize_tangents<2>
-    if (lane < 14) { const double v = __ldg(Ak + NX + NV + lane); if (lane < 2) W.J[26 + lane] = v; else W.G[lane - 2] = v; }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    for (int i = lane; i < 32 * LDF; i += 32) W.Nm[i] = 0.0;
+    asm volatile("cp.async.wait_group 1;\n" ::: "memory");            // group A has landed
     if (lane < NU) {
-      const double uj = ubar[(size_t)id * NU + lane];
+      const double uj = W.umask[lane];
       W.umask[lane] = (uj < md->ctrl_lo[lane] || uj > md->ctrl_hi[lane]) ? 0.0 : 1.0;   // clamped torque: no sensitivity
     }
-    for (int i = lane; i < 32 * LDF; i += 32) W.Nm[i] = 0.0;
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
   }
   __syncwarp();
   // ---- 2. per-knot small quantities and N = L^-1: lane c owns column c ----
@@ -235,12 +232,6 @@ k_linearize_finish(const DynModel* __restrict__ md, long nknots, int N, const in
     }
   }
   __syncwarp();
-  // the four raw-quaternion tangents = combinations of the three rotation tangents (parked in columns 3..5)
-  if (lane < NV) {
-    const double r0 = W.T[3 * LDF + lane], r1 = W.T[4 * LDF + lane], r2 = W.T[5 * LDF + lane];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) W.T[(3 + i) * LDF + lane] = W.G[3 * i] * r0 + W.G[3 * i + 1] * r1 + W.G[3 * i + 2] * r2;
-  }
   // ---- 3. Mhat^-1 = (N D^-1) N' : tile (mi, nj) only needs k < 8 (min(mi, nj) + 1) (N is lower triangular) ----
 #pragma unroll
   for (int mi = 0; mi < 4; ++mi) {
@@ -264,6 +255,15 @@ k_linearize_finish(const DynModel* __restrict__ md, long nknots, int N, const in
       const int r = 8 * mi + g, c = 8 * nj + 2 * t4;
       if (c < LDF) { W.Mi[r * LDF + c] = acc[nj][0]; W.Mi[r * LDF + c + 1] = acc[nj][1]; }
     }
+  }
+  __syncwarp();
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");              // group B (the tangents) has landed
+  __syncwarp();
+  // the four raw-quaternion tangents = combinations of the three rotation tangents (parked in columns 3..5)
+  if (lane < NV) {
+    const double r0 = W.T[3 * LDF + lane], r1 = W.T[4 * LDF + lane], r2 = W.T[5 * LDF + lane];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) W.T[(3 + i) * LDF + lane] = W.G[3 * i] * r0 + W.G[3 * i + 1] * r1 + W.G[3 * i + 2] * r2;
   }
   __syncwarp();
   // ---- 4. Adot = Mhat^-1 T (25 x 28 x 51 in 4 x 7 tiles), written back over T ----
