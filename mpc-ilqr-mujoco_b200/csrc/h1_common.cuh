@@ -78,6 +78,12 @@ struct CostModel {
   int anc_body[NB][6];
   int chain_end[NB];
   int foot_body[H1_NFOOT];
+  // ordered joint pairs (k <= l, bodies 1..NB-1) of the Hessian contraction tables: the first n_anc_pairs are the pairs
+  // with k an ancestor-or-self of l (59 for H1) — only these have non-zero entries — so a warp computes them with full
+  // lanes instead of scanning all 19 x 19 combinations
+  int n_anc_pairs;
+  unsigned char pair_k[(NB - 1) * NB / 2 + 2], pair_l[(NB - 1) * NB / 2 + 2];
 };
+constexpr int CQ_NPAIRS = (NB - 1) * NB / 2;
 
 }  // namespace h1

@@ -313,11 +313,11 @@ H1_DEV void ph_cq_tables(int lane, const CostModel& cm, CostWarp& w) {
   double RtP[CQ_SETS][3], RtU[CQ_SETS][3];
   for (int s = 0; s < CQ_SETS; ++s) { mtv3(w.R, w.lamP[s], RtP[s]); mtv3(w.R, w.lamU[s], RtU[s]); }
   // (theta_k, theta_l), (theta_k, thdot_l): lane <-> ordered pair index
-  for (int idx = lane; idx < (NB - 1) * (NB - 1); idx += 32) {
-    const int k = idx / (NB - 1) + 1, l = idx % (NB - 1) + 1;
-    if (k > l) continue;
+  // (pairs k <= l from the model's list: the ancestor-or-self pairs come first, the others only store zeros)
+  for (int idx = lane; idx < CQ_NPAIRS; idx += 32) {
+    const int k = cm.pair_k[idx], l = cm.pair_l[idx];
     double jj = 0.0, jv = 0.0;
-    if (cq_is_anc(cm, k, l)) {
+    if (idx < cm.n_anc_pairs) {
       for (int s = 0; s < CQ_SETS; ++s) {
         double rkl[3], t[3], t2[3], acc[3];
         cross3(w.ax[k], w.rj[s][l], rkl);

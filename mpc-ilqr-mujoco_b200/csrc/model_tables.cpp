@@ -115,6 +115,16 @@ bool build_cost_model(const H1Model& m, CostModel* c) {
   }
   tree_common(m, c->parent, c->axis, c->has_rfix, c->depth, c->anc_body, c->chain_end);
   for (int f = 0; f < H1_NFOOT; ++f) c->foot_body[f] = m.foot_body[f];
+  // joint pairs k <= l: ancestor-or-self pairs first
+  int n = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int k = 1; k < NB; ++k)
+      for (int l = k; l < NB; ++l) {
+        const bool anc = c->depth[k] <= c->depth[l] && c->anc_body[l][c->depth[k]] == k;
+        if (anc == (pass == 0)) { c->pair_k[n] = (unsigned char)k; c->pair_l[n] = (unsigned char)l; ++n; }
+      }
+    if (pass == 0) c->n_anc_pairs = n;
+  }
   return true;
 }
 
