@@ -37,6 +37,7 @@ struct CostWarp {
   double gcoef[CQ_ROWS];
   double QQ[4][4], QJ[4][NB], JJ[NB][NB], QV[4][NV], JV[NB][NV];
   double gq[4];                  // upright gradient
+  double hdiag[NX];              // diagonal additions of lxx: Q (or Qf) and the joint-limit penalty curvature
   int outer_a[CQ_MAXOUTER], outer_b[CQ_MAXOUTER];
   double outer_c[CQ_MAXOUTER];
   int n_outer;
@@ -407,32 +408,29 @@ H1_DEV void limit_d(double val, double lo, double hi, double wgt, double* g, dou
   if (val < lo_s) *g += -2.0 * wgt * (lo_s - val);
   if (val > hi_s || val < lo_s) *h += 2.0 * wgt;
 }
-H1_DEV void ph_cq_store(int lane, const DynModel& md, const H1Weights& wt, const CostWarp& w, const double* x,
-                        const double* u, const double* x_ref, const double* u_ref, bool terminal, double* lx,
-                        double* lu, double* lxx, double* luu) {
+// gradient lx and the diagonal additions of lxx (kept in w.hdiag for the assembly: no global loads inside the tile loop)
+H1_DEV void ph_cq_grad(int lane, const DynModel& md, const H1Weights& wt, CostWarp& w, const double* x,
+                       const double* x_ref, bool terminal, double* lx) {
   const double* Qd = terminal ? wt.Qfdiag : wt.Qdiag;
   for (int i = lane; i < NX; i += 32) {
     double g = Qd[i] * (x[i] - x_ref[i]);
+    double hd = Qd[i];
     for (int r = 0; r < CQ_ROWS; ++r)
       if (w.gcoef[r] != 0.0) g += w.gcoef[r] * w.rows[r][i];
     if (i >= 3 && i < 7) g += w.gq[i - 3];
     if (i >= 7 && i < NQ) {
       const double lo = md.jnt_lo[i - 7], hi = md.jnt_hi[i - 7];
-      double hd = 0.0;
       if (isfinite(lo) && isfinite(hi) && lo < hi) limit_d(x[i], lo, hi, wt.w_joint_limits, &g, &hd);
     }
     lx[i] = g;
+    w.hdiag[i] = hd;
   }
+}
+H1_DEV void ph_cq_store(int lane, const DynModel& md, const H1Weights& wt, const CostWarp& w, const double* x,
+                        const double* u, const double* x_ref, const double* u_ref, bool terminal, double* lx,
+                        double* lu, double* lxx, double* luu) {
   const int no = w.n_outer;
-  auto diag_terms = [&](int i, double h) {
-    h += Qd[i];
-    if (i >= 7 && i < NQ) {
-      const double lo = md.jnt_lo[i - 7], hi = md.jnt_hi[i - 7];
-      double gd = 0.0;
-      if (isfinite(lo) && isfinite(hi) && lo < hi) limit_d(x[i], lo, hi, wt.w_joint_limits, &gd, &h);
-    }
-    return h;
-  };
+  auto diag_terms = [&](int i, double h) { return h + w.hdiag[i]; };
 #if defined(__CUDACC__)
   // sum_k c_k rows[a_k] (x) rows[b_k] is the product (rows_a diag(c))' rows_b with the term index k as the
   // contraction dimension: 8 x 8 tiles of the lower triangle on the fp64 tensor core (DMMA m8n8k4), <= 7 k-steps.
@@ -486,17 +484,18 @@ H1_DEV void ph_cq_store(int lane, const DynModel& md, const H1Weights& wt, const
     }
   }
 #endif
-  if (!terminal) {
+  if (!terminal) {   // luu = diag(R + control-limit curvature): zeros first, then the diagonal by its own lanes
     for (int e = lane; e < NU * NU; e += 32) {
       const int i = e % NU, j = e / NU;
-      double h = 0.0;
-      if (i == j) {
-        double g = wt.Rdiag[i] * (u[i] - u_ref[i]);
-        h = wt.Rdiag[i];
-        limit_d(u[i], md.ctrl_lo[i], md.ctrl_hi[i], wt.w_control_limits, &g, &h);
-        lu[i] = g;
-      }
-      luu[e] = h;
+      if (i != j) luu[e] = 0.0;
+    }
+    if (lane < NU) {
+      const int i = lane;
+      double g = wt.Rdiag[i] * (u[i] - u_ref[i]);
+      double h = wt.Rdiag[i];
+      limit_d(u[i], md.ctrl_lo[i], md.ctrl_hi[i], wt.w_control_limits, &g, &h);
+      lu[i] = g;
+      luu[i * NU + i] = h;
     }
   }
 }
@@ -521,6 +520,7 @@ H1_DEV void cost_quadratics_warp(const CostModel& cm, const DynModel& md, const 
   H1_CQ_PHASE(ph_cq_rows(lane, cm, w))
   H1_CQ_PHASE(ph_cq_rows2(lane, w))
   H1_CQ_PHASE(ph_cq_tables(lane, cm, w))
+  H1_CQ_PHASE(ph_cq_grad(lane, md, wt, w, x, x_ref, kt.terminal, lx))
   H1_CQ_PHASE(ph_cq_store(lane, md, wt, w, x, u, x_ref, u_ref, kt.terminal, lx, lu, lxx, luu))
 }
 
