@@ -74,6 +74,20 @@ template <class TK, class TV> H1_DEV void body_wrench_seq(const TK* I, const TV*
   F[3] = Ia[3] + a3[0]; F[4] = Ia[4] + a3[1]; F[5] = Ia[5] + a3[2];
 }
 
+// sin / cos of the hinge of body b: from the per-knot table `sc` (sc[2 (b - 1)], sc[2 (b - 1) + 1]; the batched kernels
+// compute it once per knot for all directions) or evaluated here when sc == nullptr. `seeded_here`: the angle carries the
+// unit tangent of this direction.
+H1_DEV void joint_sincos(const double* __restrict__ x, const double* __restrict__ sc, int b, bool, double* sn, double* cs) {
+  if (sc) { *sn = sc[2 * (b - 1)]; *cs = sc[2 * (b - 1) + 1]; }
+  else sincos_t(x[6 + b], sn, cs);
+}
+H1_DEV void joint_sincos(const double* __restrict__ x, const double* __restrict__ sc, int b, bool seeded_here, Dual* sn, Dual* cs) {
+  double s, c;
+  joint_sincos(x, sc, b, false, &s, &c);
+  const double d = seeded_here ? 1.0 : 0.0;
+  *sn = Dual(s, c * d); *cs = Dual(c, -s * d);
+}
+
 template <class TK, class TV> struct SeqState {
   TK R[9], r[3];
   TV V[6], At[6];   // spatial velocity; total acceleration Va + bias (gravity folded in)
@@ -83,7 +97,7 @@ template <class TK, class TV> struct SeqState {
 // t[j] = -d g_j, for the state x (raw, 51 entries) and the fixed primal acceleration a (25 entries).
 template <class TK, class TV>
 H1_DEV void id_tangent_seq(const DynModel& md, const double* __restrict__ x, const double* __restrict__ a, int seed,
-                           double* __restrict__ t) {
+                           double* __restrict__ t, const double* __restrict__ sc = nullptr) {
   SeqState<TK, TV> cur, saved[SEQ_MAXSAVE];
   TK Sst[6][6];      // motion subspaces of the bodies on the current root->body path, by depth
   TV spst[6];        // S_b . C_{b-1} of the same bodies
@@ -142,7 +156,7 @@ H1_DEV void id_tangent_seq(const DynModel& md, const double* __restrict__ x, con
     TK S[6];
     {
       TK sn, cs;
-      sincos_t(seeded<TK>(x[6 + b], seed == 6 + b, 0.0), &sn, &cs);
+      joint_sincos(x, sc, b, seed == 6 + b, &sn, &cs);
       const int ax = md.axis[b];
       rot_right(cur.R, ax, sn, cs);
       col_of(cur.R, ax, S);
@@ -228,7 +242,7 @@ H1_DEV void id_tangent_seq(const DynModel& md, const double* __restrict__ x, con
 // seed = 6 + bj (angle; TK = Dual) or NQ + 5 + bj (rate; TK = double).
 template <class TK, class TV>
 H1_DEV void id_tangent_sub(const DynModel& md, const double* __restrict__ x, const double* __restrict__ a, int seed,
-                           int bj, double* __restrict__ t) {
+                           int bj, double* __restrict__ t, const double* __restrict__ sc = nullptr) {
   SeqState<TK, TV> cur, saved[SEQ_MAXSAVE];
   TK Sst[6][6];
   TV spst[6];
@@ -284,7 +298,7 @@ H1_DEV void id_tangent_sub(const DynModel& md, const double* __restrict__ x, con
     TK S[6];
     {
       TK sn, cs;
-      sincos_t(seeded<TK>(x[6 + b], seed == 6 + b, 0.0), &sn, &cs);
+      joint_sincos(x, sc, b, seed == 6 + b, &sn, &cs);
       const int ax = md.axis[b];
       rot_right(cur.R, ax, sn, cs);
       col_of(cur.R, ax, S);
@@ -391,7 +405,7 @@ H1_DEV void id_tangent_sub(const DynModel& md, const double* __restrict__ x, con
 template <class TK>
 H1_DEV void contact_tangent_feet(const DynModel& md, const double* __restrict__ x, const double* __restrict__ a,
                                  const TK* R0, const Dual& qz, const Dual* V0, const TK* Vab0,
-                                 double* __restrict__ t, double* __restrict__ Clin) {
+                                 double* __restrict__ t, double* __restrict__ Clin, const double* __restrict__ sc = nullptr) {
   TK Sst[6][6];
   const double h = md.h;
 #pragma unroll 1
@@ -418,7 +432,7 @@ H1_DEV void contact_tangent_feet(const DynModel& md, const double* __restrict__ 
         for (int i = 0; i < 9; ++i) R[i] = Tm[i];
       }
       TK sn, cs, S[6];
-      sincos_t(TK(x[6 + b]), &sn, &cs);
+      joint_sincos(x, sc, b, false, &sn, &cs);
       const int ax = md.axis[b];
       rot_right(R, ax, sn, cs);
       col_of(R, ax, S);
@@ -479,19 +493,19 @@ H1_DEV void base_frame_seq(const double* __restrict__ x, const double* __restric
 
 // t = -dg along z (seed 2) or along the world-frame linear velocity of the base (seed NQ + 0..2): contact only.
 H1_DEV void id_tangent_rigid(const DynModel& md, const double* __restrict__ x, const double* __restrict__ a, int seed,
-                             double* __restrict__ t) {
+                             double* __restrict__ t, const double* __restrict__ sc = nullptr) {
   double R[9], V[6], Vab[6];
   base_frame_seq(x, a, R, V, Vab);
   Dual Vd[6];
   for (int i = 0; i < 6; ++i) Vd[i] = Dual(V[i], (i >= 3 && seed == NQ + i - 3) ? 1.0 : 0.0);
   for (int j = 0; j < NV; ++j) t[j] = 0.0;
-  contact_tangent_feet<double>(md, x, a, R, Dual(x[2], seed == 2 ? 1.0 : 0.0), Vd, Vab, t, nullptr);
+  contact_tangent_feet<double>(md, x, a, R, Dual(x[2], seed == 2 ? 1.0 : 0.0), Vd, Vab, t, nullptr, sc);
   if (seed >= NQ) t[seed - NQ] -= md.damping[seed - NQ];
 }
 
 // rigid-body part of the rotation tangent: t = -[S_j . (H_j x f'; m_j f')] over one plain kinematic walk
 H1_DEV void rot_tangent_rb(const DynModel& md, const double* __restrict__ x, const double* R0, const double* fp,
-                           double* __restrict__ t) {
+                           double* __restrict__ t, const double* __restrict__ sc = nullptr) {
   struct Pose { double R[9], r[3]; } cur, saved[SEQ_MAXSAVE];
   double Sst[6][6], spst[6], C[6];
   for (int i = 0; i < 9; ++i) cur.R[i] = R0[i];
@@ -515,7 +529,7 @@ H1_DEV void rot_tangent_rb(const DynModel& md, const double* __restrict__ x, con
       for (int i = 0; i < 9; ++i) cur.R[i] = Tm[i];
     }
     double sn, cs, S[6];
-    sincos_t(x[6 + b], &sn, &cs);
+    joint_sincos(x, sc, b, false, &sn, &cs);
     const int ax = md.axis[b];
     rot_right(cur.R, ax, sn, cs);
     col_of(cur.R, ax, S);
@@ -555,14 +569,14 @@ H1_DEV void rot_tangent_rb(const DynModel& md, const double* __restrict__ x, con
 
 // t = -dg / d(theta_k): world-frame rotation of the base about e_k (k = 0, 1, 2) at fixed generalized v, a
 H1_DEV void id_tangent_rot(const DynModel& md, const double* __restrict__ x, const double* __restrict__ a, int k,
-                           double* __restrict__ t) {
+                           double* __restrict__ t, const double* __restrict__ sc = nullptr) {
   double R[9], V[6], Vab[6];
   base_frame_seq(x, a, R, V, Vab);
   const double ek[3] = {k == 0 ? 1.0 : 0.0, k == 1 ? 1.0 : 0.0, k == 2 ? 1.0 : 0.0};
   const double f0[3] = {a[0] - md.gravity[0], a[1] - md.gravity[1], a[2] - md.gravity[2]};
   double fp[3];
   cross_m(f0, ek, fp);
-  rot_tangent_rb(md, x, R, fp, t);
+  rot_tangent_rb(md, x, R, fp, t, sc);
   Dual Rd[9], Vd[6], Vabd[6];
   for (int c = 0; c < 3; ++c) {
     const double v[3] = {R[c], R[3 + c], R[6 + c]};
@@ -577,7 +591,7 @@ H1_DEV void id_tangent_rot(const DynModel& md, const double* __restrict__ x, con
     Vabd[3 + i] = Dual(a[i]);
   }
   double Clin[3] = {0.0, 0.0, 0.0};
-  contact_tangent_feet<Dual>(md, x, a, Rd, Dual(x[2]), Vd, Vabd, t, Clin);
+  contact_tangent_feet<Dual>(md, x, a, Rd, Dual(x[2]), Vd, Vabd, t, Clin, sc);
   double crb[3], cx[3];
   for (int i = 0; i < 3; ++i) crb[i] = -(md.armature[i] + md.h * md.damping[i]) * a[i] - md.damping[i] * x[NQ + i] - Clin[i];
   cross_m(ek, crb, cx);

@@ -20,7 +20,8 @@ namespace h1 {
 
 constexpr int LINT_WARPS = 8, LINT_KNOTS = 32, LINT_THREADS = LINT_WARPS * 32;
 __host__ __device__ constexpr int lint_nitems(int cls) { return cls == 0 ? NB - 1 : cls == 1 ? 3 + NB - 1 : 8; }
-constexpr size_t LINT_SMEM_DOUBLES = (size_t)LINT_KNOTS * (NV + NX) + (size_t)LINT_WARPS * LINT_KNOTS * NV;
+constexpr int LINT_SC = 2 * (NB - 1) + 1;   // sin / cos of the 19 hinges per knot (odd stride)
+constexpr size_t LINT_SMEM_DOUBLES = (size_t)LINT_KNOTS * (NV + NX + LINT_SC) + (size_t)LINT_WARPS * LINT_KNOTS * NV;
 
 H1_DEV void quat_rot_map_col(const double* __restrict__ qraw, int i, double* g3) {
   Dual q[4], qn[4], Rd[9];
@@ -66,7 +67,8 @@ k_linearize_tangents(const DynModel* gmd, long nknots, int N, const int* __restr
   if (!any) return;
   double* as = reinterpret_cast<double*>(p);          // [LINT_KNOTS][NV] primal accelerations
   double* xs = as + LINT_KNOTS * NV;                  // [LINT_KNOTS][NX]
-  double* tile = xs + LINT_KNOTS * NX + warp * LINT_KNOTS * NV;   // this warp's [LINT_KNOTS][NV]
+  double* scs = xs + LINT_KNOTS * NX;                // [LINT_KNOTS][LINT_SC] sin / cos of the hinge angles, shared by all directions
+  double* tile = scs + LINT_KNOTS * LINT_SC + warp * LINT_KNOTS * NV;   // this warp's [LINT_KNOTS][NV]
   for (int i = tid; i < nk * NV; i += LINT_THREADS) {
     const int k = i / NV, j = i - k * NV;
     const long id = kid[k];
@@ -80,9 +82,15 @@ k_linearize_tangents(const DynModel* gmd, long nknots, int N, const int* __restr
     xs[i] = xbar[((size_t)inst * (N + 1) + (id - inst * N)) * NX + j];
   }
   __syncthreads();
+  for (int i = tid; i < nk * (NB - 1); i += LINT_THREADS) {
+    const int k = i / (NB - 1), b = i - k * (NB - 1);
+    if (kid[k] >= 0) sincos_t(xs[k * NX + 7 + b], &scs[k * LINT_SC + 2 * b], &scs[k * LINT_SC + 2 * b + 1]);
+  }
+  __syncthreads();
   const bool ok = lane < nk && kid[lane] >= 0;
   const double* x = xs + lane * NX;
   const double* a = as + lane * NV;
+  const double* sc = scs + lane * LINT_SC;
   double* tl = tile + lane * NV;
   while (true) {
     int it = 0;
@@ -110,13 +118,13 @@ k_linearize_tangents(const DynModel* gmd, long nknots, int N, const int* __restr
       double tv[NV];
       if (CLS == 0) {
         col = 6 + md->dir_order[it];                  // hinges by decreasing subtree size
-        id_tangent_sub<Dual, Dual>(*md, x, a, col, col - 6, tv);
+        id_tangent_sub<Dual, Dual>(*md, x, a, col, col - 6, tv, sc);
       } else if (CLS == 1) {
-        if (it < 3) { col = NQ + 3 + it; id_tangent_seq<double, Dual>(*md, x, a, col, tv); }
-        else { col = NQ + 5 + md->dir_order[it - 3]; id_tangent_sub<double, Dual>(*md, x, a, col, col - NQ - 5, tv); }
+        if (it < 3) { col = NQ + 3 + it; id_tangent_seq<double, Dual>(*md, x, a, col, tv, sc); }
+        else { col = NQ + 5 + md->dir_order[it - 3]; id_tangent_sub<double, Dual>(*md, x, a, col, col - NQ - 5, tv, sc); }
       } else {
-        if (it < 3) { col = 3 + it; id_tangent_rot(*md, x, a, it, tv); }
-        else { col = it == 4 ? 2 : NQ + it - 5; id_tangent_rigid(*md, x, a, col, tv); }
+        if (it < 3) { col = 3 + it; id_tangent_rot(*md, x, a, it, tv, sc); }
+        else { col = it == 4 ? 2 : NQ + it - 5; id_tangent_rigid(*md, x, a, col, tv, sc); }
       }
       for (int j = 0; j < NV; ++j) tl[j] = tv[j];
     }
