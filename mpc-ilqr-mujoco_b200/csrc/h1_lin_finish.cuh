@@ -149,16 +149,15 @@ k_linearize_tangents(const DynModel* gmd, long nknots, int N, const int* __restr
 }
 
 // ---- step 2 ----
-constexpr int LINF_WARPS = 4, LINF_THREADS = LINF_WARPS * 32;
+constexpr int LINF_WARPS = 5, LINF_THREADS = LINF_WARPS * 32;   // 22.5 KB of shared memory per warp: two CTAs = 10 warps per SM
 constexpr int LDF = 28;                 // leading dimension of the 25-row operands: = 4 (mod 8) doubles, k padded to 28
 struct LinFinishWarp {
-  double Nm[32 * LDF];                  // L^-1, row-major (rows / columns >= 25 are zero)
-  double Mi[32 * LDF];                  // factor staging (PrimalFactor), then Mhat^-1 row-major
+  double Nm[32 * LDF];                  // L^-1, row-major (rows / columns >= 25 are zero); then Mhat^-1 in place
+  double Fs[sizeof(PrimalFactor) / sizeof(double) + 3];   // factor staging (PrimalFactor)
   double T[NX * LDF];                   // tangents, column c at T[c * LDF]; then Adot in place
   double Dinv[LDF];
   double x[NX + 1], a[NV + 1], J[QJ_DIRS * 4], G[12], umask[NU + 1];
 };
-static_assert(sizeof(PrimalFactor) / sizeof(double) <= 32 * LDF, "factor staging must fit in Mi");
 
 __device__ __forceinline__ void lf_cp_async8(double* smem_dst, const double* gsrc) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -185,7 +184,7 @@ k_linearize_finish(const DynModel* __restrict__ md, long nknots, int N, const in
   //      Columns 0, 1, 6 and the pad rows of T are zero ----
   {
     const double* src = reinterpret_cast<const double*>(pf_g + id);
-    for (int i = lane; i < (int)(sizeof(PrimalFactor) / sizeof(double)); i += 32) lf_cp_async8(&W.Mi[i], src + i);
+    for (int i = lane; i < (int)(sizeof(PrimalFactor) / sizeof(double)); i += 32) lf_cp_async8(&W.Fs[i], src + i);
     const long inst = id / N;
     const double* xg = xbar + ((size_t)inst * (N + 1) + (id - inst * N)) * NX;
     for (int i = lane; i < NX; i += 32) lf_cp_async8(&W.x[i], xg + i);
@@ -212,7 +211,7 @@ k_linearize_finish(const DynModel* __restrict__ md, long nknots, int N, const in
   __syncwarp();
   // ---- 2. per-knot small quantities and N = L^-1: lane c owns column c ----
   {
-    const PrimalFactor* pf = reinterpret_cast<const PrimalFactor*>(W.Mi);
+    const PrimalFactor* pf = reinterpret_cast<const PrimalFactor*>(W.Fs);
     if (lane < LDF) W.Dinv[lane] = lane < NV ? 1.0 / pf->D[lane] : 0.0;
     if (lane < NV) W.a[lane] = pf->a[lane];
     __syncwarp();
@@ -240,29 +239,40 @@ k_linearize_finish(const DynModel* __restrict__ md, long nknots, int N, const in
     }
   }
   __syncwarp();
-  // ---- 3. Mhat^-1 = (N D^-1) N' : tile (mi, nj) only needs k < 8 (min(mi, nj) + 1) (N is lower triangular) ----
+  // ---- 3. Mhat^-1 = (N D^-1) N' : tile (mi, nj) only needs k < 8 (min(mi, nj) + 1) (N is lower triangular). All 16
+  //      tiles are accumulated in registers and then written over N ----
+  {
+    double acc[4][4][2];
 #pragma unroll
-  for (int mi = 0; mi < 4; ++mi) {
-    double acc[4][2];
+    for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-    for (int nj = 0; nj < 4; ++nj) acc[nj][0] = acc[nj][1] = 0.0;
+      for (int nj = 0; nj < 4; ++nj) acc[mi][nj][0] = acc[mi][nj][1] = 0.0;
 #pragma unroll
     for (int ks = 0; ks < 7; ++ks) {
-      if (ks >= 2 * (mi + 1)) continue;
       const int k = 4 * ks + t4;
-      const double aop = W.Nm[(8 * mi + g) * LDF + k] * W.Dinv[k];
+      const double dk = W.Dinv[k];
+      double nop[4];
 #pragma unroll
-      for (int nj = 0; nj < 4; ++nj) {
-        if (ks >= 2 * (nj + 1)) continue;
-        dmma884(acc[nj][0], acc[nj][1], aop, W.Nm[(8 * nj + g) * LDF + k]);
+      for (int q = 0; q < 4; ++q) nop[q] = (ks < 2 * (q + 1)) ? W.Nm[(8 * q + g) * LDF + k] : 0.0;
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        if (ks >= 2 * (mi + 1)) continue;
+        const double aop = nop[mi] * dk;
+#pragma unroll
+        for (int nj = 0; nj < 4; ++nj) {
+          if (ks >= 2 * (nj + 1)) continue;
+          dmma884(acc[mi][nj][0], acc[mi][nj][1], aop, nop[nj]);
+        }
       }
     }
-    __syncwarp();
+    __syncwarp();   // every lane has read N
 #pragma unroll
-    for (int nj = 0; nj < 4; ++nj) {
-      const int r = 8 * mi + g, c = 8 * nj + 2 * t4;
-      if (c < LDF) { W.Mi[r * LDF + c] = acc[nj][0]; W.Mi[r * LDF + c + 1] = acc[nj][1]; }
-    }
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int nj = 0; nj < 4; ++nj) {
+        const int r = 8 * mi + g, c = 8 * nj + 2 * t4;
+        if (c < LDF) { W.Nm[r * LDF + c] = acc[mi][nj][0]; W.Nm[r * LDF + c + 1] = acc[mi][nj][1]; }
+      }
   }
   __syncwarp();
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");              // group B (the tangents) has landed
@@ -286,7 +296,7 @@ k_linearize_finish(const DynModel* __restrict__ md, long nknots, int N, const in
       const int k = 4 * ks + t4;
       double aop[4], bop[7];
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi) aop[mi] = W.Mi[(8 * mi + g) * LDF + k];
+      for (int mi = 0; mi < 4; ++mi) aop[mi] = W.Nm[(8 * mi + g) * LDF + k];
 #pragma unroll
       for (int nj = 0; nj < 7; ++nj) { const int n = 8 * nj + g; bop[nj] = n < NX ? W.T[n * LDF + k] : 0.0; }
 #pragma unroll
@@ -331,7 +341,7 @@ k_linearize_finish(const DynModel* __restrict__ md, long nknots, int N, const in
       double* dst = Bk;
 #pragma unroll 1
       for (int j = 0; j < NU; ++j, dst += NX) {
-        const double* ad = W.Mi + (6 + j) * LDF;                // (Mhat^-1 is symmetric: row = column)
+        const double* ad = W.Nm + (6 + j) * LDF;                // (Mhat^-1 is symmetric: row = column)
         const double sc = h * W.umask[j];
         const double b = sc * ad[j0];
         if (!quat0) dst[r0] = pos0 ? h * b : b;
@@ -342,7 +352,7 @@ k_linearize_finish(const DynModel* __restrict__ md, long nknots, int N, const in
     for (int e = lane; e < (NX + NU) * 4; e += 32) {            // quaternion rows: one (column, row) pair per lane
       const int c = e >> 2, q = e & 3;
       const bool isu = c >= NX;
-      const double* ad = isu ? W.Mi + (6 + c - NX) * LDF : W.T + c * LDF;
+      const double* ad = isu ? W.Nm + (6 + c - NX) * LDF : W.T + c * LDF;
       const double sc = isu ? h * W.umask[c - NX] : h;
       const double w0 = ((c == NQ + 3) ? 1.0 : 0.0) + sc * ad[3], w1 = ((c == NQ + 4) ? 1.0 : 0.0) + sc * ad[4],
                    w2 = ((c == NQ + 5) ? 1.0 : 0.0) + sc * ad[5];
