@@ -97,6 +97,16 @@ __device__ __forceinline__ void mma_tile_split(int m0, int n0, FA fa, FB fb, dou
   for (int q = 0; q < NS; ++q) { c0 += acc[q][0]; c1 += acc[q][1]; }
 }
 
+// 1 / d to within an ulp for a normal d (non-finite d gives a non-finite result, which marks the instance as diverged).
+__device__ __forceinline__ double rcp_newton(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  return fma(r, e, r);
+}
+
 // LDL^T of Quu with symmetric pivoting by largest |diagonal| (Eigen::LDLT's selection rule), ONE warp, right-
 // looking, register resident: lane i holds row i of the permuted matrix (lower triangle), column k of the
 // current Schur complement is exchanged through shared memory. Writes perm, D, Dinv, Ls (unit-lower factor). Returns true when
@@ -132,8 +142,10 @@ __device__ __forceinline__ bool quu_ldlt(RiccatiSmem& s) {
     __syncwarp();
     const double d = colk[k];
     if (!(d > 0.0)) not_pd = true;
-    const double rd = (fabs(d) > 2.2250738585072014e-308) ? 1.0 / d : 0.0;   // one reciprocal per pivot: the division is on
-    if (lane == 0) { s.D[k] = d; s.Dinv[k] = rd; }                          // the critical path of the whole knot
+    // one reciprocal per pivot, on the critical path of the whole knot: hardware seed (rel. error 2^-23) + two Newton
+    // steps = four dependent multiply-adds, without the scaling / special-case code of the generic fp64 division
+    const double rd = (fabs(d) > 2.2250738585072014e-308) ? rcp_newton(d) : 0.0;
+    if (lane == 0) { s.D[k] = d; s.Dinv[k] = rd; }
     const double lik = pik * rd;
 #pragma unroll
     for (int c = 1; c < n; ++c) {
@@ -250,15 +262,48 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
     if (warp < 7) {
       w_strip(std::integral_constant<int, 6>(), 0);
       asm volatile("bar.sync 1, 224;" ::: "memory");   // W complete (the seven contraction warps only)
-      mma_strip_store<9>(13, 8 * warp, 0,
-                         [&](int r, int k) { return s.AB[r * LDX + k]; },   // A'(r,k) = A(k,r); rows 51..55: discarded garbage
-                         [&](int k, int c) { return c < NXU ? s.W[c * LDX + k] : (c == NXU ? s.Vx[k] : 0.0); },
-                         [&](int r, int c, double v) {
-                           if (r >= NX) return;
-                           if (c < NX) s.V[c * LDX + r] = v;
-                           else if (c < NXU) s.Qxu[(c - NX) * LDX + r] = v;
-                           else if (c == NXU) s.Qx[r] = lxt[r] + v;
-                         });
+      // G2 tiles: only the lower triangle of Qxx is ever read again (G5 takes r >= c and mirrors), so of the 7 x 9 tiles
+      // of A' [W | Vx] 48 remain: every warp keeps the column tiles 6..8 of its own row strip (Qxx columns 48..50, Qxu,
+      // Qx) and takes 4 of the 27 other lower tiles — rows w and 6 - w hold 8 of them together, split between the two
+      // warps (warp 6 has 3 and repeats one without storing it). 7 DMMA per k step instead of 9.
+      {
+        const int par = 6 - warp;
+        int tc[7];
+        bool own[7];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { tc[q] = 6 + q; own[q] = true; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (warp <= 3) { own[3 + q] = q <= warp; tc[3 + q] = own[3 + q] ? q : q - warp - 1; }
+          else { own[3 + q] = true; tc[3 + q] = min(warp - 3 + q, 5); }
+        }
+        auto fb = [&](int k, int c) { return c < NXU ? s.W[c * LDX + k] : (c == NXU ? s.Vx[k] : 0.0); };
+        double acc[7][2];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) acc[q][0] = acc[q][1] = 0.0;
+#pragma unroll 1
+        for (int ks = 0; ks < 13; ++ks) {
+          const int k = 4 * ks + t4;
+          const double a1 = s.AB[(8 * warp + g) * LDX + k];   // A'(r,k) = A(k,r); rows 51..55: discarded garbage
+          const double a2 = s.AB[(8 * par + g) * LDX + k];
+#pragma unroll
+          for (int q = 0; q < 7; ++q) dmma884(acc[q][0], acc[q][1], own[q] ? a1 : a2, fb(k, 8 * tc[q] + g));
+        }
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+          if (q == 6 && warp == 6) continue;                   // the repeated tile
+          const int r = 8 * (own[q] ? warp : par) + g;
+          if (r >= NX) continue;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = 8 * tc[q] + 2 * t4 + e;
+            const double v = acc[q][e];
+            if (c < NX) s.V[c * LDX + r] = v;
+            else if (c < NXU) s.Qxu[(c - NX) * LDX + r] = v;
+            else if (c == NXU) s.Qx[r] = lxt[r] + v;
+          }
+        }
+      }
       // s.AB, s.W and s.lq are free once all seven contraction warps are through G2 -> prefetch the next knot's [A|B], lx,
       // lu, luu and this knot's lxx (consumed by the final pass) while warp 7 is still in its sequential section
       asm volatile("bar.sync 1, 224;" ::: "memory");
@@ -274,17 +319,18 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
       // N = L^-1 (unit lower; lane j owns column j, 171 multiply-adds). With N explicit the 52 pairs of triangular solves
       // of the knot become two small tensor-core contractions instead of 36 dependent shuffle / multiply-add steps per
       // right-hand side. (Computing N row by row inside the factorisation loop was measured slower.)
+      // Right-looking substitution: once N(m, j) is final every later row takes its update at once (independent
+      // multiply-adds), so the dependent chain of the whole inverse is 19 operations instead of one dot product per row.
       if (lane < LDU) {
         double x[NU];
 #pragma unroll
-        for (int i = 0; i < NU; ++i) {
-          double v0 = (i == lane) ? 1.0 : 0.0, v1 = 0.0;
+        for (int i = 0; i < NU; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
 #pragma unroll
-          for (int m = 0; m < i; ++m) {
-            if (m & 1) v1 -= s.Ls[m * NU + i] * x[m]; else v0 -= s.Ls[m * NU + i] * x[m];
-          }
-          x[i] = v0 + v1;
-          s.Li[i * LDU + lane] = x[i];
+        for (int m = 0; m < NU; ++m) {
+          const double xm = x[m];
+          s.Li[m * LDU + lane] = xm;
+#pragma unroll
+          for (int i = m + 1; i < NU; ++i) x[i] -= s.Ls[m * NU + i] * xm;
         }
       }
     }
@@ -391,31 +437,47 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
       for (int l = 0; l < NU; ++l) acc += s.Quu[l * LDU + lane] * s.Kt[NX * LDU + l];
       s.tmp[lane] = acc;
     }
+    cp_async_commit_wait_all();   // lxx_t (and the next [A|B]) have landed: G5 adds lxx in its own epilogue
     RP_SYNC(5)
-    // ---- G5: M = Qxx + K' G in place in s.V (warps 0..6) | warp 7: Vx = Qx + K'(Quu k) + K'Qu + Qxu k ----
+    // ---- G5: Vxx = lxx + Qxx + K' G, lower triangle only, mirrored in place into s.V (warps 0..6: 4 of the 28 lower
+    //      tiles each, split like the G2 tiles) | warp 7: Vx = Qx + K'(Quu k) + K'Qu + Qxu k.
+    //      K'G = K'QuuK + 2 K'Qxu' is symmetric up to rounding (K = -S Qxu' with S = P'N'D^-1 N P symmetric by
+    //      construction), so the reference's 0.5 (M + M') differs from the mirrored lower triangle by rounding only ----
     if (warp < 7) {
-      const int m0 = 8 * warp;
-      auto fa = [&](int r, int k) { return s.Kt[r * LDU + k]; };       // K'(r,k) = K(k,r); rows 51..55: kff / zeros, discarded
-      auto fb = [&](int k, int c) { return c < NX ? G[c * LDU + k] : 0.0; };
-      const int r = m0 + g;
-      double acc[7][2];
+      const int par = 6 - warp;
+      int tc[4];
+      bool own[4];
 #pragma unroll
-      for (int j = 0; j < 7; ++j)
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int c = 8 * j + 2 * t4 + q;
-          acc[j][q] = (r < NX && c < NX) ? s.V[c * LDX + r] : 0.0;
-        }
-      mma_strip<7>(5, m0, 0, fa, fb, acc);
-      if (r < NX) {
-#pragma unroll
-        for (int j = 0; j < 7; ++j)
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const int c = 8 * j + 2 * t4 + q;
-            if (c < NX) s.V[c * LDX + r] = acc[j][q];
-          }
+      for (int q = 0; q < 4; ++q) {
+        if (warp <= 3) { own[q] = q <= warp; tc[q] = own[q] ? q : q - warp - 1; }
+        else { own[q] = true; tc[q] = warp - 3 + q; }
       }
+      double acc[4][2];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int r = 8 * (own[q] ? warp : par) + g, c = 8 * tc[q] + 2 * t4 + e;
+          acc[q][e] = (r < NX && c <= r) ? s.V[c * LDX + r] + Lpre[c * NX + r] : 0.0;
+        }
+#pragma unroll
+      for (int ks = 0; ks < 5; ++ks) {
+        const int k = 4 * ks + t4;
+        const double a1 = s.Kt[(8 * warp + g) * LDU + k];     // K'(r,k) = K(k,r); rows 51..55: kff / zeros, discarded
+        const double a2 = s.Kt[(8 * par + g) * LDU + k];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = 8 * tc[q] + g;
+          dmma884(acc[q][0], acc[q][1], own[q] ? a1 : a2, c < NX ? G[c * LDU + k] : 0.0);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int r = 8 * (own[q] ? warp : par) + g, c = 8 * tc[q] + 2 * t4 + e;
+          if (r < NX && c <= r) { s.V[c * LDX + r] = acc[q][e]; s.V[r * LDX + c] = acc[q][e]; }
+        }
     } else {
       for (int i = lane; i < NX; i += 32) {
         double a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -426,18 +488,6 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
         s.Vx[i] = s.Qx[i] + a1 + a2 + a3;
       }
     }
-    cp_async_commit_wait_all();   // lxx_t (and the next [A|B]) have landed
-    RP_SYNC(6)
-    // ---- Vxx = sym(lxx + M), one thread per (i >= j) pair ----
-    for (int e = tid; e < NX * NX; e += nt) {
-      const int j = e / NX, i = e - j * NX;
-      if (i < j) continue;
-      const double mij = s.V[j * LDX + i] + Lpre[j * NX + i];
-      const double mji = s.V[i * LDX + j] + Lpre[i * NX + j];
-      const double v = 0.5 * (mij + mji);
-      s.V[j * LDX + i] = v; s.V[i * LDX + j] = v;
-    }
-    RP_MARK(16)
     // (the __syncthreads at the top of the next iteration orders these writes before G1)
   }
   RP_PRINT
