@@ -162,7 +162,7 @@ __device__ __forceinline__ bool quu_ldlt(RiccatiSmem& s) {
 #define RP_DECL long long rp_t = clock64(); long long rp_acc[20]; for (int q_ = 0; q_ < 20; ++q_) rp_acc[q_] = 0;
 #define RP_MARK(p) { const long long now_ = clock64(); rp_acc[p] += now_ - rp_t; rp_t = now_; }
 #define RP_SYNC(p) { RP_MARK(2 * (p)); __syncthreads(); { unsigned x_; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(x_) : "r"((unsigned)__cvta_generic_to_shared(&s.perm[0])) : "memory"); rp_acc[19] += x_ & 0; } RP_MARK(2 * (p) + 1); }
-#define RP_PRINT if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 7)) printf("ric warp %d work/wait: top %lld/%lld G1b %lld/%lld G3 %lld/%lld P2 %lld/%lld solve %lld/%lld G4 %lld/%lld G5 %lld/%lld sym %lld Linv %lld/%lld\n", warp, rp_acc[0], rp_acc[1], rp_acc[2], rp_acc[3], rp_acc[4], rp_acc[5], rp_acc[6], rp_acc[7], rp_acc[8], rp_acc[9], rp_acc[10], rp_acc[11], rp_acc[12], rp_acc[13], rp_acc[16], rp_acc[14], rp_acc[15]);
+#define RP_PRINT if (blockIdx.x == 0 && lane == 0) printf("ric warp %d work/wait: top %lld/%lld G1b %lld/%lld G3 %lld/%lld P2 %lld/%lld solve %lld/%lld G4 %lld/%lld G5 %lld/%lld sym %lld Linv %lld/%lld\n", warp, rp_acc[0], rp_acc[1], rp_acc[2], rp_acc[3], rp_acc[4], rp_acc[5], rp_acc[6], rp_acc[7], rp_acc[8], rp_acc[9], rp_acc[10], rp_acc[11], rp_acc[12], rp_acc[13], rp_acc[16], rp_acc[14], rp_acc[15]);
 #else
 #define RP_DECL
 #define RP_MARK(p)
@@ -207,6 +207,9 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
   for (int i = tid; i < NX * NX; i += nt) { const int c = i / NX, r = i - c * NX; s.V[c * LDX + r] = lxxN[i]; }
   bool nonfinite = false;
   double* const G = s.W + RIC_G_OFF;
+  // Operand fetches are branch-free: out-of-range rows / columns are redirected to zero pads (a divergent branch around a
+  // fragment load doubled the time of every tile that straddles an edge). zc = the pad column of V, 52 zeros at all times.
+  const double* const zc = &s.V[NX * LDX];
   double* const Lpre = s.W + RIC_LXX_OFF;
   RP_DECL
   for (int t = N - 1; t >= 0; --t) {
@@ -220,8 +223,8 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
     auto w_strip = [&](auto nt_tag, int n0) {
       constexpr int NT = decltype(nt_tag)::value;
       mma_strip_store<NT>(13, 8 * warp, n0,
-                          [&](int r, int k) { return r < LDX ? s.V[k * LDX + r] : 0.0; },
-                          [&](int k, int c) { return c < NXU ? s.AB[c * LDX + k] : 0.0; },
+                          [&](int r, int k) { return s.V[k * LDX + min(r, LDX - 1)]; },          // pad row 51 of V is zero
+                          [&](int k, int c) { return (c < NXU ? s.AB + c * LDX : zc)[k]; },
                           [&](int r, int c, double v) { if (r < LDX && c < NXU) s.W[c * LDX + r] = v; });   // row 51 of W = 0
     };
     if (warp < 7) w_strip(std::integral_constant<int, 3>(), 48);
@@ -230,7 +233,7 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
     //      tile column carries Vx and yields Qu = lu + B'Vx ----
     {
       auto fa = [&](int r, int k) { return s.AB[(NX + min(r, NU - 1)) * LDX + k]; };
-      auto fb = [&](int k, int c) { return c < NU ? s.W[(NX + c) * LDX + k] : (c == NU ? s.Vx[k] : 0.0); };
+      auto fb = [&](int k, int c) { return (c < NU ? s.W + (NX + c) * LDX : (c == NU ? s.Vx : zc))[k]; };
       // one tile per warp: the 6 tiles of the lower triangle (mirrored into the upper one — LLT / LDLT only read one
       // triangle, and B'VxxB is symmetric up to rounding) and the two remaining tiles of the column that carries Qu
       const int mi = warp < 6 ? (warp < 1 ? 0 : (warp < 3 ? 1 : 2)) : warp - 6;
@@ -277,17 +280,22 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
           if (warp <= 3) { own[3 + q] = q <= warp; tc[3 + q] = own[3 + q] ? q : q - warp - 1; }
           else { own[3 + q] = true; tc[3 + q] = min(warp - 3 + q, 5); }
         }
-        auto fb = [&](int k, int c) { return c < NXU ? s.W[c * LDX + k] : (c == NXU ? s.Vx[k] : 0.0); };
+        const double* bp[7];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+          const int c = 8 * tc[q] + g;
+          bp[q] = (c < NXU ? s.W + c * LDX : (c == NXU ? s.Vx : zc)) + t4;
+        }
+        const double* const ap1 = s.AB + (8 * warp + g) * LDX + t4;   // A'(r,k) = A(k,r); rows 51..55: discarded garbage
+        const double* const ap2 = s.AB + (8 * par + g) * LDX + t4;
         double acc[7][2];
 #pragma unroll
         for (int q = 0; q < 7; ++q) acc[q][0] = acc[q][1] = 0.0;
 #pragma unroll 1
         for (int ks = 0; ks < 13; ++ks) {
-          const int k = 4 * ks + t4;
-          const double a1 = s.AB[(8 * warp + g) * LDX + k];   // A'(r,k) = A(k,r); rows 51..55: discarded garbage
-          const double a2 = s.AB[(8 * par + g) * LDX + k];
+          const double a1 = ap1[4 * ks], a2 = ap2[4 * ks];
 #pragma unroll
-          for (int q = 0; q < 7; ++q) dmma884(acc[q][0], acc[q][1], own[q] ? a1 : a2, fb(k, 8 * tc[q] + g));
+          for (int q = 0; q < 7; ++q) dmma884(acc[q][0], acc[q][1], own[q] ? a1 : a2, bp[q][4 * ks]);
         }
 #pragma unroll
         for (int q = 0; q < 7; ++q) {
@@ -340,18 +348,22 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
     //      s.Kt, X = N' Z; no exchange between warps ----
     if (warp < 7) {
       const int n0 = 8 * warp;
+      const int nrhs = n0 + g;                                 // column of R = [Qxu' | Qu] this lane feeds: row pk of it
+      const double* const rsrc = nrhs < NX ? s.Qxu + nrhs : s.Qu;
+      const int rstride = nrhs < NX ? LDX : 1;
       double acc[3][2];
 #pragma unroll
       for (int mi = 0; mi < 3; ++mi) acc[mi][0] = acc[mi][1] = 0.0;
 #pragma unroll
       for (int ks = 0; ks < 5; ++ks) {
-        const int k = 4 * ks + t4, n = n0 + g;
+        const int k = 4 * ks + t4;
         const int pk = s.perm[min(k, NU - 1)];
-        const double b = (k < NU) ? (n < NX ? s.Qxu[pk * LDX + n] : (n == NX ? s.Qu[pk] : 0.0)) : 0.0;
+        const double bv = rsrc[pk * rstride];
+        const double b = (k < NU && nrhs <= NX) ? bv : 0.0;
 #pragma unroll
         for (int mi = 0; mi < 3; ++mi) {
-          const int r = 8 * mi + g;
-          dmma884(acc[mi][0], acc[mi][1], r < LDU ? s.Li[r * LDU + k] : 0.0, b);
+          const int r = min(8 * mi + g, LDU - 1);             // pad row 19 of Li is zero
+          dmma884(acc[mi][0], acc[mi][1], s.Li[r * LDU + k], b);
         }
       }
 #pragma unroll
@@ -372,8 +384,8 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
         const double b = s.Kt[(n0 + g) * LDU + k];
 #pragma unroll
         for (int mi = 0; mi < 3; ++mi) {
-          const int r = 8 * mi + g;
-          dmma884(acc[mi][0], acc[mi][1], r < LDU ? s.Li[k * LDU + r] : 0.0, b);   // N'(r, k) = N(k, r)
+          const int r = min(8 * mi + g, LDU - 1);             // pad column 19 of Li is zero
+          dmma884(acc[mi][0], acc[mi][1], s.Li[k * LDU + r], b);   // N'(r, k) = N(k, r)
         }
       }
       __syncwarp();   // every lane has read Z before its columns are overwritten with the gains
@@ -404,7 +416,7 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
     }
     if (warp < 7) {
       const int n0 = 8 * warp;
-      auto fa = [&](int r, int k) { return r < LDU ? s.Quu[k * LDU + r] : 0.0; };
+      auto fa = [&](int r, int k) { return s.Quu[k * LDU + min(r, LDU - 1)]; };   // pad row 19 of Quu is zero
       auto fb = [&](int k, int c) { return s.Kt[c * LDU + k]; };
       double acc[3][2];
 #pragma unroll
@@ -412,7 +424,8 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int r = 8 * mi + g, c = n0 + 2 * t4 + q;
-          acc[mi][q] = (r < NU && c < NX) ? 2.0 * s.Qxu[r * LDX + c] : 0.0;
+          const double qv = s.Qxu[min(r, NU - 1) * LDX + min(c, NX - 1)];
+          acc[mi][q] = (r < NU && c < NX) ? 2.0 * qv : 0.0;
         }
 #pragma unroll
       for (int ks = 0; ks < 5; ++ks) {       // the three row tiles are independent chains
@@ -458,7 +471,9 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int r = 8 * (own[q] ? warp : par) + g, c = 8 * tc[q] + 2 * t4 + e;
-          acc[q][e] = (r < NX && c <= r) ? s.V[c * LDX + r] + Lpre[c * NX + r] : 0.0;
+          const int rc = min(r, NX - 1), cc = min(c, NX - 1);
+          const double qv = s.V[cc * LDX + rc] + Lpre[cc * NX + rc];
+          acc[q][e] = (r < NX && c <= r) ? qv : 0.0;
         }
 #pragma unroll
       for (int ks = 0; ks < 5; ++ks) {
@@ -468,7 +483,8 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int c = 8 * tc[q] + g;
-          dmma884(acc[q][0], acc[q][1], own[q] ? a1 : a2, c < NX ? G[c * LDU + k] : 0.0);
+          const double gv = G[c * LDU + k];                   // c = 51..55: reads the lxx prefetch behind G, discarded
+          dmma884(acc[q][0], acc[q][1], own[q] ? a1 : a2, c < NX ? gv : 0.0);
         }
       }
 #pragma unroll
@@ -479,14 +495,22 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
           if (r < NX && c <= r) { s.V[c * LDX + r] = acc[q][e]; s.V[r * LDX + c] = acc[q][e]; }
         }
     } else {
-      for (int i = lane; i < NX; i += 32) {
-        double a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        for (int l = 0; l < NU; ++l) {
-          const double kli = s.Kt[i * LDU + l];
-          a1 += kli * s.tmp[l]; a2 += kli * s.Qu[l]; a3 += s.Qxu[l * LDX + i] * s.Kt[NX * LDU + l];
-        }
-        s.Vx[i] = s.Qx[i] + a1 + a2 + a3;
+      // both rows of a lane (i and i + 32) and the even / odd halves of each sum run as 12 independent chains
+      const int i0 = lane, i1 = min(lane + 32, NX - 1);
+      double a[2][3][2];
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+        for (int m = 0; m < 3; ++m) a[h2][m][0] = a[h2][m][1] = 0.0;
+#pragma unroll
+      for (int l = 0; l < NU; ++l) {
+        const double tl = s.tmp[l], ql = s.Qu[l], kl = s.Kt[NX * LDU + l];
+        const double k0 = s.Kt[i0 * LDU + l], k1 = s.Kt[i1 * LDU + l];
+        a[0][0][l & 1] += k0 * tl; a[0][1][l & 1] += k0 * ql; a[0][2][l & 1] += s.Qxu[l * LDX + i0] * kl;
+        a[1][0][l & 1] += k1 * tl; a[1][1][l & 1] += k1 * ql; a[1][2][l & 1] += s.Qxu[l * LDX + i1] * kl;
       }
+      s.Vx[i0] = s.Qx[i0] + (a[0][0][0] + a[0][0][1]) + (a[0][1][0] + a[0][1][1]) + (a[0][2][0] + a[0][2][1]);
+      if (lane + 32 < NX) s.Vx[i1] = s.Qx[i1] + (a[1][0][0] + a[1][0][1]) + (a[1][1][0] + a[1][1][1]) + (a[1][2][0] + a[1][2][1]);
     }
     // (the __syncthreads at the top of the next iteration orders these writes before G1)
   }
