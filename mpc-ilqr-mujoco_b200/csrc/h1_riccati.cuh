@@ -405,20 +405,11 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
           }
         }
       }
-    }
-    RP_SYNC(4)
-    // ---- gains to global | G4: G = Quu K + 2 Qxu' (warps 0..6: one 8-column strip each) | warp 7: tmp = Quu k ----
-    {
-      double* Kt_g = K + ((size_t)inst * N + t) * NU * NX;
-      double* kf_g = kff + ((size_t)inst * N + t) * NU;
-      for (int i = tid; i < NU * NX; i += nt) { const int c = i / NU, r = i - c * NU; Kt_g[i] = s.Kt[c * LDU + r]; }
-      for (int i = tid; i < NU; i += nt) kf_g[i] = s.Kt[NX * LDU + i];
-    }
-    if (warp < 7) {
-      const int n0 = 8 * warp;
+      __syncwarp();
+      // ---- G4: G = Quu K + 2 Qxu', the strip of the SAME 8 columns this warp has just solved for (no barrier between the
+      //      solves and G4); column 51 of the last strip is kff, so its product is Quu k, which the Vx update needs ----
       auto fa = [&](int r, int k) { return s.Quu[k * LDU + min(r, LDU - 1)]; };   // pad row 19 of Quu is zero
       auto fb = [&](int k, int c) { return s.Kt[c * LDU + k]; };
-      double acc[3][2];
 #pragma unroll
       for (int mi = 0; mi < 3; ++mi)
 #pragma unroll
@@ -442,16 +433,19 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
           for (int q = 0; q < 2; ++q) {
             const int c = n0 + 2 * t4 + q;
             if (c < NX) G[c * LDU + r] = acc[mi][q];
+            else if (c == NX && r < NU) s.tmp[r] = acc[mi][q];
           }
         }
       }
-    } else if (lane < NU) {
-      double acc = 0.0;
-      for (int l = 0; l < NU; ++l) acc += s.Quu[l * LDU + lane] * s.Kt[NX * LDU + l];
-      s.tmp[lane] = acc;
     }
     cp_async_commit_wait_all();   // lxx_t (and the next [A|B]) have landed: G5 adds lxx in its own epilogue
-    RP_SYNC(5)
+    RP_SYNC(4)
+    {   // gains to global
+      double* Kt_g = K + ((size_t)inst * N + t) * NU * NX;
+      double* kf_g = kff + ((size_t)inst * N + t) * NU;
+      for (int i = tid; i < NU * NX; i += nt) { const int c = i / NU, r = i - c * NU; Kt_g[i] = s.Kt[c * LDU + r]; }
+      for (int i = tid; i < NU; i += nt) kf_g[i] = s.Kt[NX * LDU + i];
+    }
     // ---- G5: Vxx = lxx + Qxx + K' G, lower triangle only, mirrored in place into s.V (warps 0..6: 4 of the 28 lower
     //      tiles each, split like the G2 tiles) | warp 7: Vx = Qx + K'(Quu k) + K'Qu + Qxu k.
     //      K'G = K'QuuK + 2 K'Qxu' is symmetric up to rounding (K = -S Qxu' with S = P'N'D^-1 N P symmetric by
