@@ -319,7 +319,7 @@ def main():
                          "bound": "tensor", "achieved": bwd_knots * BWD_FLOPS_PER_KNOT / bwd_s / 1e12, "peak": dmma_peak,
                          "unit": "TFLOP/s", "frac": bwd_knots * BWD_FLOPS_PER_KNOT / bwd_s / 1e12 / max(dmma_peak, 1e-9),
                          "traffic": BWD_TRAFFIC_BYTES_PER_KNOT * B * N_HORIZON,
-                         "traffic_note": "ncu --set full dram read+write of one full-batch launch (profiles/r01h_ncu_top_kernels.txt: 61.5 KB per knot, "
+                         "traffic_note": "ncu --set full dram read+write of one full-batch launch (profiles/r01i_ncu_top_kernels.txt: 61.7 KB per knot, "
                                          "algorithmic 60.7 KB), scaled to this batch",
                          "peak_source": "fp64 tensor-core peak measured live in this run (mma.sync m8n8k4 f64 probe kernel); MEASURED_PEAKS.json "
                                         "carries HBM and bf16 figures only, and the bf16 tcgen05 peak does not apply to an fp64 path",
@@ -328,7 +328,7 @@ def main():
                          "hbm": {"achieved": bwd_knots * BWD_ALG_BYTES_PER_KNOT / bwd_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": bwd_knots * BWD_ALG_BYTES_PER_KNOT / bwd_s / 1e9 / hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback"},
-                         "note": "latency bound on the sequential section of a knot (pivoted LDL^T of Quu + 52 triangular solves), see DESIGN.md"},
+                         "note": "achieved = ALGORITHMIC flops (SURVEY 8(d), no symmetry credit) / time; the kernel executes 2028 DMMA = 1.04 MFLOP per knot (lower triangles of Qxx / Vxx only), DMMA pipe 57 % active in the r01i capture; bound by the sequential section of a knot (pivoted LDL^T of Quu) beside the A-block contractions and by two resident instances per SM, see DESIGN.md"},
             # second stage: analytic linearization = 3 tangent kernels (FMA pipe) + k_linearize_finish (DMMA)
             "roofline_linearize": {"kernel": "k_linearize_tangents<0|1|2> + k_linearize_finish",
                                    "bound": "fp64", "achieved_tflops": knots * LIN_FLOPS_PER_KNOT / lin_s / 1e12, "peak_tflops": fp64_peak,
@@ -348,18 +348,18 @@ def main():
         dist.destroy_process_group()
 
 
-# ---- per-knot work figures (ncu numbers from profiles/r01h_ncu_top_kernels.txt, 4096 x 25 knots) ----
+# ---- per-knot work figures (ncu numbers from profiles/r01i_ncu_top_kernels.txt, 4096 x 25 knots) ----
 # Riccati backward pass: algorithmic flops of one knot (the five contractions with shared products, the
 # factorisation and the solves) and its algorithmic bytes (A, B, lx, lu, lxx, luu read; K, kff written).
 BWD_FLOPS_PER_KNOT = 1.153e6
 BWD_ALG_BYTES_PER_KNOT = 52816.0 + 7904.0
-BWD_TRAFFIC_BYTES_PER_KNOT = (5.499e9 + 0.800e9) / (4096 * 25)      # dram__bytes_read.sum + dram__bytes_write.sum of one launch
+BWD_TRAFFIC_BYTES_PER_KNOT = (5.500e9 + 0.817e9) / (4096 * 25)      # dram__bytes_read.sum + dram__bytes_write.sum of one launch
 # Linearization: fp64 operations EXECUTED per knot (2 per DFMA, 1 per DADD / DMUL from the smsp__sass_thread_inst_executed_op_*
-# counters: tangent kernels 10.48 + 10.50 + 4.10 GFLOP, finish 2.51 GFLOP, plus 255 DMMA m8n8k4 = 130.6 kflop per knot in finish)
-LIN_FLOPS_PER_KNOT = (10.48e9 + 10.50e9 + 4.10e9 + 2.51e9) / (4096 * 25) + 255 * 512.0
+# counters: tangent kernels 10.22 + 10.03 + 3.71 GFLOP, finish 2.52 GFLOP, plus 255 DMMA m8n8k4 = 130.6 kflop per knot in finish)
+LIN_FLOPS_PER_KNOT = (10.22e9 + 10.03e9 + 3.71e9 + 2.52e9) / (4096 * 25) + 255 * 512.0
 # algorithmic bytes: A_k, B_k written; x_k, u_k and the factor (L, D, a) read; the parked tangents written and read once
 LIN_ALG_BYTES_PER_KNOT = (51 * 51 + 51 * 19 + 51 + 19) * 8.0 + (25 * 11 + 25 + 25) * 8.0 + 2 * 48 * 25 * 8.0
-LIN_TRAFFIC_BYTES_PER_KNOT = (0.168e9 + 1.140e9 + 0.180e9 + 0.780e9 + 0.116e9 + 0.317e9 + 2.014e9 + 2.869e9) / (4096 * 25)
+LIN_TRAFFIC_BYTES_PER_KNOT = (0.171e9 + 1.201e9 + 0.181e9 + 0.809e9 + 0.117e9 + 0.299e9 + 1.954e9 + 2.870e9) / (4096 * 25)
 
 if __name__ == "__main__":
     main()
