@@ -48,37 +48,11 @@ def parse():
 
 
 def workload(batch, rank, kinematics):
-    """Instances [rank*batch, (rank+1)*batch) of the sharded walking workload (deterministic, seed 0)."""
-    from mpc_ilqr_mujoco_b200.references import ReferenceSet
-    d = np.load(os.path.join(ROOT, "data", "h1_refs.npz"))
-    refs = ReferenceSet(d["walking_q"], d["walking_v"], d["walking_contact"], kinematics)
-    ids = np.arange(rank * batch, (rank + 1) * batch)
-    t0 = ids % (refs.T - (N_HORIZON + 1))
-    wins = [refs.window(int(t), N_HORIZON) for t in np.unique(t0)]
-    lut = {int(t): w for t, w in zip(np.unique(t0), wins)}
-    stack = lambda k: np.ascontiguousarray(np.stack([lut[int(t)][k] for t in t0]))
-    win = tuple(stack(k) for k in range(6))
-    x_nom = refs.x_ref_full[t0]
-    x0 = np.vstack([_perturb_one(x_nom[j], int(i)) for j, i in enumerate(ids)])  # keyed by the GLOBAL instance id
+    """Instances [rank*batch, (rank+1)*batch) of the sharded walking workload (deterministic, seed 0): exactly the
+    instances tests/test_gpu_workloads.py::test_bench_workload_parity checks against the oracle."""
+    from mpc_ilqr_mujoco_b200 import workloads as wl
+    win, x0, _ = wl.walking_instances(np.arange(rank * batch, (rank + 1) * batch), kinematics, N=N_HORIZON)
     return win, x0
-
-
-def _perturb_one(x_nom, gid):
-    from mpc_ilqr_mujoco_b200.references import NQ, NV
-    rng = np.random.Generator(np.random.Philox(key=0, counter=[gid, 0, 0, 0]))
-    x = np.array(x_nom, dtype=np.float64)
-    x[0:3] += rng.uniform(-0.02, 0.02, 3)
-    rv = rng.uniform(-0.05, 0.05, 3)
-    ang = np.linalg.norm(rv)
-    dq = np.array([np.cos(ang / 2), *(np.sin(ang / 2) / ang * rv)])
-    w0, x0, y0, z0 = x[3:7] / np.linalg.norm(x[3:7])
-    w1, x1, y1, z1 = dq
-    qn = np.array([w0 * w1 - x0 * x1 - y0 * y1 - z0 * z1, w0 * x1 + x0 * w1 + y0 * z1 - z0 * y1,
-                   w0 * y1 - x0 * z1 + y0 * w1 + z0 * x1, w0 * z1 + x0 * y1 - y0 * x1 + z0 * w1])
-    x[3:7] = qn / np.linalg.norm(qn)
-    x[7:NQ] += rng.uniform(-0.05, 0.05, NQ - 7)
-    x[NQ:] += rng.uniform(-0.1, 0.1, NV)
-    return x
 
 
 class ClockSampler(threading.Thread):

@@ -110,10 +110,14 @@ int h1ilqr_solve(H1Ilqr* h, const double* x0, double* cost_out, int* iters_out, 
 
 /* MPC step for all instances: initialize (warm where a previous solution exists) + solve +
  * u_apply = ubar[0] + K[0](x_measured - xbar[0]) + store previous solution.
- * Replaces MPC::stepOnce (src/ilqr/mpc.cpp:40-127). u_apply [batch][19]. */
+ * Replaces MPC::stepOnce (src/ilqr/mpc.cpp:40-127). u_apply [batch][19]. Returns H1ILQR_ENOTFINITE (with u_apply /
+ * cost_out filled in) when an instance produced a non-finite cost or gains; h1ilqr_get_status tells which. */
 int h1ilqr_mpc_step(H1Ilqr* h, const double* x_measured, const double* u_init, int u_init_shared,
                     double* u_apply, double* cost_out);
 int h1ilqr_mpc_reset(H1Ilqr* h);
+/* Per-instance status (0 ok, 1 non-finite cost / gains) and iteration count of the last solve / MPC step.
+ * h1ilqr_mpc_step and h1ilqr_solve return H1ILQR_ENOTFINITE (outputs still delivered) when any status is 1. */
+int h1ilqr_get_status(H1Ilqr* h, int* status_out, int* iters_out);
 
 /* Kernel families. The path has two sm_100a implementations of its per-knot / per-rollout stages with identical
  * semantics (both are parity-tested against the oracle): COOPERATIVE = one warp per unit (lowest latency, used for
@@ -146,6 +150,10 @@ int h1ilqr_bias_forces(H1Ilqr* h, int n, const double* x, double* bias);
 /* Dynamics-model FK used to precompute references: CoM (subtree_com of the root) and ankle body
  * positions, RobotUtils::loadReferences (robot_utils.cpp:370-403). com [n][3], ee [n][2][3]. */
 int h1ilqr_reference_kinematics(H1Ilqr* h, int n, const double* x, double* com, double* ee);
+/* Whole-body CoM velocity (world frame) of arbitrary states on the dynamics model: the per-row CoM-velocity target
+ * J_subtreeCom(root) * qvel of RobotUtils::loadReferences (robot_utils.cpp:388-397), tracked by
+ * addCoMVelCostDerivatives when W_com_vel > 0 (ilqr.cpp:675-695). com_vel [n][3]. */
+int h1ilqr_reference_com_velocity(H1Ilqr* h, int n, const double* x, double* com_vel);
 /* World positions of the 2 x 4 sole contact points of f_D for arbitrary states, pts [n][8][3] (left foot first).
  * Input of the contact-schedule generation that replaces get_contacts.py:96-157 (MuJoCo foot-geom contacts with
  * dist < 1e-3): a foot is in stance when one of its sole points is lower than the threshold. */

@@ -34,7 +34,8 @@ __global__ void k_dyn_step(const DynModel* gmd, int n, const double* __restrict_
 // ---- bias forces, dynamics-model CoM, ankle positions and sole contact points of arbitrary states
 //      (computeGravComp, loadReferences' per-row FK, contact-schedule generation) ----
 __global__ void k_dyn_query(const DynModel* gmd, int n, const double* __restrict__ x, double* __restrict__ bias,
-                            double* __restrict__ com, double* __restrict__ ee, double* __restrict__ sole) {
+                            double* __restrict__ com, double* __restrict__ ee, double* __restrict__ sole,
+                            double* __restrict__ comvel) {
   extern __shared__ __align__(16) unsigned char smem[];
   const DynModel* md;
   unsigned char* p = stage_model(smem, gmd, &md);
@@ -48,6 +49,28 @@ __global__ void k_dyn_query(const DynModel* gmd, int n, const double* __restrict
   if (ee && lane < 6) ee[(size_t)i * 6 + lane] = w.q[lane % 3] + w.footr[lane / 3][lane % 3];
   if (sole && lane < NCPT)
     for (int c = 0; c < 3; ++c) sole[((size_t)i * NCPT + lane) * 3 + c] = w.q[c] + w.cp[lane][c];
+  if (comvel) {
+    // whole-body CoM velocity (world frame) = total linear momentum / total mass: the value of
+    // mj_jacSubtreeCom(root) * qvel in RobotUtils::loadReferences (robot_utils.cpp:388-397). Lane b: spatial velocity
+    // of body b about the base origin = sum of S_k v_k over its ancestor dofs, momentum l = m v_O - h x omega.
+    double p[3] = {0.0, 0.0, 0.0}, m = 0.0;
+    if (lane < NB) {
+      const int j = 5 + lane, ns = md->nlist[j];
+      double V[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      for (int s = 0; s < ns; ++s) {
+        const int k = md->alist[j][s];
+        for (int c = 0; c < 6; ++c) V[c] += w.S[k][c] * w.v[k];
+      }
+      const double* I = &w.body[lane][6];
+      m = I[0];
+      double hw[3];
+      cross3(I + 1, V, hw);
+      for (int c = 0; c < 3; ++c) p[c] = m * V[3 + c] - hw[c];
+    }
+    m = warp_sum(m);
+    for (int c = 0; c < 3; ++c) p[c] = warp_sum(p[c]);
+    if (lane < 3) comvel[(size_t)i * 3 + lane] = p[lane] / m;
+  }
 }
 
 // ---- nominal rollout xbar[t+1] = f_D(xbar[t], ubar[t]) with the trajectory cost as a by-product

@@ -150,6 +150,7 @@ __device__ __forceinline__ bool solve_state_accept(const SolveState& st, const H
   const double cur = st.ls_cost[i];
   st.iters[i] = it + 1;
   st.cost[i] = cur;
+  st.nominal_cost[i] = cur;   // baseline of the next line search = cost of the trajectory this accept installed
   st.lambda[i] = fmax(st.lambda[i] / 2.0, o.reg_min);
   st.cost_trace[(size_t)i * maxit + it] = cur;
   bool on = true;
@@ -173,7 +174,11 @@ __global__ void k_solve_state(SolveState st, const H1SolverOptions* gopt, int B,
     st.second[i] = 0;
     if (st.active[i]) {
       st.prev_cost[i] = st.cost[i];
-      if (it > 0) st.nominal_cost[i] = st.cost[i];   // baseline of the line search: cost of the unchanged trajectory
+      // The baseline of the line search (ilqr.cpp:318: computeTotalCost of the re-rolled-out trajectory) lives in
+      // nominal_cost: the iteration-0 rollout from x0 writes it and every accepted candidate replaces it
+      // (solve_state_accept). It is NOT cost[i] while no candidate has been accepted: cost[i] is then still the
+      // cost of the initial guess BEFORE the rollout, which differs for a warm start whose measured state left
+      // the predicted one (the shifted trajectory is not dynamics-consistent).
       st.act_list[atomicAdd(&st.list_count[0], 1)] = i;   // (the counter is zeroed before the phase-0 launch)
     }
     return;

@@ -639,6 +639,7 @@ int h1ilqr_mpc_step(H1Ilqr* h, const double* x_measured, const double* u_init, i
   // pinned staging: x in, u_apply + cost out
   double* pin_x = (double*)h->pin; double* pin_u = pin_x + B * NX; double* pin_c = pin_u + B * NU;
   double* pin_ui = pin_c + B;
+  int* pin_st = reinterpret_cast<int*>(pin_ui + B * NU);
   std::memcpy(pin_x, x_measured, B * NX * sizeof(double));
   H2D(h->x0, pin_x, B * NX * sizeof(double));
   if (u_init) {
@@ -653,11 +654,25 @@ int h1ilqr_mpc_step(H1Ilqr* h, const double* x_measured, const double* u_init, i
   enqueue_mpc_tail(h);
   D2H(pin_u, h->u_apply, B * NU * sizeof(double));
   D2H(pin_c, h->cost, B * sizeof(double));
+  D2H(pin_st, h->status, B * sizeof(int));
   SYNC();
   CU(cudaGetLastError());
   h->times.launches = h->launches - l0;
   std::memcpy(u_apply, pin_u, B * NU * sizeof(double));
   if (cost_out) std::memcpy(cost_out, pin_c, B * sizeof(double));
+  // same convention as h1ilqr_solve: the outputs are delivered, the return code says whether an instance went non-finite
+  // (the reference carries non-finite gains on with a warning, ilqr.cpp:290-293; a batched caller must not miss it)
+  int bad = 0;
+  for (size_t i = 0; i < B; ++i) bad |= pin_st[i];
+  if (bad) return set_err(H1ILQR_ENOTFINITE, "non-finite cost or gains in at least one instance (h1ilqr_get_status)");
+  return 0;
+}
+
+int h1ilqr_get_status(H1Ilqr* h, int* status_out, int* iters_out) {
+  GUARD(h);
+  if (status_out) D2H(status_out, h->status, (size_t)h->B * sizeof(int));
+  if (iters_out) D2H(iters_out, h->iters, (size_t)h->B * sizeof(int));
+  SYNC();
   return 0;
 }
 
@@ -717,16 +732,18 @@ int h1ilqr_dynamics_step(H1Ilqr* h, int n, const double* x, const double* u, dou
   return 0;
 }
 
-static int query(H1Ilqr* h, int n, const double* x, double* bias, double* com, double* ee, double* sole = nullptr) {
+static int query(H1Ilqr* h, int n, const double* x, double* bias, double* com, double* ee, double* sole = nullptr,
+                 double* comvel = nullptr) {
   if (n < 1 || !x) return set_err(H1ILQR_EARG, "bad query arguments");
-  int rc = ensure_scratch(h, (size_t)n * (NX + NV + 9 + 3 * NCPT) * sizeof(double));
+  int rc = ensure_scratch(h, (size_t)n * (NX + NV + 12 + 3 * NCPT) * sizeof(double));
   if (rc) return rc;
   double* dx = h->scratch; double* db = dx + (size_t)n * NX; double* dc = db + (size_t)n * NV; double* de = dc + (size_t)n * 3;
-  double* ds = de + (size_t)n * 6;
+  double* ds = de + (size_t)n * 6; double* dv = ds + (size_t)n * 3 * NCPT;
   H2D(dx, x, (size_t)n * NX * sizeof(double));
   k_dyn_query<<<(n + 3) / 4, 128, h->smem_dyn4, h->stream>>>(h->d_dyn, n, dx, bias ? db : nullptr, com ? dc : nullptr,
-                                                            ee ? de : nullptr, sole ? ds : nullptr);
+                                                            ee ? de : nullptr, sole ? ds : nullptr, comvel ? dv : nullptr);
   LAUNCHED();
+  if (comvel) D2H(comvel, dv, (size_t)n * 3 * sizeof(double));
   if (bias) D2H(bias, db, (size_t)n * NV * sizeof(double));
   if (com) D2H(com, dc, (size_t)n * 3 * sizeof(double));
   if (ee) D2H(ee, de, (size_t)n * 6 * sizeof(double));
@@ -736,6 +753,11 @@ static int query(H1Ilqr* h, int n, const double* x, double* bias, double* com, d
 }
 int h1ilqr_bias_forces(H1Ilqr* h, int n, const double* x, double* bias) { GUARD(h); return query(h, n, x, bias, nullptr, nullptr); }
 int h1ilqr_reference_kinematics(H1Ilqr* h, int n, const double* x, double* com, double* ee) { GUARD(h); return query(h, n, x, nullptr, com, ee); }
+int h1ilqr_reference_com_velocity(H1Ilqr* h, int n, const double* x, double* com_vel) {
+  GUARD(h);
+  if (!com_vel) return set_err(H1ILQR_EARG, "null com_vel");
+  return query(h, n, x, nullptr, nullptr, nullptr, nullptr, com_vel);
+}
 int h1ilqr_sole_points(H1Ilqr* h, int n, const double* x, double* pts) {
   GUARD(h);
   if (!pts) return set_err(H1ILQR_EARG, "null pts");

@@ -20,7 +20,7 @@ EXPORTS = [
     "h1ilqr_horizon", "h1ilqr_set_weights", "h1ilqr_set_reference_window", "h1ilqr_initialize", "h1ilqr_solve",
     "h1ilqr_mpc_step", "h1ilqr_mpc_reset", "h1ilqr_rollout_nominal", "h1ilqr_linearize", "h1ilqr_cost_quadratics",
     "h1ilqr_backward_pass", "h1ilqr_line_search", "h1ilqr_total_cost", "h1ilqr_dynamics_step", "h1ilqr_bias_forces",
-    "h1ilqr_reference_kinematics", "h1ilqr_sole_points", "h1ilqr_set_trajectory", "h1ilqr_get_trajectory", "h1ilqr_get_gains",
+    "h1ilqr_reference_kinematics", "h1ilqr_reference_com_velocity", "h1ilqr_get_status", "h1ilqr_sole_points", "h1ilqr_set_trajectory", "h1ilqr_get_trajectory", "h1ilqr_get_gains",
     "h1ilqr_set_gains", "h1ilqr_get_linearization", "h1ilqr_set_linearization", "h1ilqr_get_cost_quadratics",
     "h1ilqr_set_cost_quadratics", "h1ilqr_get_regularization", "h1ilqr_set_regularization", "h1ilqr_get_solve_trace",
     "h1ilqr_upload_inputs", "h1ilqr_host_register", "h1ilqr_host_unregister", "h1ilqr_run_resident_steps", "h1ilqr_measure_fp64_peak", "h1ilqr_measure_fp64_mma_peak", "h1ilqr_enable_stage_timing", "h1ilqr_set_kernel_policy", "h1ilqr_get_stage_times", "h1ilqr_stream", "h1_default_dynamics_model",
@@ -163,8 +163,18 @@ class H1IlqrBatch:
             shared = int(u_init.size == NU)
         ua = np.empty((self.B, NU))
         cost = np.empty(self.B)
-        _check(lib().h1ilqr_mpc_step(self._h, dptr(x), dptr(u_init), C.c_int(shared), dptr(ua), dptr(cost)))
+        rc = lib().h1ilqr_mpc_step(self._h, dptr(x), dptr(u_init), C.c_int(shared), dptr(ua), dptr(cost))
+        self.last_rc = rc
+        if rc not in (0, -3):   # -3 = H1ILQR_ENOTFINITE: outputs are delivered, get_status() tells which instance
+            _check(rc)
         return ua, cost
+
+    def get_status(self):
+        """(status[B] (0 ok, 1 non-finite cost / gains), iters[B]) of the last solve / MPC step."""
+        st = np.empty(self.B, dtype=np.int32)
+        it = np.empty(self.B, dtype=np.int32)
+        _check(lib().h1ilqr_get_status(self._h, iptr(st), iptr(it)))
+        return st, it
 
     def mpc_reset(self):
         _check(lib().h1ilqr_mpc_reset(self._h))
@@ -213,6 +223,13 @@ class H1IlqrBatch:
         ee = np.empty((x.shape[0], 2, 3))
         _check(lib().h1ilqr_reference_kinematics(self._h, C.c_int(x.shape[0]), dptr(x), dptr(com), dptr(ee)))
         return com, ee
+
+    def reference_com_velocity(self, x):
+        """Whole-body CoM velocity [n][3] (world frame) on the dynamics model (robot_utils.cpp:388-397)."""
+        x = _f(x).reshape(-1, NX)
+        cv = np.empty((x.shape[0], 3))
+        _check(lib().h1ilqr_reference_com_velocity(self._h, C.c_int(x.shape[0]), dptr(x), dptr(cv)))
+        return cv
 
     def sole_points(self, x):
         """World positions [n][8][3] of the sole contact points (left foot's four first)."""
@@ -301,10 +318,6 @@ class H1IlqrBatch:
         t = C.c_double()
         _check(lib().h1ilqr_measure_fp64_mma_peak(self._h, C.byref(t)))
         return t.value
-
-    def get_costs(self):
-        """Final cost / iterations / status of the last solve (device -> host)."""
-        return self.solve_trace()
 
     def set_kernel_policy(self, policy):
         """KERNELS_AUTO (0), KERNELS_COOPERATIVE (1: warp per unit, latency) or KERNELS_BATCHED (2: thread per unit)."""

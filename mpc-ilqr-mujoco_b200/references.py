@@ -74,14 +74,25 @@ def write_contact_csv(path, contact):
 class ReferenceSet:
     """x_ref_full / com_ref_full / ee_pos_ref_full / contact schedule of one reference motion."""
 
-    def __init__(self, q, v, contact, kinematics):
+    def __init__(self, q, v, contact, kinematics, com_velocity=None):
         """`kinematics(x[n,51]) -> (com[n,3], ee[n,2,3])` on the dynamics model; the product passes
-        H1IlqrBatch.reference_kinematics (GPU), the tests may pass the oracle's."""
+        H1IlqrBatch.reference_kinematics (GPU), the tests may pass the oracle's. `com_velocity(x[n,51]) -> [n,3]`
+        is the per-row CoM-velocity target J_subtreeCom * qvel of loadReferences (robot_utils.cpp:388-397;
+        H1IlqrBatch.reference_com_velocity on the GPU). It is only tracked when W_com_vel > 0 (0 as shipped); without
+        the callable the targets are zero and `require_com_velocity` refuses a positive weight."""
         self.x_ref_full = np.ascontiguousarray(np.hstack([q, v]))
         self.T = self.x_ref_full.shape[0]
         self.com_ref_full, self.ee_pos_ref_full = kinematics(self.x_ref_full)
         self.contact = np.asarray(contact, dtype=np.int32)
-        self.com_vel_ref_full = np.zeros((self.T, 3))
+        self.has_com_velocity = com_velocity is not None
+        self.com_vel_ref_full = (np.ascontiguousarray(com_velocity(self.x_ref_full)) if com_velocity is not None
+                                 else np.zeros((self.T, 3)))
+
+    def require_com_velocity(self, weights):
+        """Raise instead of silently tracking a zero CoM velocity when the weight is positive."""
+        if weights.w_com_vel > 0.0 and not self.has_com_velocity:
+            raise RuntimeError("W_com_vel > 0 needs the CoM-velocity targets: build the ReferenceSet with "
+                               "com_velocity=H1IlqrBatch.reference_com_velocity")
 
     def is_stance(self, ee, t):
         if t < 0 or t >= self.contact.shape[0] or ee < 0 or ee >= self.contact.shape[1]:

@@ -13,6 +13,7 @@ void normalize_quat(const double* q, double* qn);
 void dyn_fk(const H1Model& md, const double* q, double (*R)[9], double (*r)[3]);
 void dyn_com(const H1Model& md, const double* x, double* com);
 void dyn_body_pos(const H1Model& md, const double* x, int body, double* p);
+void dyn_com_vel(const H1Model& md, const double* x, double* com_vel);
 void dyn_bias(const H1Model& md, const double* x, double* bias);
 void dyn_step(const H1Model& md, const double* x, const double* u, double* xn);
 void dyn_linearize_fd(const H1Model& md, const double* x, const double* u, double eps, double* A, double* B);
@@ -53,6 +54,12 @@ struct Solver {
   std::vector<double> xbar, ubar, K, kff, A, B, lx, lu, lxx, luu;
   std::vector<double> cost_trace;
   std::vector<int> alpha_trace;  // [iter][2]: alpha index of first / second line search (-1 none, -2 not run)
+  // decision margins of the last solve, in cost units (test diagnostics: how far every accept / reject / stop
+  // decision was from flipping). ls_margin [iter][2]: min over the candidates evaluated by that line search of
+  // |c - (baseline - accept_margin)| (-1 = not run); stop_margin [iter]: distance of the iteration's stop tests
+  // (|cur - prev| vs tolerance, cur vs divergence_cost) from flipping (-1 = not evaluated).
+  std::vector<double> ls_margin, stop_margin;
+  double last_ls_margin = -1.0;
   int iters = 0;
   // MPC state
   bool has_prev = false;

@@ -40,6 +40,7 @@ void orc_dyn_linearize_ad(const H1Model* m, const double* x, const double* u, do
   dyn_linearize_ad(*pick(m, H1_DYNAMICS_MODEL), x, u, A, B);
 }
 void orc_dyn_com(const H1Model* m, const double* x, double* com) { dyn_com(*pick(m, H1_DYNAMICS_MODEL), x, com); }
+void orc_dyn_com_vel(const H1Model* m, const double* x, double* cv) { dyn_com_vel(*pick(m, H1_DYNAMICS_MODEL), x, cv); }
 void orc_dyn_bias(const H1Model* m, const double* x, double* bias) { dyn_bias(*pick(m, H1_DYNAMICS_MODEL), x, bias); }
 void orc_dyn_body_pos(const H1Model* m, const double* x, int body, double* p) {
   dyn_body_pos(*pick(m, H1_DYNAMICS_MODEL), x, body, p);
@@ -116,6 +117,13 @@ void orc_get_trace(void* hv, int i, double* cost_trace, int* alpha_trace) {
   Solver& s = S(hv, i);
   std::memcpy(cost_trace, s.cost_trace.data(), sizeof(double) * s.cost_trace.size());
   std::memcpy(alpha_trace, s.alpha_trace.data(), sizeof(int) * s.alpha_trace.size());
+}
+
+// decision margins of the last solve (test diagnostics): ls_margin [max_iterations][2], stop_margin [max_iterations]
+void orc_get_margins(void* hv, int i, double* ls_margin, double* stop_margin) {
+  Solver& s = S(hv, i);
+  std::memcpy(ls_margin, s.ls_margin.data(), sizeof(double) * s.ls_margin.size());
+  std::memcpy(stop_margin, s.stop_margin.data(), sizeof(double) * s.stop_margin.size());
 }
 
 // CPU baseline legs: every instance does one MPC step (initialize with u_init or warm start + solve) from its

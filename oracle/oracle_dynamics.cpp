@@ -107,6 +107,38 @@ void dyn_com(const H1Model& md, const double* x, double* com) {
   for (int i = 0; i < 3; ++i) com[i] = acc[i] / tot;
 }
 
+// Whole-body CoM velocity in the world frame: the value of mj_jacSubtreeCom(root) * qvel that
+// RobotUtils::loadReferences stores per reference row (/root/reference/src/common/robot_utils.cpp:388-397).
+// Body-by-body velocity propagation (origin velocity + angular velocity per body), mass-weighted mean of the
+// body-CoM velocities. qvel conventions: world-frame base linear velocity, body-frame base angular velocity.
+void dyn_com_vel(const H1Model& md, const double* x, double* cv) {
+  double R[H1_NB][9], r[H1_NB][3];
+  dyn_fk(md, x, R, r);
+  double w[H1_NB][3], vo[H1_NB][3];
+  const double* v = x + H1_NQ;
+  matvec3(R[0], v + 3, w[0]);
+  for (int i = 0; i < 3; ++i) vo[0][i] = v[i];
+  double tot = 0, acc[3] = {0, 0, 0};
+  for (int b = 0; b < H1_NB; ++b) {
+    if (b > 0) {
+      const int p = md.parent[b], ax = md.axis[b];
+      double off[3], t[3];
+      for (int i = 0; i < 3; ++i) off[i] = r[b][i] - r[p][i];
+      cross3(w[p], off, t);
+      for (int i = 0; i < 3; ++i) {
+        vo[b][i] = vo[p][i] + t[i];
+        w[b][i] = w[p][i] + R[b][3 * i + ax] * v[5 + b];
+      }
+    }
+    double c[3], t[3];
+    matvec3(R[b], md.ipos[b], c);
+    cross3(w[b], c, t);
+    tot += md.mass[b];
+    for (int i = 0; i < 3; ++i) acc[i] += md.mass[b] * (vo[b][i] + t[i]);
+  }
+  for (int i = 0; i < 3; ++i) cv[i] = acc[i] / tot;
+}
+
 void dyn_body_pos(const H1Model& md, const double* x, int body, double* p) {
   double R[H1_NB][9], r[H1_NB][3];
   dyn_fk(md, x, R, r);

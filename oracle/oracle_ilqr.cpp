@@ -272,6 +272,7 @@ bool line_search(Solver& s, const double* x0, double* new_cost, int* alpha_index
   const Problem& p = *s.p;
   const int N = s.N;
   double baseline = total_cost(s, s.xbar.data(), s.ubar.data());
+  s.last_ls_margin = -1.0;
   std::vector<double> xn((N + 1) * NX), un(N * NU);
   for (int ai = 0; ai < H1ILQR_NALPHA; ++ai) {
     double alpha = p.opt.alphas[ai];
@@ -286,6 +287,11 @@ bool line_search(Solver& s, const double* x0, double* new_cost, int* alpha_index
       dyn_step(p.dyn, &xn[t * NX], &un[t * NU], &xn[(t + 1) * NX]);
     }
     double c = total_cost(s, xn.data(), un.data());
+    {
+      // a non-finite candidate cost is rejected whatever the rounding: it does not narrow the margin
+      const double m = std::fabs(c - (baseline - p.opt.accept_margin));
+      if (m == m && (s.last_ls_margin < 0.0 || m < s.last_ls_margin)) s.last_ls_margin = m;
+    }
     if (c < baseline - p.opt.accept_margin) {
       s.xbar = xn; s.ubar = un;
       *new_cost = c; *alpha_index = ai;
@@ -314,6 +320,8 @@ bool solve(Solver& s, const double* x0, double* cost_out) {
   const H1SolverOptions& o = s.p->opt;
   s.cost_trace.assign(o.max_iterations, 0.0);
   s.alpha_trace.assign(2 * o.max_iterations, -2);
+  s.ls_margin.assign(2 * o.max_iterations, -1.0);
+  s.stop_margin.assign(o.max_iterations, -1.0);
   double cur = total_cost(s, s.xbar.data(), s.ubar.data());
   int it = 0;
   for (it = 0; it < o.max_iterations; ++it) {
@@ -325,11 +333,13 @@ bool solve(Solver& s, const double* x0, double* cost_out) {
     double nc; int ai;
     bool improved = line_search(s, x0, &nc, &ai);
     s.alpha_trace[2 * it] = ai;
+    s.ls_margin[2 * it] = s.last_ls_margin;
     if (!improved) {
       s.lambda = std::min(s.lambda * 10.0, o.reg_max);
       backward_pass(s);
       improved = line_search(s, x0, &nc, &ai);
       s.alpha_trace[2 * it + 1] = ai;
+      s.ls_margin[2 * it + 1] = s.last_ls_margin;
       if (!improved) {
         s.cost_trace[it] = cur;
         if (it > 1) { ++it; break; }
@@ -339,6 +349,7 @@ bool solve(Solver& s, const double* x0, double* cost_out) {
     cur = nc;
     s.lambda = std::max(s.lambda / 2.0, o.reg_min);
     s.cost_trace[it] = cur;
+    s.stop_margin[it] = std::min(std::fabs(std::fabs(cur - prev) - o.tolerance), std::fabs(cur - o.divergence_cost));
     if (std::fabs(cur - prev) < o.tolerance) { ++it; break; }
     if (cur > o.divergence_cost) { ++it; break; }
   }

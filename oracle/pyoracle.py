@@ -98,6 +98,13 @@ def dyn_com(x, model=None):
     return out
 
 
+def dyn_com_vel(x, model=None):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty(3)
+    lib().orc_dyn_com_vel(_mp(model), dptr(x), dptr(out))
+    return out
+
+
 def dyn_bias(x, model=None):
     x = np.ascontiguousarray(x, dtype=np.float64)
     out = np.empty(25)
@@ -219,6 +226,14 @@ class OracleSolver:
         at = np.empty((self.opt.max_iterations, 2), dtype=np.int32)
         lib().orc_get_trace(self.h, C.c_int(i), dptr(ct), iptr(at))
         return ct, at
+
+    def margins(self, i=0):
+        """Distance (cost units) of every accept / reject / stop decision of the last solve from flipping:
+        (ls_margin [max_iterations][2], stop_margin [max_iterations]); -1 = decision not taken."""
+        lm = np.empty((self.opt.max_iterations, 2))
+        sm = np.empty(self.opt.max_iterations)
+        lib().orc_get_margins(self.h, C.c_int(i), dptr(lm), dptr(sm))
+        return lm, sm
 
     _shapes = {
         "xbar": lambda N: (N + 1, NX), "ubar": lambda N: (N, NU), "K": lambda N: (N, NX, NU),

@@ -125,3 +125,45 @@ def test_golden_vectors_regression(oracle):
         assert (at == g[f"{tag}_solve_alpha"]).all()
         assert abs(c - g[f"{tag}_solve_cost"][0]) <= 1e-9 * abs(c)
         assert np.abs(s.get("xbar") - g[f"{tag}_solve_xbar"]).max() < 1e-8
+
+
+def test_com_velocity_matches_finite_difference_of_com(oracle):
+    """dyn_com_vel (the J_subtreeCom * qvel target of loadReferences, robot_utils.cpp:388-397) = d/dt of dyn_com along
+    the exact configuration flow (world-frame base velocity, body-frame angular velocity, hinge rates)."""
+    rng = np.random.default_rng(0)
+    x = np.zeros(51)
+    x[2] = 1.0
+    q = rng.normal(size=4); x[3:7] = q / np.linalg.norm(q)
+    x[7:26] = rng.uniform(-0.5, 0.5, 19); x[26:] = rng.uniform(-1, 1, 25)
+
+    def flow(x, eps):
+        y = x.copy(); y[0:3] += eps * x[26:29]
+        w = x[29:32]; ang = np.linalg.norm(w) * eps
+        b = np.array([np.cos(ang / 2), *(np.sin(ang / 2) * w / np.linalg.norm(w))]); a = x[3:7]
+        y[3:7] = [a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                  a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]]
+        y[7:26] += eps * x[32:]
+        return y
+    e = 1e-6
+    fd = (oracle.dyn_com(flow(x, e)) - oracle.dyn_com(flow(x, -e))) / (2 * e)
+    assert np.abs(fd - oracle.dyn_com_vel(x)).max() < 1e-9
+
+
+def test_decision_margins_and_compare_solve(oracle):
+    """The oracle's decision margins (test diagnostics) are consistent with its trace, and compare_solve accepts an
+    identical solve, flags a forked one as a real mismatch when the margin is wide, and as a near-tie when it is not."""
+    from helpers import compare_solve, grav_comp_guess, make_oracle, standing_state
+    so, w, win = make_oracle("walking")
+    x0 = standing_state(); ug = grav_comp_guess(x0)
+    so.initialize(x0, False, ug); c = so.solve(x0)
+    ct, at = so.trace(); lm, sm = so.margins(); it = so.iters()
+    for k in range(it):
+        assert lm[k][0] >= 0 and (lm[k][1] >= 0) == (at[k][1] != -2)
+    assert (lm[it:] == -1).all() and (sm[it:] == -1).all()
+    x, u = so.get("xbar"), so.get("ubar")
+    assert compare_solve(so, c, it, ct, at, x, u) == "match"
+    bad = at.copy(); bad[1][0] = (bad[1][0] + 1) % 8
+    with pytest.raises(AssertionError):
+        compare_solve(so, c, it, ct, bad, x, u)     # wide margin: a fork there is a real mismatch
+    with pytest.raises(AssertionError):
+        compare_solve(so, c * (1 + 1e-5), it, ct, at, x, u)
