@@ -168,6 +168,12 @@ int h1ilqr_get_linearization(H1Ilqr* h, double* A, double* B);
 int h1ilqr_set_linearization(H1Ilqr* h, const double* A, const double* B);
 int h1ilqr_get_cost_quadratics(H1Ilqr* h, double* lx, double* lu, double* lxx, double* luu);
 int h1ilqr_set_cost_quadratics(H1Ilqr* h, const double* lx, const double* lu, const double* lxx, const double* luu);
+/* Previous MPC solution that a warm start shifts by one knot: the prev_xbar / prev_ubar arguments of
+ * iLQR::initializeWithReference (ilqr.hpp:41-45), owned by MPC (mpc.hpp:57-58). h1ilqr_mpc_step maintains it on the
+ * device; a caller that owns the previous solution itself (the iLQR shim class) hands it over here and then calls
+ * h1ilqr_initialize with warm = 1. prev_xbar [batch][N+1][51], prev_ubar [batch][N][19]. */
+int h1ilqr_set_previous_solution(H1Ilqr* h, const double* prev_xbar, const double* prev_ubar);
+int h1ilqr_get_previous_solution(H1Ilqr* h, double* prev_xbar, double* prev_ubar);
 int h1ilqr_get_regularization(H1Ilqr* h, double* lambda);
 int h1ilqr_set_regularization(H1Ilqr* h, const double* lambda, int shared);
 /* per-iteration trace of the last solve: cost_trace [batch][max_iterations], alpha_trace [batch][max_iterations][2] */

@@ -783,6 +783,22 @@ COPY_PAIR(h1ilqr_get_trajectory, h1ilqr_set_trajectory, xbar, SZ((h->N + 1) * NX
 COPY_PAIR(h1ilqr_get_gains, h1ilqr_set_gains, K, SZ(h->N * NU * NX), kff, SZ(h->N * NU))
 COPY_PAIR(h1ilqr_get_linearization, h1ilqr_set_linearization, A, SZ(h->N * NX * NX), Bm, SZ(h->N * NX * NU))
 
+// previous solution of the MPC loop (MPC::prev_xbar_ / prev_ubar_, mpc.hpp:57-58): the warm start shifts it (k_init_guess)
+int h1ilqr_set_previous_solution(H1Ilqr* h, const double* prev_xbar, const double* prev_ubar) {
+  GUARD(h);
+  if (!prev_xbar || !prev_ubar) return set_err(H1ILQR_EARG, "null previous solution");
+  H2D(h->prev_xbar, prev_xbar, SZ((h->N + 1) * NX) * sizeof(double));
+  H2D(h->prev_ubar, prev_ubar, SZ(h->N * NU) * sizeof(double));
+  k_fill_int<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->B, h->has_prev, 1);
+  SYNC(); return 0;
+}
+int h1ilqr_get_previous_solution(H1Ilqr* h, double* prev_xbar, double* prev_ubar) {
+  GUARD(h);
+  if (prev_xbar) D2H(prev_xbar, h->prev_xbar, SZ((h->N + 1) * NX) * sizeof(double));
+  if (prev_ubar) D2H(prev_ubar, h->prev_ubar, SZ(h->N * NU) * sizeof(double));
+  SYNC(); return 0;
+}
+
 int h1ilqr_get_cost_quadratics(H1Ilqr* h, double* lx, double* lu, double* lxx, double* luu) {
   GUARD(h);
   if (lx) D2H(lx, h->lx, SZ((h->N + 1) * NX) * sizeof(double));

@@ -22,7 +22,7 @@ EXPORTS = [
     "h1ilqr_backward_pass", "h1ilqr_line_search", "h1ilqr_total_cost", "h1ilqr_dynamics_step", "h1ilqr_bias_forces",
     "h1ilqr_reference_kinematics", "h1ilqr_reference_com_velocity", "h1ilqr_get_status", "h1ilqr_sole_points", "h1ilqr_set_trajectory", "h1ilqr_get_trajectory", "h1ilqr_get_gains",
     "h1ilqr_set_gains", "h1ilqr_get_linearization", "h1ilqr_set_linearization", "h1ilqr_get_cost_quadratics",
-    "h1ilqr_set_cost_quadratics", "h1ilqr_get_regularization", "h1ilqr_set_regularization", "h1ilqr_get_solve_trace",
+    "h1ilqr_set_cost_quadratics", "h1ilqr_set_previous_solution", "h1ilqr_get_previous_solution", "h1ilqr_get_regularization", "h1ilqr_set_regularization", "h1ilqr_get_solve_trace",
     "h1ilqr_upload_inputs", "h1ilqr_host_register", "h1ilqr_host_unregister", "h1ilqr_run_resident_steps", "h1ilqr_measure_fp64_peak", "h1ilqr_measure_fp64_mma_peak", "h1ilqr_enable_stage_timing", "h1ilqr_set_kernel_policy", "h1ilqr_get_stage_times", "h1ilqr_stream", "h1_default_dynamics_model",
     "h1_default_cost_model",
 ]
@@ -279,6 +279,17 @@ class H1IlqrBatch:
 
     def set_cost_quadratics(self, lx, lu, lxx, luu):
         _check(lib().h1ilqr_set_cost_quadratics(self._h, dptr(_f(lx)), dptr(_f(lu)), dptr(_f(lxx)), dptr(_f(luu))))
+
+    def set_previous_solution(self, prev_xbar, prev_ubar):
+        """Hand over the previous MPC solution a warm start shifts (MPC::prev_xbar_ / prev_ubar_)."""
+        _check(lib().h1ilqr_set_previous_solution(self._h, dptr(_f(prev_xbar, (self.B, self.N + 1, NX))),
+                                                  dptr(_f(prev_ubar, (self.B, self.N, NU)))))
+
+    def get_previous_solution(self):
+        xb = np.empty((self.B, self.N + 1, NX))
+        ub = np.empty((self.B, self.N, NU))
+        _check(lib().h1ilqr_get_previous_solution(self._h, dptr(xb), dptr(ub)))
+        return xb, ub
 
     def get_regularization(self):
         lam = np.empty(self.B)

@@ -4,7 +4,7 @@
 TAG=${1:-x}; shift
 O=gpurun_out; mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv,noheader > $O/${TAG}_gpu.txt 2>&1
-(time timeout ${TEST_TIMEOUT:-900} python -m pytest tests -m gpu -q -x --durations=15 ${SEL:+-k "$SEL"}) > $O/${TAG}_tests.log 2>&1; tail -25 $O/${TAG}_tests.log
+(time timeout ${TEST_TIMEOUT:-900} python -m pytest tests -m gpu -q ${PYTEST_X:+-x} --durations=15 ${SEL:+-k "$SEL"}) > $O/${TAG}_tests.log 2>&1; tail -25 $O/${TAG}_tests.log
 if [ -z "$NOSMOKE" ]; then timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; tail -3 $O/${TAG}_smoke.log; fi
 if [ -z "$NOBENCH" ]; then
 timeout 600 python bench.py "$@" > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; tail -3 $O/${TAG}_bench.err
