@@ -4,6 +4,7 @@
 // device or returns H1ILQR_ECUDA.
 #include "h1_kernels_solve.cuh"
 #include "h1_kernels_seq.cuh"
+#include "h1_kernels_quad.cuh"
 #include "h1_lin_finish.cuh"
 #include "h1_riccati.cuh"
 #include "model_tables.h"
@@ -55,7 +56,9 @@ struct H1Ilqr {
   int policy = H1ILQR_KERNELS_AUTO;
   int seq_min_batch = 768;  // AUTO: batch at or above which rollouts / line searches run one THREAD per f_D evaluation (h1_dyn_seq.cuh);
                             // measured break-even with the warp-per-evaluation kernels: between 512 and 1024 instances
-  size_t smem_seq = 0, smem_seq_ls = 0, smem_lint = 0, smem_linf = 0;
+  size_t smem_seq = 0, smem_seq_ls = 0, smem_lint = 0, smem_linf = 0, smem_q4 = 0;
+  int q4_warps = 8;         // instances per CTA of k_line_search_quad (8: 255 registers; 10: 168 registers)
+  bool ls_quad = true;      // batched line search: quad-cooperative kernel (h1_kernels_quad.cuh); false = thread-sequential one
   bool seq_ok = false;      // the model has the chain structure the thread-sequential f_D is specialised for
   long lin_cols_min_knots = 148 * 32;   // AUTO: B*N at or above which the direction-uniform linearization (32 knots per CTA) fills the GPU;
                                         // below it the knot-major thread-per-column kernel (k_linearize_dirs) is the faster one
@@ -180,6 +183,11 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   if (const char* e = getenv("H1_SEQ_SMEM_PAD")) h->smem_seq += (size_t)atoi(e) * 1024;   // experiment: limits resident CTAs
   h->smem_seq_ls = h->smem_seq + (size_t)SEQ_THREADS * NX * sizeof(double);
   CUH(cudaFuncSetAttribute(k_line_search_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_seq_ls));
+  if (const char* e = getenv("H1_Q4_WARPS")) h->q4_warps = atoi(e) == 10 ? 10 : 8;   // A/B measurements
+  h->smem_q4 = mdl + (size_t)h->q4_warps * sizeof(Q4WarpSmem);
+  CUH(cudaFuncSetAttribute(k_line_search_quad<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(mdl + 8 * sizeof(Q4WarpSmem))));
+  CUH(cudaFuncSetAttribute(k_line_search_quad<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(mdl + 10 * sizeof(Q4WarpSmem))));
+  if (const char* e = getenv("H1_LS_SEQ")) h->ls_quad = atoi(e) == 0;   // A/B measurements against the thread-sequential kernel
   CUH(cudaFuncSetAttribute(k_rollout_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_seq));
   CUH(cudaFuncSetAttribute(k_dyn_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
   CUH(cudaFuncSetAttribute(k_dyn_query, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
@@ -328,6 +336,17 @@ static void launch_backward(H1Ilqr* h, const int* mask) {
   LAUNCHED();
 }
 static void launch_line_search(H1Ilqr* h, const int* mask) {
+  if (h->seq_ok && h->ls_quad && use_batched(h, h->B, h->seq_min_batch)) {   // one warp per instance: 8 candidates x 4 chains
+    const int* cnt; const int* list = list_for(h, mask, &cnt);
+#define Q4_LAUNCH(W)                                                                                            \
+  k_line_search_quad<W><<<(unsigned)((h->B + W - 1) / W), W * 32, h->smem_q4, h->stream>>>(                     \
+      h->d_dyn, h->d_w, h->d_opt, ref_table(h), h->B, h->N, mask, list, cnt, h->x0, h->nominal_cost, h->xbar, h->ubar, \
+      h->K, h->kff, h->xnew, h->unew, h->ls_ok, h->ls_cost, h->ls_alpha)
+    if (h->q4_warps == 10) Q4_LAUNCH(10); else Q4_LAUNCH(8);
+#undef Q4_LAUNCH
+    LAUNCHED();
+    return;
+  }
   if (h->seq_ok && use_batched(h, h->B, h->seq_min_batch)) {   // one thread per (instance, candidate)
     const long threads = (long)h->B * H1ILQR_NALPHA;
     const int* cnt; const int* list = list_for(h, mask, &cnt);
