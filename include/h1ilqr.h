@@ -120,9 +120,11 @@ int h1ilqr_mpc_reset(H1Ilqr* h);
 int h1ilqr_get_status(H1Ilqr* h, int* status_out, int* iters_out);
 
 /* Kernel families. The path has two sm_100a implementations of its per-knot / per-rollout stages with identical
- * semantics (both are parity-tested against the oracle): COOPERATIVE = one warp per unit (lowest latency, used for
- * a single MPC instance, the reference's use case), BATCHED = one thread per unit (highest throughput, used when
- * many independent instances are resident). AUTO (default) chooses by batch*N. There is no CPU path in either. */
+ * semantics (both are parity-tested against the oracle): COOPERATIVE = one warp per unit (dynamics evaluation,
+ * candidate rollout, knot), BATCHED = one thread per unit for the nominal rollout / factorisation / tangent
+ * directions and one warp per instance (8 candidates x 4 kinematic chains) for the line search. AUTO (default)
+ * chooses per stage by batch size; its line search is the BATCHED one at every batch size (it is also the faster
+ * one for a single instance). There is no CPU path in either. */
 #define H1ILQR_KERNELS_AUTO 0
 #define H1ILQR_KERNELS_COOPERATIVE 1
 #define H1ILQR_KERNELS_BATCHED 2
@@ -187,6 +189,10 @@ int h1ilqr_get_solve_trace(H1Ilqr* h, double* cost_trace, int* alpha_trace);
  * so that every step is the same cold-start solve. */
 int h1ilqr_upload_inputs(H1Ilqr* h, const double* x_measured, const double* u_init, int u_init_shared);
 int h1ilqr_run_resident_steps(H1Ilqr* h, int steps, int cold_each_step, double* elapsed_ms);
+/* Device time (CUDA events on the handle's stream, milliseconds summed over `reps` launches) of one stage on the handle's
+ * current trajectory / derivatives / gains: 0 factorisation of Mhat, 1 linearization, 2 cost quadratics, 3 backward
+ * pass, 4 line search (the trajectory is restored after every repetition). Measurement only. */
+int h1ilqr_time_stage(H1Ilqr* h, int stage, int reps, double* elapsed_ms);
 /* sustained fp64 FMA throughput of the device (TFLOP/s), measured with a register-resident DFMA kernel: the
  * FP64 roofline denominator (MEASURED_PEAKS.json carries none). */
 int h1ilqr_measure_fp64_peak(H1Ilqr* h, double* tflops);

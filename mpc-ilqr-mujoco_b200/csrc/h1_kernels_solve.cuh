@@ -226,6 +226,12 @@ __global__ void k_first_control(int B, int N, const double* __restrict__ x_meas,
   u_apply[(size_t)inst * NU + i] = ubar[(size_t)inst * N * NU + i] + acc;
 }
 
+// x0[i] = xbar[i][0] (stage timing: candidates of the line search start from the trajectory's own first state)
+__global__ void k_copy_x0(int B, int N, const double* __restrict__ xbar, double* __restrict__ x0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  for (int k = 0; k < NX; ++k) x0[(size_t)i * NX + k] = xbar[(size_t)i * (N + 1) * NX + k];
+}
 __global__ void k_fill_int(int n, int* p, int v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

@@ -263,6 +263,80 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
     //      | warp 7: pivoted LDL^T of Quu, then N = L^-1: the sequential section of the knot, beside both contractions and the
     //      prefetch (one barrier for the whole phase) ----
     if (warp < 7) {
+#ifdef RIC_P3_SIX   // measured on B200 (r02i): 11.05 ms per 8192-instance launch against 9.98 ms for the seven-warp split below — not adopted
+      // Six contraction warps (0,1,2,4,5,6); warp 3 — the one that shares a scheduler sub-partition with the LDL^T warp 7 —
+      // issues no DMMA in this phase: a dependent fp64 operation of the sequential warp otherwise queues behind the 16-cycle
+      // DMMAs of its neighbour at every step of the factorisation, which made the LDL^T (not the contractions) the longest
+      // part of a knot.
+      const int cq = warp < 3 ? warp : warp - 1;       // 0..5 for the contraction warps
+      if (warp != 3) {
+        // G1a by COLUMN tile: W(:, 8 cq .. 8 cq + 7) = Vxx A(:, same), all seven row tiles
+        double acc[7][2];
+#pragma unroll
+        for (int m = 0; m < 7; ++m) acc[m][0] = acc[m][1] = 0.0;
+        const double* const bq = s.AB + (8 * cq + g) * LDX + t4;
+        const double* ar[7];
+#pragma unroll
+        for (int m = 0; m < 7; ++m) ar[m] = s.V + min(8 * m + g, LDX - 1) + t4 * LDX;   // pad row 51 of V is zero
+#pragma unroll 1
+        for (int ks = 0; ks < 13; ++ks) {
+          const double b = bq[4 * ks];
+#pragma unroll
+          for (int m = 0; m < 7; ++m) dmma884(acc[m][0], acc[m][1], ar[m][4 * ks * LDX], b);
+        }
+#pragma unroll
+        for (int m = 0; m < 7; ++m) {
+          const int r = 8 * m + g;
+          if (r < LDX) { s.W[(8 * cq + 2 * t4) * LDX + r] = acc[m][0]; s.W[(8 * cq + 2 * t4 + 1) * LDX + r] = acc[m][1]; }   // row 51 of W = 0
+        }
+      }
+      asm volatile("bar.sync 1, 224;" ::: "memory");   // W complete (warp 3 arrives at once)
+      if (warp != 3) {
+        // G2: the 48 tiles of A' [W | Vx] that are read again (lower triangle of Qxx, all of Qxu and Qx), 8 per warp: column
+        // tiles are paired so that every warp has 8 — {0 (7 rows), 3}, {1 (6), 5 (2)}, {2 (5), 4 (3)}, {6, 3}, {7, 3}, {8, 3};
+        // column tile 3 has 4 tiles (rows 3..6), one for each warp that owns a 7-row column
+        int tr[8], tc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (cq == 1) { tc[q] = q < 6 ? 1 : 5; tr[q] = q < 6 ? 1 + q : 5 + (q - 6); }
+          else if (cq == 2) { tc[q] = q < 5 ? 2 : 4; tr[q] = q < 5 ? 2 + q : 4 + (q - 5); }
+          else {
+            const int col = cq == 0 ? 0 : 3 + cq;                 // 0, 6, 7, 8
+            const int extra = cq == 0 ? 3 : cq + 1;               // row of the column-3 tile: 3, 4, 5, 6
+            tc[q] = q < 7 ? col : 3; tr[q] = q < 7 ? q : extra;
+          }
+        }
+        const double* bp[8];
+        const double* ap[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int c = 8 * tc[q] + g;
+          bp[q] = (c < NXU ? s.W + c * LDX : (c == NXU ? s.Vx : zc)) + t4;
+          ap[q] = s.AB + (8 * tr[q] + g) * LDX + t4;              // A'(r,k) = A(k,r); rows 51..55: discarded garbage
+        }
+        double acc[8][2];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q][0] = acc[q][1] = 0.0;
+#pragma unroll 1
+        for (int ks = 0; ks < 13; ++ks) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) dmma884(acc[q][0], acc[q][1], ap[q][4 * ks], bp[q][4 * ks]);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int r = 8 * tr[q] + g;
+          if (r >= NX) continue;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = 8 * tc[q] + 2 * t4 + e;
+            const double v = acc[q][e];
+            if (c < NX) s.V[c * LDX + r] = v;
+            else if (c < NXU) s.Qxu[(c - NX) * LDX + r] = v;
+            else if (c == NXU) s.Qx[r] = lxt[r] + v;
+          }
+        }
+      }
+#else
       w_strip(std::integral_constant<int, 6>(), 0);
       asm volatile("bar.sync 1, 224;" ::: "memory");   // W complete (the seven contraction warps only)
       // G2 tiles: only the lower triangle of Qxx is ever read again (G5 takes r >= c and mirrors), so of the 7 x 9 tiles
@@ -312,6 +386,7 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
           }
         }
       }
+#endif
       // s.AB, s.W and s.lq are free once all seven contraction warps are through G2 -> prefetch the next knot's [A|B], lx,
       // lu, luu and this knot's lxx (consumed by the final pass) while warp 7 is still in its sequential section
       asm volatile("bar.sync 1, 224;" ::: "memory");

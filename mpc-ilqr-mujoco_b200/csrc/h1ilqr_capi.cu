@@ -57,7 +57,7 @@ struct H1Ilqr {
   int seq_min_batch = 768;  // AUTO: batch at or above which rollouts / line searches run one THREAD per f_D evaluation (h1_dyn_seq.cuh);
                             // measured break-even with the warp-per-evaluation kernels: between 512 and 1024 instances
   size_t smem_seq = 0, smem_seq_ls = 0, smem_lint = 0, smem_linf = 0, smem_q4 = 0;
-  int q4_warps = 8;         // instances per CTA of k_line_search_quad (8: 255 registers; 10: 168 registers)
+  int q4_warps = 8;         // instances per CTA of k_line_search_quad
   bool ls_quad = true;      // batched line search: quad-cooperative kernel (h1_kernels_quad.cuh); false = thread-sequential one
   bool seq_ok = false;      // the model has the chain structure the thread-sequential f_D is specialised for
   long lin_cols_min_knots = 148 * 32;   // AUTO: B*N at or above which the direction-uniform linearization (32 knots per CTA) fills the GPU;
@@ -183,10 +183,13 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   if (const char* e = getenv("H1_SEQ_SMEM_PAD")) h->smem_seq += (size_t)atoi(e) * 1024;   // experiment: limits resident CTAs
   h->smem_seq_ls = h->smem_seq + (size_t)SEQ_THREADS * NX * sizeof(double);
   CUH(cudaFuncSetAttribute(k_line_search_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_seq_ls));
-  if (const char* e = getenv("H1_Q4_WARPS")) h->q4_warps = atoi(e) == 10 ? 10 : 8;   // A/B measurements
+  // instances per CTA of the quad line search: 8 (one 215 KB CTA per SM) for large batches; 1 while one-warp CTAs (28 KB,
+  // seven per SM) still cover the batch in a single wave, so that a handful of instances spread over as many SMs
+  h->q4_warps = batch > 7 * prop.multiProcessorCount ? 8 : 1;
+  if (const char* e = getenv("H1_Q4_WARPS")) h->q4_warps = atoi(e) == 1 ? 1 : 8;   // A/B measurements
   h->smem_q4 = mdl + (size_t)h->q4_warps * sizeof(Q4WarpSmem);
   CUH(cudaFuncSetAttribute(k_line_search_quad<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(mdl + 8 * sizeof(Q4WarpSmem))));
-  CUH(cudaFuncSetAttribute(k_line_search_quad<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(mdl + 10 * sizeof(Q4WarpSmem))));
+  CUH(cudaFuncSetAttribute(k_line_search_quad<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(mdl + 1 * sizeof(Q4WarpSmem))));
   if (const char* e = getenv("H1_LS_SEQ")) h->ls_quad = atoi(e) == 0;   // A/B measurements against the thread-sequential kernel
   CUH(cudaFuncSetAttribute(k_rollout_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_seq));
   CUH(cudaFuncSetAttribute(k_dyn_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
@@ -336,13 +339,13 @@ static void launch_backward(H1Ilqr* h, const int* mask) {
   LAUNCHED();
 }
 static void launch_line_search(H1Ilqr* h, const int* mask) {
-  if (h->seq_ok && h->ls_quad && use_batched(h, h->B, h->seq_min_batch)) {   // one warp per instance: 8 candidates x 4 chains
+  if (h->seq_ok && h->ls_quad && h->policy != H1ILQR_KERNELS_COOPERATIVE) {   // one warp per instance: 8 candidates x 4 chains (any batch size)
     const int* cnt; const int* list = list_for(h, mask, &cnt);
 #define Q4_LAUNCH(W)                                                                                            \
   k_line_search_quad<W><<<(unsigned)((h->B + W - 1) / W), W * 32, h->smem_q4, h->stream>>>(                     \
       h->d_dyn, h->d_w, h->d_opt, ref_table(h), h->B, h->N, mask, list, cnt, h->x0, h->nominal_cost, h->xbar, h->ubar, \
       h->K, h->kff, h->xnew, h->unew, h->ls_ok, h->ls_cost, h->ls_alpha)
-    if (h->q4_warps == 10) Q4_LAUNCH(10); else Q4_LAUNCH(8);
+    if (h->q4_warps == 1) Q4_LAUNCH(1); else Q4_LAUNCH(8);
 #undef Q4_LAUNCH
     LAUNCHED();
     return;
@@ -725,6 +728,52 @@ int h1ilqr_line_search(H1Ilqr* h, const double* x0, int* improved, double* new_c
   if (new_cost) D2H(new_cost, h->ls_cost, (size_t)h->B * sizeof(double));
   if (alpha_index) D2H(alpha_index, h->ls_alpha, (size_t)h->B * sizeof(int));
   SYNC(); CU(cudaGetLastError());
+  return 0;
+}
+
+// Device time of `reps` back-to-back launches of one stage on the current trajectory / derivatives / gains of every
+// instance (CUDA events on the handle's stream): the per-kernel launch duration the roofline figures are built from.
+// stage: 0 factorisation of Mhat (analytic linearization input), 1 linearization (factors ready), 2 cost quadratics,
+// 3 backward pass, 4 line search (candidates are rolled out, the accepted one is NOT installed: xbar / ubar are restored).
+int h1ilqr_time_stage(H1Ilqr* h, int stage, int reps, double* elapsed_ms) {
+  GUARD(h);
+  if (stage < 0 || stage > 4 || reps < 1 || !elapsed_ms) return set_err(H1ILQR_EARG, "h1ilqr_time_stage: bad arguments");
+  const size_t B = h->B, N = h->N;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  double *xs = nullptr, *us = nullptr;
+  if (stage == 4) {   // the line search overwrites the trajectory of the instances that accept a candidate
+    CU(cudaMalloc((void**)&xs, B * (N + 1) * NX * sizeof(double))); CU(cudaMalloc((void**)&us, B * N * NU * sizeof(double)));
+    CU(cudaMemcpyAsync(xs, h->xbar, B * (N + 1) * NX * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(us, h->ubar, B * N * NU * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    k_copy_x0<<<(h->B + 127) / 128, 128, 0, h->stream>>>(h->B, h->N, h->xbar, h->x0);
+    launch_rollout(h, nullptr, nullptr, h->N, h->nominal_cost);
+  }
+  float total = 0.f;
+  for (int r = 0; r < reps; ++r) {
+    CU(cudaEventRecord(e0, h->stream));
+    switch (stage) {
+      case 0: launch_factors(h, nullptr); break;
+      case 1: launch_linearize(h, nullptr, h->opt.linearization != H1ILQR_LIN_FD); break;
+      case 2: launch_cost_quadratics(h, nullptr); break;
+      case 3: launch_backward(h, nullptr); break;
+      default: launch_line_search(h, nullptr); break;
+    }
+    CU(cudaEventRecord(e1, h->stream));
+    if (stage == 4) {
+      CU(cudaMemcpyAsync(h->xbar, xs, B * (N + 1) * NX * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      CU(cudaMemcpyAsync(h->ubar, us, B * N * NU * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    total += ms;
+  }
+  SYNC(); CU(cudaGetLastError());
+  if (xs) cudaFree(xs);
+  if (us) cudaFree(us);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *elapsed_ms = total;
   return 0;
 }
 

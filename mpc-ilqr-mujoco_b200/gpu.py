@@ -13,7 +13,7 @@ from .ctypes_defs import (H1Model, H1SolverOptions, H1StageTimes, H1Weights, NQ,
                           dptr, iptr)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libh1ilqr.so")
+LIB_PATH = os.environ.get("H1ILQR_LIB") or os.path.join(_HERE, "lib", "libh1ilqr.so")   # (override: A/B experiment builds)
 
 EXPORTS = [
     "h1ilqr_default_options", "h1ilqr_create", "h1ilqr_destroy", "h1ilqr_last_error", "h1ilqr_batch",
@@ -23,7 +23,7 @@ EXPORTS = [
     "h1ilqr_reference_kinematics", "h1ilqr_reference_com_velocity", "h1ilqr_get_status", "h1ilqr_sole_points", "h1ilqr_set_trajectory", "h1ilqr_get_trajectory", "h1ilqr_get_gains",
     "h1ilqr_set_gains", "h1ilqr_get_linearization", "h1ilqr_set_linearization", "h1ilqr_get_cost_quadratics",
     "h1ilqr_set_cost_quadratics", "h1ilqr_set_previous_solution", "h1ilqr_get_previous_solution", "h1ilqr_get_regularization", "h1ilqr_set_regularization", "h1ilqr_get_solve_trace",
-    "h1ilqr_upload_inputs", "h1ilqr_host_register", "h1ilqr_host_unregister", "h1ilqr_run_resident_steps", "h1ilqr_measure_fp64_peak", "h1ilqr_measure_fp64_mma_peak", "h1ilqr_enable_stage_timing", "h1ilqr_set_kernel_policy", "h1ilqr_get_stage_times", "h1ilqr_stream", "h1_default_dynamics_model",
+    "h1ilqr_upload_inputs", "h1ilqr_host_register", "h1ilqr_host_unregister", "h1ilqr_run_resident_steps", "h1ilqr_time_stage", "h1ilqr_measure_fp64_peak", "h1ilqr_measure_fp64_mma_peak", "h1ilqr_enable_stage_timing", "h1ilqr_set_kernel_policy", "h1ilqr_get_stage_times", "h1ilqr_stream", "h1_default_dynamics_model",
     "h1_default_cost_model",
 ]
 
@@ -319,6 +319,14 @@ class H1IlqrBatch:
         ms = C.c_double()
         _check(lib().h1ilqr_run_resident_steps(self._h, C.c_int(steps), C.c_int(int(cold_each_step)), C.byref(ms)))
         return ms.value
+
+    STAGES = {"factor": 0, "linearize": 1, "cost_quadratics": 2, "backward": 3, "line_search": 4}
+
+    def time_stage(self, stage, reps=1):
+        """Device milliseconds PER LAUNCH of one stage on the current trajectory / derivatives / gains."""
+        ms = C.c_double()
+        _check(lib().h1ilqr_time_stage(self._h, C.c_int(self.STAGES[stage]), C.c_int(reps), C.byref(ms)))
+        return ms.value / reps
 
     def measure_fp64_peak(self):
         t = C.c_double()

@@ -123,3 +123,25 @@ def test_cost_quadratics_phases_match_oracle(emul, oracle, tag):
         if t < 25:
             assert np.abs(glu - lu[t]).max() <= 1e-12 * max(np.abs(lu[t]).max(), 1e-300)
             assert np.abs(gluu - luu[t]).max() <= 1e-12 * np.abs(luu[t]).max()
+
+
+def test_quad_cooperative_dynamics_matches_dense_oracle(emul, oracle):
+    """csrc/h1_dyn_quad.cuh (four lanes per f_D, one per kinematic chain: articulated-body recursion with the parent
+    pose recovered by the inverse joint transform, torso shared by the two arm lanes, 6 x 6 base block summed over the
+    lanes) against the dense oracle; the four lanes run as four host threads, the kernel's xor-shuffles as exchanges
+    between barriers. Includes clamped torques, un-normalised quaternions, feet deep in contact and in the air."""
+    lib = C.CDLL(os.path.join(EMUL, "libquad_emul.so"))
+    x, u = states(96, 9)
+    u[::5, 2] = 500.0; u[1::5, 7] = -500.0
+    x[::4, 2] -= 0.08
+    x[1::4, 2] += 0.3
+    x[::7, 3:7] *= 1.07
+    xe = np.zeros_like(x); com = np.empty((96, 3)); com2 = np.empty((96, 3))
+    assert lib.emul_dyn_step_quad(96, P(x), P(u), P(xe), P(com), P(com2)) == 0
+    assert np.abs(xe - oracle.dyn_step(x, u)).max() < 5e-12
+    assert max(np.abs(com[i] - oracle.dyn_com(x[i])).max() for i in range(96)) < 1e-14
+    assert np.abs(com2 - com).max() < 1e-14
+    # zero torques (u = nullptr) = the plant's free fall
+    xz = np.zeros_like(x)
+    assert lib.emul_dyn_step_quad(96, P(x), None, P(xz), P(com), P(com2)) == 0
+    assert np.abs(xz - oracle.dyn_step(x, np.zeros_like(u))).max() < 5e-12
