@@ -188,7 +188,29 @@ int h1ilqr_get_solve_trace(H1Ilqr* h, double* cost_trace, int* alpha_trace);
  * elapsed milliseconds. cold_each_step != 0 forgets the previous solution and resets lambda before every step
  * so that every step is the same cold-start solve. */
 int h1ilqr_upload_inputs(H1Ilqr* h, const double* x_measured, const double* u_init, int u_init_shared);
+/* cold_each_step: bit 0 = cold start at every step; bit 1 = capture the step once into a CUDA graph and replay it (the
+ * launch sequence of a step is fixed: iteration counts are handled on the device by the compact instance lists). */
 int h1ilqr_run_resident_steps(H1Ilqr* h, int steps, int cold_each_step, double* elapsed_ms);
+
+/* ---- device-resident closed loop: main/humanoid_mpc.cpp:130-179 for the whole batch without a host round
+ * trip per step: getState -> MPC::stepOnce (window at t_idx, warm start, solve, first control) -> setControl -> step.
+ * h1ilqr_set_reference_table uploads RobotUtils' full tables once (x_ref_full_ [rows][51], com_ref_full_ [rows][3],
+ * ee_pos_ref_full_ [rows][2][3], com_vel_ref_full_ [rows][3] (NULL = zeros), contact_schedule_ [contact_rows][2]; loadReferences
+ * / loadContactSchedule, robot_utils.cpp:281-492). Windows are extracted on the device with the reference's rules: rows
+ * min(t_idx + i, last) for x_ref / com_ref (robot_utils.cpp:422-443), HORIZON-LOCAL rows i for isStance / getEEReference /
+ * getCoMVelReference (quirk Q6; schedule_offset != 0 uses rows t_idx + i instead), u_ref = 0.
+ * h1ilqr_run_closed_loop runs `steps` closed-loop steps of every instance: plant = f_D (RobotUtils::step, robot_utils.cpp:
+ * 99-103), time index t_idx0[i] + step (NULL: continue from the current indices, which start at 0), warm start from the
+ * previous solution kept on the device (h1ilqr_mpc_reset forgets it), lambda persistent. x_start NULL = continue from the
+ * current plant states. Outputs (any may be NULL): x_final [batch][51], cost_log / iters_log [steps][batch],
+ * u_log [steps][batch][19] (applied controls), elapsed_ms (CUDA events around the whole loop). use_graph: replay one captured
+ * step. Returns H1ILQR_ENOTFINITE when an instance is non-finite at the last step. */
+int h1ilqr_set_reference_table(H1Ilqr* h, int rows, const double* x_ref_full, const double* com_ref_full,
+                               const double* ee_ref_full, const double* com_vel_ref_full, int contact_rows,
+                               const int* contact, int schedule_offset);
+int h1ilqr_run_closed_loop(H1Ilqr* h, int steps, const int* t_idx0, const double* x_start, const double* u_init,
+                           int u_init_shared, int use_graph, double* x_final, double* cost_log, int* iters_log,
+                           double* u_log, double* elapsed_ms);
 /* Device time (CUDA events on the handle's stream, milliseconds summed over `reps` launches) of one stage on the handle's
  * current trajectory / derivatives / gains: 0 factorisation of Mhat, 1 linearization, 2 cost quadratics, 3 backward
  * pass, 4 line search (the trajectory is restored after every repetition). Measurement only. */

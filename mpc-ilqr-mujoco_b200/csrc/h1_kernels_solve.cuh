@@ -226,6 +226,49 @@ __global__ void k_first_control(int B, int N, const double* __restrict__ x_meas,
   u_apply[(size_t)inst * NU + i] = ubar[(size_t)inst * N * NU + i] + acc;
 }
 
+// ---- device-resident closed loop (main/humanoid_mpc.cpp:130-179 without host round trips) ----
+// Full reference tables of RobotUtils (x_ref_full_, com_ref_full_, ee_pos_ref_full_, com_vel_ref_full_, contact_schedule_),
+// uploaded once; every instance has its own time index.
+struct RefTables {
+  const double *x, *com, *ee, *cv;   // [rows][51], [rows][3], [rows][2][3], [rows][3]
+  const int* contact;                // [contact_rows][2]
+  int rows, contact_rows;
+  int schedule_offset;               // 0: horizon-local schedule / foot / CoM-velocity lookups as the reference does (quirk Q6)
+};
+// Reference window of every instance at its time index: MPC::extractReferenceWindow / RobotUtils::getReferenceWindow
+// (mpc.cpp:163-166, robot_utils.cpp:422-443: rows min(t_idx + i, last)), isStance / getEEReference / getCoMVelReference
+// with the HORIZON-LOCAL knot index i (robot_utils.cpp:494-549). One thread per (instance, knot).
+__global__ void k_extract_window(RefTables tb, int B, int N, const int* __restrict__ t_idx, double* __restrict__ x_ref,
+                                 double* __restrict__ com_ref, double* __restrict__ ee_ref, double* __restrict__ cv_ref,
+                                 int* __restrict__ stance) {
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long)B * (N + 1)) return;
+  const int inst = (int)(g / (N + 1)), i = (int)(g - (long)inst * (N + 1));
+  const int row = min(t_idx[inst] + i, tb.rows - 1);
+  const int loc = tb.schedule_offset ? row : min(i, tb.rows - 1);
+  const size_t o = (size_t)inst * (N + 1) + i;
+  for (int k = 0; k < NX; ++k) x_ref[o * NX + k] = tb.x[(size_t)row * NX + k];
+  for (int k = 0; k < 3; ++k) { com_ref[o * 3 + k] = tb.com[(size_t)row * 3 + k]; cv_ref[o * 3 + k] = tb.cv[(size_t)loc * 3 + k]; }
+  for (int k = 0; k < 6; ++k) ee_ref[o * 6 + k] = tb.ee[(size_t)loc * 6 + k];
+  const int srow = tb.schedule_offset ? t_idx[inst] + i : i;   // isStance: rows past the schedule count as stance
+  for (int e = 0; e < 2; ++e) stance[o * 2 + e] = (srow < tb.contact_rows) ? (tb.contact[srow * 2 + e] == 1) : 1;
+}
+// end of a closed-loop step: logs, t_idx_++ (mpc.cpp:113), step counter
+__global__ void k_closed_loop_advance(int B, int* __restrict__ t_idx, int* __restrict__ step_ctr, const double* __restrict__ cost,
+                                      const int* __restrict__ iters, const double* __restrict__ u_apply,
+                                      double* __restrict__ log_cost, int* __restrict__ log_iters, double* __restrict__ log_u) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int step = *step_ctr;
+  if (i < B) {
+    t_idx[i] += 1;
+    if (log_cost) log_cost[(size_t)step * B + i] = cost[i];
+    if (log_iters) log_iters[(size_t)step * B + i] = iters[i];
+    if (log_u) for (int k = 0; k < NU; ++k) log_u[((size_t)step * B + i) * NU + k] = u_apply[(size_t)i * NU + k];
+  }
+  __syncthreads();
+}
+__global__ void k_increment(int* p) { *p += 1; }
+
 // x0[i] = xbar[i][0] (stage timing: candidates of the line search start from the trajectory's own first state)
 __global__ void k_copy_x0(int B, int N, const double* __restrict__ xbar, double* __restrict__ x0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -63,6 +63,17 @@ struct H1Ilqr {
   long lin_cols_min_knots = 148 * 32;   // AUTO: B*N at or above which the direction-uniform linearization (32 knots per CTA) fills the GPU;
                                         // below it the knot-major thread-per-column kernel (k_linearize_dirs) is the faster one
   size_t smem_dyn4 = 0, smem_lin = 0, smem_cq = 0, smem_ls = 0, smem_ric = 0;
+  // device-resident closed loop: full reference tables, per-instance time index, step counter, per-step logs
+  double *tab_x = nullptr, *tab_com = nullptr, *tab_ee = nullptr, *tab_cv = nullptr;
+  int* tab_contact = nullptr;
+  int tab_rows = 0, tab_contact_rows = 0, tab_schedule_offset = 0;
+  int *t_idx = nullptr, *step_ctr = nullptr;
+  double* plant_next = nullptr;
+  std::vector<void*> table_allocs;
+  // CUDA graphs of one step: [0] resident warm, [1] resident cold, [2] closed loop (without logs), [3] closed loop (with logs)
+  cudaGraphExec_t graph[4] = {nullptr, nullptr, nullptr, nullptr};
+  int graph_launches[4] = {0, 0, 0, 0};
+  double *log_cost = nullptr, *log_u = nullptr; int* log_iters = nullptr; int log_capacity = 0;
 };
 
 template <class T> static cudaError_t dalloc(H1Ilqr* h, T** p, size_t n) {
@@ -71,6 +82,9 @@ template <class T> static cudaError_t dalloc(H1Ilqr* h, T** p, size_t n) {
   return e;
 }
 
+static void invalidate_graphs(H1Ilqr* h) {   // pointers / flags baked into a captured step changed
+  for (auto& g : h->graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+}
 static RefTable ref_table(const H1Ilqr* h) {
   RefTable r;
   r.x_ref = h->x_ref; r.u_ref = h->u_ref; r.com_ref = h->com_ref; r.ee_ref = h->ee_ref;
@@ -96,6 +110,8 @@ void h1ilqr_destroy(H1Ilqr* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto& g : h->graph) if (g) cudaGraphExecDestroy(g);
+  for (void* p : h->table_allocs) cudaFree(p);
   for (void* p : h->allocs) cudaFree(p);
   if (h->pin) cudaFreeHost(h->pin);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -157,6 +173,7 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   CUH(dalloc(h, &h->warm_mask, B)); CUH(dalloc(h, &h->act_list, B)); CUH(dalloc(h, &h->sec_list, B)); CUH(dalloc(h, &h->list_count, 4));
   CUH(dalloc(h, &h->early, B)); CUH(dalloc(h, &h->late, B)); CUH(dalloc(h, &h->early_list, B)); CUH(dalloc(h, &h->late_list, B)); CUH(dalloc(h, &h->cold_mask, B)); CUH(dalloc(h, &h->warm_in, B));
   CUH(dalloc(h, &h->pf, B * N));
+  CUH(dalloc(h, &h->t_idx, B)); CUH(dalloc(h, &h->step_ctr, 1)); CUH(dalloc(h, &h->plant_next, B * NX));
   CUH(dalloc(h, &h->cost_trace, B * h->opt.max_iterations)); CUH(dalloc(h, &h->alpha_trace, B * h->opt.max_iterations * 2));
   h->scratch_bytes = B * N1 * (NX + NU + NX + NV + 9) * sizeof(double);
   { double* sp = nullptr; CUH(dalloc(h, &sp, h->scratch_bytes / sizeof(double))); h->scratch = sp; }
@@ -233,6 +250,7 @@ int h1ilqr_set_reference_window(H1Ilqr* h, const double* x_ref, const double* u_
   GUARD(h);
   if (!x_ref || !u_ref || !com_ref || !ee_ref || !stance) return set_err(H1ILQR_EARG, "null reference array");
   const size_t n = shared ? 1 : h->B, N1 = h->N + 1, N = h->N;
+  if (h->ref_shared != (shared ? 1 : 0)) invalidate_graphs(h);   // the flag is a kernel argument of a captured step
   h->ref_shared = shared ? 1 : 0;
   H2D(h->x_ref, x_ref, n * N1 * NX * sizeof(double)); H2D(h->u_ref, u_ref, n * N * NU * sizeof(double));
   H2D(h->com_ref, com_ref, n * N1 * 3 * sizeof(double)); H2D(h->ee_ref, ee_ref, n * N1 * 6 * sizeof(double));
@@ -541,25 +559,160 @@ int h1ilqr_upload_inputs(H1Ilqr* h, const double* x_measured, const double* u_in
   return 0;
 }
 
-int h1ilqr_run_resident_steps(H1Ilqr* h, int steps, int cold_each_step, double* elapsed_ms) {
+// ---- one MPC step as a launch sequence (directly on the stream, or captured once into a CUDA graph) ----
+static void enqueue_resident_step(H1Ilqr* h, bool cold) {
+  if (cold) {
+    k_fill_int<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->B, h->has_prev, 0);
+    k_fill_double<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->B, h->lambda, h->opt.reg_init);
+    h->launches += 2;
+  }
+  enqueue_initialize(h, nullptr, 0);
+  enqueue_solve(h);
+  enqueue_mpc_tail(h);
+}
+static RefTables ref_tables(const H1Ilqr* h) {
+  RefTables tb;
+  tb.x = h->tab_x; tb.com = h->tab_com; tb.ee = h->tab_ee; tb.cv = h->tab_cv; tb.contact = h->tab_contact;
+  tb.rows = h->tab_rows; tb.contact_rows = h->tab_contact_rows; tb.schedule_offset = h->tab_schedule_offset;
+  return tb;
+}
+// closed-loop step: window at t_idx -> MPC step (warm start from the previous solution) -> plant x <- f_D(x, u_apply) -> t_idx++
+static void enqueue_closed_loop_step(H1Ilqr* h, bool logs) {
+  const long nw = (long)h->B * (h->N + 1);
+  k_extract_window<<<(unsigned)((nw + 127) / 128), 128, 0, h->stream>>>(ref_tables(h), h->B, h->N, h->t_idx, h->x_ref, h->com_ref,
+                                                                      h->ee_ref, h->com_vel_ref, h->stance);
+  LAUNCHED();
+  enqueue_resident_step(h, false);
+  k_dyn_step<<<(h->B + 3) / 4, 128, h->smem_dyn4, h->stream>>>(h->d_dyn, h->B, h->x0, h->u_apply, h->plant_next);
+  cudaMemcpyAsync(h->x0, h->plant_next, (size_t)h->B * NX * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+  k_closed_loop_advance<<<(h->B + 127) / 128, 128, 0, h->stream>>>(h->B, h->t_idx, h->step_ctr, h->cost, h->iters, h->u_apply,
+                                                                  logs ? h->log_cost : nullptr, logs ? h->log_iters : nullptr,
+                                                                  logs ? h->log_u : nullptr);
+  k_increment<<<1, 1, 0, h->stream>>>(h->step_ctr);
+  h->launches += 3;
+}
+// Capture `which` (0 resident warm, 1 resident cold, 2 closed loop, 3 closed loop with logs) once; the launch sequence of a
+// step is the same for every step (iteration counts are handled on the device by the compact instance lists), so the
+// graph is replayed unchanged. Both streams of the pipelined solve are part of the capture (fork / join events).
+static int ensure_graph(H1Ilqr* h, int which) {
+  if (h->graph[which]) return 0;
+  const int l0 = h->launches;
+  cudaGraph_t g = nullptr;
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  if (which < 2) enqueue_resident_step(h, which == 1); else enqueue_closed_loop_step(h, which == 3);
+  cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+  h->graph_launches[which] = h->launches - l0;
+  h->launches = l0;
+  if (e != cudaSuccess) return set_err(H1ILQR_ECUDA, "cudaStreamEndCapture", e);
+  e = cudaGraphInstantiate(&h->graph[which], g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) { h->graph[which] = nullptr; return set_err(H1ILQR_ECUDA, "cudaGraphInstantiate", e); }
+  return 0;
+}
+
+int h1ilqr_set_reference_table(H1Ilqr* h, int rows, const double* x_ref_full, const double* com_ref_full,
+                               const double* ee_ref_full, const double* com_vel_ref_full, int contact_rows,
+                               const int* contact, int schedule_offset) {
+  GUARD(h);
+  if (rows < 1 || !x_ref_full || !com_ref_full || !ee_ref_full || contact_rows < 0 || (contact_rows > 0 && !contact))
+    return set_err(H1ILQR_EARG, "h1ilqr_set_reference_table: bad arguments");
+  // getEEReference / getCoMVelReference throw past the table (robot_utils.cpp:525-549): the horizon-local lookups need N + 1 rows
+  if (!schedule_offset && rows < h->N + 1) return set_err(H1ILQR_EARG, "Invalid reference index: the table has fewer than N + 1 rows");
+  invalidate_graphs(h);
+  for (void* p : h->table_allocs) cudaFree(p);
+  h->table_allocs.clear();
+  auto up = [&](const void* src, size_t bytes, void** dst) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, bytes ? bytes : 8);
+    if (e != cudaSuccess) return e;
+    h->table_allocs.push_back(*dst);
+    if (src) return cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, h->stream);
+    return cudaMemsetAsync(*dst, 0, bytes ? bytes : 8, h->stream);
+  };
+  CU(up(x_ref_full, (size_t)rows * NX * sizeof(double), (void**)&h->tab_x));
+  CU(up(com_ref_full, (size_t)rows * 3 * sizeof(double), (void**)&h->tab_com));
+  CU(up(ee_ref_full, (size_t)rows * 6 * sizeof(double), (void**)&h->tab_ee));
+  CU(up(com_vel_ref_full, (size_t)rows * 3 * sizeof(double), (void**)&h->tab_cv));   // NULL: zeros (only read when W_com_vel > 0)
+  CU(up(contact, (size_t)contact_rows * 2 * sizeof(int), (void**)&h->tab_contact));
+  h->tab_rows = rows; h->tab_contact_rows = contact_rows; h->tab_schedule_offset = schedule_offset ? 1 : 0;
+  SYNC();
+  return 0;
+}
+
+int h1ilqr_run_closed_loop(H1Ilqr* h, int steps, const int* t_idx0, const double* x_start, const double* u_init,
+                           int u_init_shared, int use_graph, double* x_final, double* cost_log, int* iters_log,
+                           double* u_log, double* elapsed_ms) {
   GUARD(h);
   if (steps < 1) return set_err(H1ILQR_EARG, "steps < 1");
+  if (!h->tab_x) return set_err(H1ILQR_EARG, "h1ilqr_run_closed_loop: no reference table (h1ilqr_set_reference_table)");
+  const size_t B = h->B;
+  int rc = 0;
+  if (x_start && (rc = h1ilqr_upload_inputs(h, x_start, u_init, u_init_shared))) return rc;
+  if (t_idx0) H2D(h->t_idx, t_idx0, B * sizeof(int));
+  const bool logs = cost_log || iters_log || u_log;
+  if (logs && h->log_capacity < steps) {
+    invalidate_graphs(h);
+    if (h->log_cost) { cudaFree(h->log_cost); cudaFree(h->log_iters); cudaFree(h->log_u); }
+    CU(cudaMalloc((void**)&h->log_cost, (size_t)steps * B * sizeof(double)));
+    CU(cudaMalloc((void**)&h->log_iters, (size_t)steps * B * sizeof(int)));
+    CU(cudaMalloc((void**)&h->log_u, (size_t)steps * B * NU * sizeof(double)));
+    h->log_capacity = steps;
+  }
+  CU(cudaMemsetAsync(h->step_ctr, 0, sizeof(int), h->stream));
+  CU(cudaMemsetAsync(h->u_ref, 0, B * h->N * NU * sizeof(double), h->stream));   // u_ref_full_ is all zeros (robot_utils.cpp:367)
+  if (h->ref_shared) invalidate_graphs(h);
+  h->ref_shared = 0;     // the loop writes per-instance windows
+  const int which = logs ? 3 : 2;
+  const bool timing = h->timing;
+  h->timing = false;
+  if (use_graph && (rc = ensure_graph(h, which))) { h->timing = timing; return rc; }
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
   const int l0 = h->launches;
-  const bool timing = h->timing;
-  h->timing = false;  // stage timing would insert host syncs
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaEventRecord(e0, h->stream));
   for (int s = 0; s < steps; ++s) {
-    if (cold_each_step) {
-      k_fill_int<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->B, h->has_prev, 0);
-      k_fill_double<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->B, h->lambda, h->opt.reg_init);
-      h->launches += 2;
-    }
-    enqueue_initialize(h, nullptr, 0);
-    enqueue_solve(h);
-    enqueue_mpc_tail(h);
+    if (use_graph) { CU(cudaGraphLaunch(h->graph[which], h->stream)); h->launches += h->graph_launches[which]; }
+    else enqueue_closed_loop_step(h, logs);
+  }
+  CU(cudaEventRecord(e1, h->stream));
+  CU(cudaEventSynchronize(e1));
+  CU(cudaGetLastError());
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  h->timing = timing;
+  h->times.launches = h->launches - l0;
+  if (elapsed_ms) *elapsed_ms = ms;
+  if (x_final) D2H(x_final, h->x0, B * NX * sizeof(double));
+  if (cost_log) D2H(cost_log, h->log_cost, (size_t)steps * B * sizeof(double));
+  if (iters_log) D2H(iters_log, h->log_iters, (size_t)steps * B * sizeof(int));
+  if (u_log) D2H(u_log, h->log_u, (size_t)steps * B * NU * sizeof(double));
+  std::vector<int> st(B);
+  D2H(st.data(), h->status, B * sizeof(int));
+  SYNC();
+  int bad = 0;
+  for (size_t i = 0; i < B; ++i) bad |= st[i];
+  if (bad) return set_err(H1ILQR_ENOTFINITE, "non-finite cost or gains in at least one instance at the last step");
+  return 0;
+}
+
+int h1ilqr_run_resident_steps(H1Ilqr* h, int steps, int cold_each_step, double* elapsed_ms) {
+  GUARD(h);
+  if (steps < 1) return set_err(H1ILQR_EARG, "steps < 1");
+  const bool use_graph = (cold_each_step & 2) != 0;   // bit 1: replay the step as a CUDA graph
+  cold_each_step &= 1;
+  const bool timing = h->timing;
+  h->timing = false;  // stage timing would insert host syncs
+  if (use_graph) { int rc = ensure_graph(h, cold_each_step); if (rc) { h->timing = timing; return rc; } }
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  const int l0 = h->launches;
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaEventRecord(e0, h->stream));
+  for (int s = 0; s < steps; ++s) {
+    if (use_graph) { CU(cudaGraphLaunch(h->graph[cold_each_step], h->stream)); h->launches += h->graph_launches[cold_each_step]; }
+    else enqueue_resident_step(h, cold_each_step != 0);
   }
   CU(cudaEventRecord(e1, h->stream));
   CU(cudaEventSynchronize(e1));
@@ -904,6 +1057,7 @@ int h1ilqr_get_solve_trace(H1Ilqr* h, double* cost_trace, int* alpha_trace) {
 int h1ilqr_set_kernel_policy(H1Ilqr* h, int policy) {
   GUARD(h);
   if (policy < H1ILQR_KERNELS_AUTO || policy > H1ILQR_KERNELS_BATCHED) return set_err(H1ILQR_EARG, "bad kernel policy");
+  if (h->policy != policy) invalidate_graphs(h);
   h->policy = policy;
   return 0;
 }

@@ -23,7 +23,7 @@ EXPORTS = [
     "h1ilqr_reference_kinematics", "h1ilqr_reference_com_velocity", "h1ilqr_get_status", "h1ilqr_sole_points", "h1ilqr_set_trajectory", "h1ilqr_get_trajectory", "h1ilqr_get_gains",
     "h1ilqr_set_gains", "h1ilqr_get_linearization", "h1ilqr_set_linearization", "h1ilqr_get_cost_quadratics",
     "h1ilqr_set_cost_quadratics", "h1ilqr_set_previous_solution", "h1ilqr_get_previous_solution", "h1ilqr_get_regularization", "h1ilqr_set_regularization", "h1ilqr_get_solve_trace",
-    "h1ilqr_upload_inputs", "h1ilqr_host_register", "h1ilqr_host_unregister", "h1ilqr_run_resident_steps", "h1ilqr_time_stage", "h1ilqr_measure_fp64_peak", "h1ilqr_measure_fp64_mma_peak", "h1ilqr_enable_stage_timing", "h1ilqr_set_kernel_policy", "h1ilqr_get_stage_times", "h1ilqr_stream", "h1_default_dynamics_model",
+    "h1ilqr_upload_inputs", "h1ilqr_host_register", "h1ilqr_host_unregister", "h1ilqr_run_resident_steps", "h1ilqr_time_stage", "h1ilqr_set_reference_table", "h1ilqr_run_closed_loop", "h1ilqr_measure_fp64_peak", "h1ilqr_measure_fp64_mma_peak", "h1ilqr_enable_stage_timing", "h1ilqr_set_kernel_policy", "h1ilqr_get_stage_times", "h1ilqr_stream", "h1_default_dynamics_model",
     "h1_default_cost_model",
 ]
 
@@ -314,11 +314,41 @@ class H1IlqrBatch:
             shared = int(u_init.size == NU)
         _check(lib().h1ilqr_upload_inputs(self._h, dptr(x), dptr(u_init), C.c_int(shared)))
 
-    def run_resident_steps(self, steps, cold_each_step=True):
-        """`steps` MPC steps with inputs already on the device; returns CUDA-event milliseconds on the handle's stream."""
+    def run_resident_steps(self, steps, cold_each_step=True, graph=False):
+        """`steps` MPC steps with inputs already on the device; returns CUDA-event milliseconds on the handle's stream.
+        graph: capture the step once into a CUDA graph and replay it."""
         ms = C.c_double()
-        _check(lib().h1ilqr_run_resident_steps(self._h, C.c_int(steps), C.c_int(int(cold_each_step)), C.byref(ms)))
+        _check(lib().h1ilqr_run_resident_steps(self._h, C.c_int(steps), C.c_int(int(bool(cold_each_step)) | (2 if graph else 0)),
+                                               C.byref(ms)))
         return ms.value
+
+    def set_reference_table(self, refs, schedule_offset=False):
+        """Upload a ReferenceSet's full tables for the device-resident closed loop."""
+        x = _f(refs.x_ref_full); com = _f(refs.com_ref_full); ee = _f(refs.ee_pos_ref_full).reshape(-1, 6)
+        cv = _f(refs.com_vel_ref_full)
+        ct = np.ascontiguousarray(refs.contact, dtype=np.int32).reshape(-1, 2)
+        _check(lib().h1ilqr_set_reference_table(self._h, C.c_int(x.shape[0]), dptr(x), dptr(com), dptr(ee), dptr(cv),
+                                                C.c_int(ct.shape[0]), iptr(ct), C.c_int(int(schedule_offset))))
+
+    def run_closed_loop(self, steps, t_idx0=None, x_start=None, u_init=None, graph=True, logs=True):
+        """`steps` closed-loop MPC steps of every instance on the device (plant = f_D). Returns a dict with x_final,
+        cost / iters / u logs (when `logs`) and the CUDA-event milliseconds of the whole loop."""
+        t0 = np.ascontiguousarray(np.broadcast_to(np.asarray(t_idx0, dtype=np.int32), (self.B,))) if t_idx0 is not None else None
+        xs = _f(x_start).reshape(self.B, NX) if x_start is not None else None
+        shared = 1
+        if u_init is not None:
+            u_init = _f(u_init)
+            shared = int(u_init.size == NU)
+        xf = np.empty((self.B, NX))
+        cl = np.empty((steps, self.B)) if logs else None
+        il = np.empty((steps, self.B), dtype=np.int32) if logs else None
+        ul = np.empty((steps, self.B, NU)) if logs else None
+        ms = C.c_double()
+        rc = lib().h1ilqr_run_closed_loop(self._h, C.c_int(steps), iptr(t0), dptr(xs), dptr(u_init), C.c_int(shared),
+                                          C.c_int(int(graph)), dptr(xf), dptr(cl), iptr(il), dptr(ul), C.byref(ms))
+        if rc not in (0, -3):
+            _check(rc)
+        return {"x_final": xf, "cost": cl, "iters": il, "u": ul, "ms": ms.value, "rc": rc}
 
     STAGES = {"factor": 0, "linearize": 1, "cost_quadratics": 2, "backward": 3, "line_search": 4}
 
