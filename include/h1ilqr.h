@@ -156,6 +156,23 @@ int h1ilqr_reference_kinematics(H1Ilqr* h, int n, const double* x, double* com, 
  * J_subtreeCom(root) * qvel of RobotUtils::loadReferences (robot_utils.cpp:388-397), tracked by
  * addCoMVelCostDerivatives when W_com_vel > 0 (ilqr.cpp:675-695). com_vel [n][3]. */
 int h1ilqr_reference_com_velocity(H1Ilqr* h, int n, const double* x, double* com_vel);
+/* World velocity of the two ankle-body origins: the ee_vel_ref rows jac_pos * qvel of RobotUtils::loadReferences
+ * (robot_utils.cpp:405-412; RobotUtils::getEEVelReference). ee_vel [n][2][3]. */
+int h1ilqr_reference_ee_velocity(H1Ilqr* h, int n, const double* x, double* ee_vel);
+/* One (x, u) pair linearized on its own: RobotUtils::linearizeDynamicsFD (robot_utils.cpp:120-160, include/common/
+ * robot_utils.hpp:51-53) for mode == H1ILQR_LIN_FD (forward differences with step eps), the exact Jacobians of f_D for
+ * H1ILQR_LIN_ANALYTIC. A [51 x 51], B [51 x 19] column-major. The solver state of the handle is not touched. */
+int h1ilqr_linearize_state(H1Ilqr* h, int mode, double eps, const double* x, const double* u, double* A, double* B);
+/* RobotUtils::constraintCost / constraintGradients / constraintHessians (robot_utils.cpp:615-778) for n (x, u) pairs
+ * (u == NULL: joint-limit terms only, the terminal form of robot_utils.cpp:226-250). Outputs, any may be NULL: cost [n],
+ * grad_x [n][51], grad_u [n][19], and the DIAGONALS of the diagonal Hessians, hess_xx_diag [n][51], hess_uu_diag [n][19]. */
+int h1ilqr_limit_penalties(H1Ilqr* h, int n, const double* x, const double* u, double* cost, double* grad_x, double* grad_u,
+                           double* hess_xx_diag, double* hess_uu_diag);
+/* RobotUtils::stageCost (u != NULL) / terminalCost (u == NULL), robot_utils.cpp:162-252: 0.5 e'Qe + 0.5 eu'R eu +
+ * 0.5 W_com |com(x) - com_ref|^2 + limit penalties, for n states against the reference rows x_ref [n][51], u_ref [n][19]
+ * (NULL = zeros), com_ref [n][3] (NULL = no CoM term), with the handle's diagonal Q / R / Qf. cost [n]. */
+int h1ilqr_stage_cost(H1Ilqr* h, int n, const double* x, const double* u, const double* x_ref, const double* u_ref,
+                      const double* com_ref, double* cost);
 /* World positions of the 2 x 4 sole contact points of f_D for arbitrary states, pts [n][8][3] (left foot first).
  * Input of the contact-schedule generation that replaces get_contacts.py:96-157 (MuJoCo foot-geom contacts with
  * dist < 1e-3): a foot is in stance when one of its sole points is lower than the threshold. */

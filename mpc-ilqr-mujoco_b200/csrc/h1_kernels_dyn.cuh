@@ -35,7 +35,7 @@ __global__ void k_dyn_step(const DynModel* gmd, int n, const double* __restrict_
 //      (computeGravComp, loadReferences' per-row FK, contact-schedule generation) ----
 __global__ void k_dyn_query(const DynModel* gmd, int n, const double* __restrict__ x, double* __restrict__ bias,
                             double* __restrict__ com, double* __restrict__ ee, double* __restrict__ sole,
-                            double* __restrict__ comvel) {
+                            double* __restrict__ comvel, double* __restrict__ eevel) {
   extern __shared__ __align__(16) unsigned char smem[];
   const DynModel* md;
   unsigned char* p = stage_model(smem, gmd, &md);
@@ -71,6 +71,87 @@ __global__ void k_dyn_query(const DynModel* gmd, int n, const double* __restrict
     for (int c = 0; c < 3; ++c) p[c] = warp_sum(p[c]);
     if (lane < 3) comvel[(size_t)i * 3 + lane] = p[lane] / m;
   }
+  if (eevel && lane < H1_NFOOT) {
+    // world velocity of the ankle body origin = jac_pos * qvel of RobotUtils::loadReferences (robot_utils.cpp:405-412):
+    // spatial velocity of the foot body about the base origin, v = v_O + omega x r_foot
+    const int j = md->foot_dof[lane], ns = md->nlist[j];
+    double V[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int s = 0; s < ns; ++s) {
+      const int k = md->alist[j][s];
+      for (int c = 0; c < 6; ++c) V[c] += w.S[k][c] * w.v[k];
+    }
+    double wr[3];
+    cross3(V, w.footr[lane], wr);
+    for (int c = 0; c < 3; ++c) eevel[((size_t)i * H1_NFOOT + lane) * 3 + c] = V[3 + c] + wr[c];
+  }
+}
+
+// ---- soft limit penalties of arbitrary (x, u) pairs with their derivatives: RobotUtils::constraintCost /
+//      constraintGradients / constraintHessians (robot_utils.cpp:615-778). One thread per pair; u == nullptr: no control
+//      terms (the terminal-knot form of terminalCost, robot_utils.cpp:226-250). Outputs may be nullptr. ----
+__global__ void k_limit_penalties(const DynModel* gmd, const H1Weights* gw, int n, const double* __restrict__ x,
+                                  const double* __restrict__ u, double* __restrict__ cost, double* __restrict__ gx,
+                                  double* __restrict__ gu, double* __restrict__ hxx, double* __restrict__ huu) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const DynModel& md = *gmd;
+  double c = 0.0;
+  if (gx) for (int k = 0; k < NX; ++k) gx[(size_t)i * NX + k] = 0.0;
+  if (hxx) for (int k = 0; k < NX; ++k) hxx[(size_t)i * NX + k] = 0.0;
+  auto pen = [&](double val, double lo, double hi, double wgt, double* g, double* hh) {
+    const double margin = 0.1 * (hi - lo), lo_s = lo + margin, hi_s = hi - margin;
+    double gg = 0.0, h2 = 0.0;
+    if (val > hi_s) { const double viol = val - hi_s; c += wgt * viol * viol; gg += 2.0 * wgt * viol; }
+    if (val < lo_s) { const double viol = lo_s - val; c += wgt * viol * viol; gg += -2.0 * wgt * viol; }
+    if (val > hi_s || val < lo_s) h2 = 2.0 * wgt;
+    if (g) *g = gg;
+    if (hh) *hh = h2;
+  };
+  for (int k = 0; k < NU; ++k) {
+    if (u) pen(u[(size_t)i * NU + k], md.ctrl_lo[k], md.ctrl_hi[k], gw->w_control_limits, gu ? gu + (size_t)i * NU + k : nullptr,
+               huu ? huu + (size_t)i * NU + k : nullptr);
+    const double lo = md.jnt_lo[k], hi = md.jnt_hi[k];
+    if (isfinite(lo) && isfinite(hi) && lo < hi)
+      pen(x[(size_t)i * NX + 7 + k], lo, hi, gw->w_joint_limits, gx ? gx + (size_t)i * NX + 7 + k : nullptr,
+          hxx ? hxx + (size_t)i * NX + 7 + k : nullptr);
+  }
+  if (cost) cost[i] = c;
+}
+
+// ---- RobotUtils::stageCost / terminalCost (robot_utils.cpp:162-252): 0.5 e'Qe + 0.5 eu'R eu + 0.5 w_com |com - com_ref|^2
+//      + limit penalties for arbitrary states against given reference rows (diagonal Q / R / Qf). One warp per state;
+//      u == nullptr: terminal form (Qf, joint limits only). ----
+__global__ void k_stage_cost(const DynModel* gmd, const H1Weights* gw, int n, const double* __restrict__ x,
+                             const double* __restrict__ u, const double* __restrict__ x_ref, const double* __restrict__ u_ref,
+                             const double* __restrict__ com_ref, double* __restrict__ cost) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const DynModel* md;
+  unsigned char* p = stage_model(smem, gmd, &md);
+  DynWarp& w = reinterpret_cast<DynWarp*>(p)[threadIdx.x >> 5];
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int lane = threadIdx.x & 31;
+  const bool terminal = u == nullptr;
+  dyn_assemble_warp(*md, w, x + (size_t)i * NX, nullptr);
+  const double* Qd = terminal ? gw->Qfdiag : gw->Qdiag;
+  double acc = 0.0;
+  for (int k = lane; k < NX; k += 32) { const double e = x[(size_t)i * NX + k] - x_ref[(size_t)i * NX + k]; acc += 0.5 * e * Qd[k] * e; }
+  if (lane < NU) {
+    if (!terminal) {
+      const double uv = u[(size_t)i * NU + lane];
+      const double e = uv - (u_ref ? u_ref[(size_t)i * NU + lane] : 0.0);
+      acc += 0.5 * e * gw->Rdiag[lane] * e;
+      acc += limit_pen(uv, md->ctrl_lo[lane], md->ctrl_hi[lane], gw->w_control_limits);
+    }
+    const double lo = md->jnt_lo[lane], hi = md->jnt_hi[lane];
+    if (isfinite(lo) && isfinite(hi) && lo < hi) acc += limit_pen(x[(size_t)i * NX + 7 + lane], lo, hi, gw->w_joint_limits);
+  }
+  if (lane < 3 && gw->w_com > 0.0 && com_ref) {
+    const double e = w.com[lane] - com_ref[(size_t)i * 3 + lane];
+    acc += 0.5 * gw->w_com * e * e;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) cost[i] = acc;
 }
 
 // ---- nominal rollout xbar[t+1] = f_D(xbar[t], ubar[t]) with the trajectory cost as a by-product

@@ -211,6 +211,7 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   CUH(cudaFuncSetAttribute(k_rollout_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_seq));
   CUH(cudaFuncSetAttribute(k_dyn_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
   CUH(cudaFuncSetAttribute(k_dyn_query, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
+  CUH(cudaFuncSetAttribute(k_stage_cost, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
   CUH(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
   CUH(cudaFuncSetAttribute(k_primal_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
   CUH(cudaFuncSetAttribute(k_linearize_fd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_lin));
@@ -954,17 +955,19 @@ int h1ilqr_dynamics_step(H1Ilqr* h, int n, const double* x, const double* u, dou
 }
 
 static int query(H1Ilqr* h, int n, const double* x, double* bias, double* com, double* ee, double* sole = nullptr,
-                 double* comvel = nullptr) {
+                 double* comvel = nullptr, double* eevel = nullptr) {
   if (n < 1 || !x) return set_err(H1ILQR_EARG, "bad query arguments");
-  int rc = ensure_scratch(h, (size_t)n * (NX + NV + 12 + 3 * NCPT) * sizeof(double));
+  int rc = ensure_scratch(h, (size_t)n * (NX + NV + 18 + 3 * NCPT) * sizeof(double));
   if (rc) return rc;
   double* dx = h->scratch; double* db = dx + (size_t)n * NX; double* dc = db + (size_t)n * NV; double* de = dc + (size_t)n * 3;
-  double* ds = de + (size_t)n * 6; double* dv = ds + (size_t)n * 3 * NCPT;
+  double* ds = de + (size_t)n * 6; double* dv = ds + (size_t)n * 3 * NCPT; double* dw = dv + (size_t)n * 3;
   H2D(dx, x, (size_t)n * NX * sizeof(double));
   k_dyn_query<<<(n + 3) / 4, 128, h->smem_dyn4, h->stream>>>(h->d_dyn, n, dx, bias ? db : nullptr, com ? dc : nullptr,
-                                                            ee ? de : nullptr, sole ? ds : nullptr, comvel ? dv : nullptr);
+                                                            ee ? de : nullptr, sole ? ds : nullptr, comvel ? dv : nullptr,
+                                                            eevel ? dw : nullptr);
   LAUNCHED();
   if (comvel) D2H(comvel, dv, (size_t)n * 3 * sizeof(double));
+  if (eevel) D2H(eevel, dw, (size_t)n * 6 * sizeof(double));
   if (bias) D2H(bias, db, (size_t)n * NV * sizeof(double));
   if (com) D2H(com, dc, (size_t)n * 3 * sizeof(double));
   if (ee) D2H(ee, de, (size_t)n * 6 * sizeof(double));
@@ -979,6 +982,85 @@ int h1ilqr_reference_com_velocity(H1Ilqr* h, int n, const double* x, double* com
   if (!com_vel) return set_err(H1ILQR_EARG, "null com_vel");
   return query(h, n, x, nullptr, nullptr, nullptr, nullptr, com_vel);
 }
+int h1ilqr_reference_ee_velocity(H1Ilqr* h, int n, const double* x, double* ee_vel) {
+  GUARD(h);
+  if (!ee_vel) return set_err(H1ILQR_EARG, "null ee_vel");
+  return query(h, n, x, nullptr, nullptr, nullptr, nullptr, nullptr, ee_vel);
+}
+
+// One (x, u) pair linearized on its own: RobotUtils::linearizeDynamicsFD (robot_utils.cpp:120-160) when mode ==
+// H1ILQR_LIN_FD (forward differences with `eps`), the exact Jacobians of f_D otherwise. Works on scratch buffers: the
+// solver state of the handle is untouched. A [51 x 51], B [51 x 19] column-major.
+int h1ilqr_linearize_state(H1Ilqr* h, int mode, double eps, const double* x, const double* u, double* A, double* B) {
+  GUARD(h);
+  if (!x || !u || !A || !B) return set_err(H1ILQR_EARG, "h1ilqr_linearize_state: null argument");
+  const size_t need = (size_t)(2 * NX + NU + NX * NX + NX * NU) * sizeof(double) + sizeof(PrimalFactor);
+  int rc = ensure_scratch(h, need);
+  if (rc) return rc;
+  double* dx = h->scratch; double* du = dx + 2 * NX; double* dA = du + NU; double* dB = dA + NX * NX;
+  PrimalFactor* pf = reinterpret_cast<PrimalFactor*>(dB + NX * NU);
+  H2D(dx, x, NX * sizeof(double)); H2D(du, u, NU * sizeof(double));
+  if (mode == H1ILQR_LIN_FD) {
+    if (!(eps > 0.0)) return set_err(H1ILQR_EARG, "h1ilqr_linearize_state: eps must be positive");
+    k_linearize_fd<<<1, LIN_WARPS * 32, h->smem_lin, h->stream>>>(h->d_dyn, 1, eps, nullptr, dx, du, dA, dB);
+  } else {
+    k_primal_factor<<<1, 128, h->smem_dyn4, h->stream>>>(h->d_dyn, 1, 1, nullptr, dx, du, pf);
+    k_linearize_analytic<<<1, LINA_WARPS * 32, h->smem_lina, h->stream>>>(h->d_dyn, 1, nullptr, dx, du, pf, dA, dB);
+  }
+  h->launches += 2;
+  D2H(A, dA, (size_t)NX * NX * sizeof(double)); D2H(B, dB, (size_t)NX * NU * sizeof(double));
+  SYNC(); CU(cudaGetLastError());
+  return 0;
+}
+
+// RobotUtils::constraintCost / constraintGradients / constraintHessians (robot_utils.cpp:615-778) for n (x, u) pairs.
+// u == NULL: joint-limit terms only. Outputs (any may be NULL): cost [n], grad_x [n][51], grad_u [n][19], and the DIAGONALS
+// of the (diagonal) Hessians hess_xx [n][51], hess_uu [n][19].
+int h1ilqr_limit_penalties(H1Ilqr* h, int n, const double* x, const double* u, double* cost, double* grad_x, double* grad_u,
+                           double* hess_xx_diag, double* hess_uu_diag) {
+  GUARD(h);
+  if (n < 1 || !x) return set_err(H1ILQR_EARG, "h1ilqr_limit_penalties: bad arguments");
+  int rc = ensure_scratch(h, (size_t)n * (3 * NX + 3 * NU + 1) * sizeof(double));
+  if (rc) return rc;
+  double* dx = h->scratch; double* du = dx + (size_t)n * NX; double* dc = du + (size_t)n * NU; double* dgx = dc + n;
+  double* dgu = dgx + (size_t)n * NX; double* dhx = dgu + (size_t)n * NU; double* dhu = dhx + (size_t)n * NX;
+  H2D(dx, x, (size_t)n * NX * sizeof(double));
+  if (u) H2D(du, u, (size_t)n * NU * sizeof(double));
+  CU(cudaMemsetAsync(dgu, 0, (size_t)n * NU * sizeof(double), h->stream));
+  CU(cudaMemsetAsync(dhu, 0, (size_t)n * NU * sizeof(double), h->stream));
+  k_limit_penalties<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_dyn, h->d_w, n, dx, u ? du : nullptr, dc, dgx, dgu, dhx, dhu);
+  LAUNCHED();
+  if (cost) D2H(cost, dc, (size_t)n * sizeof(double));
+  if (grad_x) D2H(grad_x, dgx, (size_t)n * NX * sizeof(double));
+  if (grad_u) D2H(grad_u, dgu, (size_t)n * NU * sizeof(double));
+  if (hess_xx_diag) D2H(hess_xx_diag, dhx, (size_t)n * NX * sizeof(double));
+  if (hess_uu_diag) D2H(hess_uu_diag, dhu, (size_t)n * NU * sizeof(double));
+  SYNC(); CU(cudaGetLastError());
+  return 0;
+}
+
+// RobotUtils::stageCost (u != NULL) / terminalCost (u == NULL) (robot_utils.cpp:162-252) of n states against the given
+// reference rows x_ref [n][51], u_ref [n][19] (NULL = zeros), com_ref [n][3] (NULL: no CoM term); cost [n].
+int h1ilqr_stage_cost(H1Ilqr* h, int n, const double* x, const double* u, const double* x_ref, const double* u_ref,
+                      const double* com_ref, double* cost) {
+  GUARD(h);
+  if (n < 1 || !x || !x_ref || !cost) return set_err(H1ILQR_EARG, "h1ilqr_stage_cost: bad arguments");
+  int rc = ensure_scratch(h, (size_t)n * (2 * NX + 2 * NU + 4) * sizeof(double));
+  if (rc) return rc;
+  double* dx = h->scratch; double* du = dx + (size_t)n * NX; double* dxr = du + (size_t)n * NU; double* dur = dxr + (size_t)n * NX;
+  double* dcr = dur + (size_t)n * NU; double* dc = dcr + (size_t)n * 3;
+  H2D(dx, x, (size_t)n * NX * sizeof(double)); H2D(dxr, x_ref, (size_t)n * NX * sizeof(double));
+  if (u) H2D(du, u, (size_t)n * NU * sizeof(double));
+  if (u_ref) H2D(dur, u_ref, (size_t)n * NU * sizeof(double));
+  if (com_ref) H2D(dcr, com_ref, (size_t)n * 3 * sizeof(double));
+  k_stage_cost<<<(n + 3) / 4, 128, h->smem_dyn4, h->stream>>>(h->d_dyn, h->d_w, n, dx, u ? du : nullptr, dxr, u_ref ? dur : nullptr,
+                                                             com_ref ? dcr : nullptr, dc);
+  LAUNCHED();
+  D2H(cost, dc, (size_t)n * sizeof(double));
+  SYNC(); CU(cudaGetLastError());
+  return 0;
+}
+
 int h1ilqr_sole_points(H1Ilqr* h, int n, const double* x, double* pts) {
   GUARD(h);
   if (!pts) return set_err(H1ILQR_EARG, "null pts");

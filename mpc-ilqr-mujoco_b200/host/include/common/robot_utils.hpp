@@ -36,6 +36,16 @@ class RobotUtils {
   void setControl(const Eigen::VectorXd& u);
   void step();
   void rolloutOneStep(const Eigen::VectorXd& x, const Eigen::VectorXd& u, Eigen::VectorXd& x_next);
+  void linearizeDynamicsFD(const Eigen::VectorXd& x, const Eigen::VectorXd& u, Eigen::MatrixXd& A, Eigen::MatrixXd& B,
+                           double eps = 1e-5);
+
+  double stageCost(int t, const Eigen::VectorXd& x, const Eigen::VectorXd& u) const;
+  double terminalCost(const Eigen::VectorXd& x) const;
+  double constraintCost(const Eigen::VectorXd& x, const Eigen::VectorXd& u) const;
+  void constraintGradients(const Eigen::VectorXd& x, const Eigen::VectorXd& u, Eigen::VectorXd& grad_x,
+                           Eigen::VectorXd& grad_u) const;
+  void constraintHessians(const Eigen::VectorXd& x, const Eigen::VectorXd& u, Eigen::MatrixXd& hess_xx,
+                          Eigen::MatrixXd& hess_uu) const;
 
   void setCostWeights(const Eigen::MatrixXd& Q, const Eigen::MatrixXd& R, const Eigen::MatrixXd& Qf);
   void setCoMWeight(double w) { w_com_ = w; }
@@ -57,9 +67,13 @@ class RobotUtils {
                           std::vector<Eigen::VectorXd>& u_ref_window, std::vector<Eigen::Vector3d>& com_ref_window) const;
   bool loadContactSchedule(const std::string& contact_path);
   bool isStance(int ee_idx, int t) const;
+  int jointId(const std::string& name) const;
   std::string getEEFrameName(int ee_idx) const;
   Eigen::Vector3d getEEReference(int t, int ee_idx) const;
+  Eigen::Vector3d getEEVelReference(int t, int ee_idx) const;
   Eigen::Vector3d getCoMVelReference(int t) const;
+  void resetToReference(int t);
+  void scaleRobotMass(double scale_factor);
   Eigen::Vector3d computeCoM(const Eigen::VectorXd& x) const;
   void initializeStandingPose();
   void computeGravComp(Eigen::VectorXd& ugrav) const;
@@ -70,6 +84,7 @@ class RobotUtils {
   // ---- used by the iLQR / MPC shims (not part of the reference API) ----
   H1Ilqr* query_handle() const { return query_; }                 // batch-1 handle for plant / FK queries
   const H1Model& dynamics_model() const { return dyn_model_; }
+  int model_version() const { return model_version_; }            // bumped by setTimeStep / setGravity / scaleRobotMass
   H1Weights weights() const;                                      // current Q/R/Qf diagonals + task weights
   bool weights_are_diagonal() const { return diag_ok_; }
   int reference_rows() const { return static_cast<int>(x_ref_full_.size()); }
@@ -77,8 +92,10 @@ class RobotUtils {
   void refresh_bias();                                            // data_.qfrc_bias <- GPU
 
  private:
-  bool ensure_query();
+  bool ensure_query() const;
+  void model_changed();
   bool loaded_;
+  int model_version_;
   int nx_, nu_;
   double dt_;
   H1Model dyn_model_;
@@ -91,6 +108,6 @@ class RobotUtils {
   double w_com_, w_com_vel_, w_ee_pos_, w_ee_vel_, w_joint_limits_, w_control_limits_, w_upright_, w_balance_;
   std::vector<Eigen::VectorXd> x_ref_full_, u_ref_full_;
   std::vector<Eigen::Vector3d> com_ref_full_, com_vel_ref_full_;
-  std::vector<std::vector<Eigen::Vector3d>> ee_pos_ref_full_;
+  std::vector<std::vector<Eigen::Vector3d>> ee_pos_ref_full_, ee_vel_ref_full_;
   std::vector<std::vector<int>> contact_schedule_;
 };

@@ -32,6 +32,7 @@ class iLQR {
 
  private:
   bool recreate();
+  void sync_model();
   bool upload_window(const std::vector<Eigen::VectorXd>& x_ref, const std::vector<Eigen::VectorXd>& u_ref,
                      const std::vector<Eigen::Vector3d>& com_ref);
   void download_solution();
@@ -40,6 +41,7 @@ class iLQR {
   double dt_;
   H1SolverOptions opt_;
   H1Ilqr* h_;
+  int model_version_ = -1;
   std::vector<Eigen::VectorXd> xbar_, ubar_, kff_;
   std::vector<Eigen::MatrixXd> K_;
 };

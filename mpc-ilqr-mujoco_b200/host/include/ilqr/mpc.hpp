@@ -12,6 +12,9 @@ class MPC {
   void reset();
   void setTimeIndex(int t_idx) { t_idx_ = t_idx; }
   int getTimeIndex() const { return t_idx_; }
+  void enableCSVLogging(const std::string& filename);
+  void logCurrentStep(const Eigen::VectorXd& x_measured, const Eigen::VectorXd& u_applied);
+  void finalizeCSVLog();
   void enableOptimalTrajectoryLogging(const std::string& base_path);
   void logAppliedOptimal(const Eigen::VectorXd& x_applied, const Eigen::VectorXd& u_applied);
   void finalizeOptimalTrajectoryLog();
@@ -36,4 +39,6 @@ class MPC {
   double last_solve_cost_, last_solve_time_ms_;
   std::string trajectory_base_path_;
   std::ofstream q_optimal_file_, u_optimal_file_;
+  std::ofstream csv_file_;
+  std::string csv_filename_;
 };

@@ -1,9 +1,13 @@
 // Closed-loop demo on the host API: the same sequence of calls the reference's main/humanoid_mpc.cpp makes
 // (load config -> set up RobotUtils -> MPC -> loop getState / stepOnce / setControl / step), written for this
-// repository. Usage: humanoid_mpc_demo [config.yaml] [sim_steps]
+// repository. Usage: humanoid_mpc_demo [config.yaml] [sim_steps] [step_log.csv]
+// With a third argument the wide step CSV (MPC::enableCSVLogging) is written there; q_optimal.csv / u_optimal.csv go to
+// the configured results directory when save_trajectories is set. The last line is machine readable:
+// BENCH_JSON {"step_ms": [...], "cost": [...]} — wall time of every MPC::stepOnce call (host buffers in and out).
 #include <chrono>
 #include <cstdlib>
 #include <iostream>
+#include <vector>
 #include "common/config.hpp"
 #include "common/robot_utils.hpp"
 #include "ilqr/mpc.hpp"
@@ -26,6 +30,9 @@ int main(int argc, char** argv) {
   if (!robot.loadReferences(config.q_ref_path, config.v_ref_path)) { std::cerr << "Failed to load reference trajectories." << std::endl; return 1; }
   if (!robot.loadContactSchedule(config.contact_schedule_path)) std::cerr << "Warning: no contact schedule" << std::endl;
   MPC mpc(robot, config.mpc.horizon, config.mpc.dt, config.urdf_path);
+  if (argc > 3) mpc.enableCSVLogging(argv[3]);
+  if (config.save_trajectories) mpc.enableOptimalTrajectoryLogging(config.results_path);
+  std::vector<double> step_ms, step_cost;
   double total_ms = 0.0;
   for (int step = 0; step < config.mpc.sim_steps; ++step) {
     Eigen::VectorXd x(robot.nx()), u(robot.nu());
@@ -33,7 +40,9 @@ int main(int argc, char** argv) {
     if (!x.allFinite()) { std::cerr << "NaN detected in state at step " << step << ", breaking." << std::endl; break; }
     auto t0 = std::chrono::steady_clock::now();
     bool ok = mpc.stepOnce(x, u);
-    total_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    step_ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    total_ms += step_ms.back();
+    step_cost.push_back(mpc.getLastSolveCost());
     if (!ok || !u.allFinite()) u.setZero();
     robot.setControl(u);
     robot.step();
@@ -41,5 +50,13 @@ int main(int argc, char** argv) {
               << "," << x(1) << "," << x(2) << ") m | Control range: [" << u.minCoeff() << ", " << u.maxCoeff() << "]" << std::endl;
   }
   std::cout << "Average MPC_stepOnce time: " << total_ms / std::max(1, config.mpc.sim_steps) << " ms" << std::endl;
+  mpc.finalizeCSVLog();
+  if (config.save_trajectories) mpc.finalizeOptimalTrajectoryLog();
+  std::cout.precision(17);
+  std::cout << "BENCH_JSON {\"step_ms\": [";
+  for (size_t i = 0; i < step_ms.size(); ++i) std::cout << (i ? ", " : "") << step_ms[i];
+  std::cout << "], \"cost\": [";
+  for (size_t i = 0; i < step_cost.size(); ++i) std::cout << (i ? ", " : "") << step_cost[i];
+  std::cout << "]}" << std::endl;
   return 0;
 }

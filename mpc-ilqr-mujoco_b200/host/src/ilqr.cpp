@@ -17,16 +17,37 @@ iLQR::iLQR(RobotUtils& robot, int N, double dt, const std::string& urdf_path)
 }
 iLQR::~iLQR() { if (h_) h1ilqr_destroy(h_); }
 
+// (Re)build the device handle from the robot's CURRENT dynamics model and the current options; the regularisation carries
+// over. The old handle survives a failure (e.g. max_iterations beyond H1ILQR_MAX_ITERS), so the solver stays usable.
 bool iLQR::recreate() {
   double lambda = opt_.reg_init;
-  if (h_) { h1ilqr_get_regularization(h_, &lambda); h1ilqr_destroy(h_); h_ = nullptr; }
+  if (h_) h1ilqr_get_regularization(h_, &lambda);
   H1Model dm = robot_.dynamics_model();
-  if (h1ilqr_create(&dm, nullptr, &opt_, 1, N_, 0, &h_) != H1ILQR_OK) return false;
-  return h1ilqr_set_regularization(h_, &lambda, 1) == H1ILQR_OK;
+  H1Ilqr* fresh = nullptr;
+  if (h1ilqr_create(&dm, nullptr, &opt_, 1, N_, 0, &fresh) != H1ILQR_OK) return false;
+  if (h1ilqr_set_regularization(fresh, &lambda, 1) != H1ILQR_OK) { h1ilqr_destroy(fresh); return false; }
+  if (h_) h1ilqr_destroy(h_);
+  h_ = fresh;
+  model_version_ = robot_.model_version();
+  return true;
+}
+// RobotUtils::setTimeStep / setGravity / scaleRobotMass after construction change the model the plant steps with; the
+// solver must optimise with the same one (the reference shares one mjModel between both).
+void iLQR::sync_model() {
+  if (model_version_ != robot_.model_version() && !recreate())
+    throw std::runtime_error(std::string("iLQR: cannot rebuild the GPU solver for the changed model: ") + h1ilqr_last_error());
 }
 void iLQR::setRegularization(double lambda) { if (h_) h1ilqr_set_regularization(h_, &lambda, 1); }
-void iLQR::setMaxIterations(int max_iter) { opt_.max_iterations = max_iter; recreate(); }
-void iLQR::setTolerance(double tol) { opt_.tolerance = tol; recreate(); }
+void iLQR::setMaxIterations(int max_iter) {
+  const int old = opt_.max_iterations;
+  opt_.max_iterations = max_iter;
+  if (!recreate()) { opt_.max_iterations = old; throw std::runtime_error(std::string("iLQR::setMaxIterations: ") + h1ilqr_last_error()); }
+}
+void iLQR::setTolerance(double tol) {
+  const double old = opt_.tolerance;
+  opt_.tolerance = tol;
+  if (!recreate()) { opt_.tolerance = old; throw std::runtime_error(std::string("iLQR::setTolerance: ") + h1ilqr_last_error()); }
+}
 
 bool iLQR::upload_window(const std::vector<Eigen::VectorXd>& x_ref, const std::vector<Eigen::VectorXd>& u_ref,
                          const std::vector<Eigen::Vector3d>& com_ref) {
@@ -66,18 +87,18 @@ void iLQR::initializeWithReference(const Eigen::VectorXd& x0, const std::vector<
                                    const std::vector<Eigen::VectorXd>& u_ref, const std::vector<Eigen::Vector3d>& com_ref,
                                    const std::vector<Eigen::VectorXd>* prev_xbar, const std::vector<Eigen::VectorXd>* prev_ubar) {
   (void)x_ref; (void)u_ref; (void)com_ref;
+  sync_model();
   const int nx = robot_.nx(), nu = robot_.nu();
   if (prev_xbar && prev_ubar && prev_xbar->size() == xbar_.size() && prev_ubar->size() == ubar_.size()) {
-    // warm start: shift by one knot, roll out the last step (ilqr.cpp:68-81)
+    // warm start: the caller's previous solution goes to the device, which shifts it by one knot and rolls out the last
+    // step (ilqr.cpp:68-81) — one upload and one launch sequence instead of a host-side shift
     std::vector<double> xb((N_ + 1) * nx), ub(N_ * nu);
-    for (int t = 0; t < N_; ++t) {
-      const Eigen::VectorXd& u = (*prev_ubar)[t < N_ - 1 ? t + 1 : N_ - 1];
-      for (int i = 0; i < nu; ++i) ub[t * nu + i] = u(i);
-    }
-    for (int i = 0; i < nx; ++i) xb[i] = x0(i);
-    for (int t = 0; t < N_ - 1; ++t) for (int i = 0; i < nx; ++i) xb[(t + 1) * nx + i] = (*prev_xbar)[t + 2](i);
-    h1ilqr_dynamics_step(h_, 1, &xb[(N_ - 1) * nx], &ub[(N_ - 1) * nu], &xb[N_ * nx]);
-    h1ilqr_set_trajectory(h_, xb.data(), ub.data());
+    for (int t = 0; t <= N_; ++t) for (int i = 0; i < nx; ++i) xb[t * nx + i] = (*prev_xbar)[t](i);
+    for (int t = 0; t < N_; ++t) for (int i = 0; i < nu; ++i) ub[t * nu + i] = (*prev_ubar)[t](i);
+    const int warm = 1;
+    if (h1ilqr_set_previous_solution(h_, xb.data(), ub.data()) != H1ILQR_OK ||
+        h1ilqr_initialize(h_, x0.data(), &warm, nullptr, 1) != H1ILQR_OK)
+      throw std::runtime_error(std::string("iLQR warm start: ") + h1ilqr_last_error());
   } else {
     std::cout << "Initial Guess Strategy: Gravity Compensation" << std::endl;
     Eigen::VectorXd ug;
@@ -94,6 +115,7 @@ bool iLQR::solve(const Eigen::VectorXd& x0, const std::vector<Eigen::VectorXd>& 
               << " expected=" << N_ << ", com_ref=" << com_ref.size() << " expected=" << N_ + 1 << std::endl;
     return false;
   }
+  sync_model();
   if (!robot_.weights_are_diagonal()) throw std::runtime_error("non-diagonal Q/R/Qf are not supported by the GPU solver core");
   if (!upload_window(x_ref, u_ref, com_ref)) throw std::runtime_error(std::string("iLQR upload: ") + h1ilqr_last_error());
   int status = 0, iters = 0;

@@ -3,7 +3,6 @@
 // the reference's format.
 #include "ilqr/mpc.hpp"
 #include <chrono>
-#include <iomanip>
 #include <iostream>
 
 MPC::MPC(RobotUtils& robot, int N, double dt, const std::string& urdf_path)
@@ -37,8 +36,9 @@ bool MPC::stepOnce(const Eigen::VectorXd& x_measured, Eigen::VectorXd& u_apply) 
     prev_xbar_ = xbar; prev_ubar_ = ubar; prev_K_ = K;
     has_prev_solution_ = true;
     last_solve_cost_ = solve_cost;
-    last_solve_time_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - start).count();
+    last_solve_time_ms_ = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - start).count() / 1000.0;
     t_idx_++;
+    logCurrentStep(x_measured, u_apply);
     logAppliedOptimal(x_measured, u_apply);
     return true;
   } catch (const std::exception& e) {
@@ -60,33 +60,68 @@ void MPC::getNominalTrajectory(std::vector<Eigen::VectorXd>& x_traj, std::vector
   if (has_prev_solution_) { x_traj = prev_xbar_; u_traj = prev_ubar_; } else { x_traj.clear(); u_traj.clear(); }
 }
 
+// ---- wide step CSV (mpc.cpp:181-268): one row per MPC step, default ostream number formatting, std::endl ----
+void MPC::enableCSVLogging(const std::string& filename) {
+  csv_filename_ = filename;
+  csv_file_.open(csv_filename_, std::ios::out | std::ios::trunc);
+  if (!csv_file_.is_open()) { std::cerr << "Failed to open CSV file: " << csv_filename_ << std::endl; return; }
+  csv_file_ << "time_index,time_sec,solve_cost,solve_time_ms";
+  for (int i = 0; i < robot_.nx(); ++i) csv_file_ << ",x_" << i;
+  for (int i = 0; i < robot_.nu(); ++i) csv_file_ << ",u_" << i;
+  for (int i = 0; i < robot_.nx(); ++i) csv_file_ << ",x_ref_" << i;
+  for (int i = 0; i < robot_.nu(); ++i) csv_file_ << ",u_ref_" << i;
+  csv_file_ << std::endl;
+  std::cout << "CSV logging started: " << csv_filename_ << std::endl;
+}
+void MPC::logCurrentStep(const Eigen::VectorXd& x_measured, const Eigen::VectorXd& u_applied) {
+  if (!csv_file_.is_open()) return;
+  csv_file_ << t_idx_ << "," << (t_idx_ * dt_) << "," << last_solve_cost_ << "," << last_solve_time_ms_;
+  for (long i = 0; i < x_measured.size(); ++i) csv_file_ << "," << x_measured(i);
+  for (long i = 0; i < u_applied.size(); ++i) csv_file_ << "," << u_applied(i);
+  if (!x_ref_window_.empty()) { for (long i = 0; i < x_ref_window_[0].size(); ++i) csv_file_ << "," << x_ref_window_[0](i); }
+  else { for (int i = 0; i < robot_.nx(); ++i) csv_file_ << ",0.0"; }
+  if (!u_ref_window_.empty()) { for (long i = 0; i < u_ref_window_[0].size(); ++i) csv_file_ << "," << u_ref_window_[0](i); }
+  else { for (int i = 0; i < robot_.nu(); ++i) csv_file_ << ",0.0"; }
+  csv_file_ << std::endl;
+}
+void MPC::finalizeCSVLog() {
+  if (csv_file_.is_open()) {
+    csv_file_.flush();
+    csv_file_.close();
+    std::cout << "CSV log finalized: " << csv_filename_ << std::endl;
+  }
+}
+
+// ---- q_optimal.csv / u_optimal.csv (mpc.cpp:270-355): first knot of the optimised trajectory per step, the format
+//      simulate.py / plotter.py read; default ostream number formatting like the reference ----
 void MPC::enableOptimalTrajectoryLogging(const std::string& base_path) {
   trajectory_base_path_ = base_path;
-  q_optimal_file_.open(base_path + "/q_optimal.csv");
-  u_optimal_file_.open(base_path + "/u_optimal.csv");
+  q_optimal_file_.open(base_path + "/q_optimal.csv", std::ios::out | std::ios::trunc);
+  u_optimal_file_.open(base_path + "/u_optimal.csv", std::ios::out | std::ios::trunc);
   if (!q_optimal_file_.is_open() || !u_optimal_file_.is_open()) {
-    std::cerr << "Warning: cannot open trajectory logs under " << base_path << std::endl;
+    std::cerr << "Failed to open optimal trajectory files in: " << base_path << std::endl;
     return;
   }
   q_optimal_file_ << "step,time_sec";
   for (int i = 0; i < robot_.nq(); ++i) q_optimal_file_ << ",q_" << i;
-  q_optimal_file_ << "\n";
+  q_optimal_file_ << std::endl;
   u_optimal_file_ << "step,time_sec";
   for (int i = 0; i < robot_.nu(); ++i) u_optimal_file_ << ",u_" << i;
-  u_optimal_file_ << "\n";
+  u_optimal_file_ << std::endl;
 }
 void MPC::logAppliedOptimal(const Eigen::VectorXd& x_applied, const Eigen::VectorXd& u_applied) {
-  (void)x_applied; (void)u_applied;
   if (!q_optimal_file_.is_open() || !u_optimal_file_.is_open()) return;
-  const auto& xbar = ilqr_.xbar(); const auto& ubar = ilqr_.ubar();
-  q_optimal_file_ << t_idx_ << "," << std::fixed << std::setprecision(6) << t_idx_ * dt_;
-  for (int i = 0; i < robot_.nq(); ++i) q_optimal_file_ << "," << std::setprecision(8) << xbar[0](i);
-  q_optimal_file_ << "\n";
-  u_optimal_file_ << t_idx_ << "," << std::fixed << std::setprecision(6) << t_idx_ * dt_;
-  for (int i = 0; i < robot_.nu(); ++i) u_optimal_file_ << "," << std::setprecision(8) << ubar[0](i);
-  u_optimal_file_ << "\n";
+  const auto& x_optimal = ilqr_.xbar(); const auto& u_optimal = ilqr_.ubar();
+  q_optimal_file_ << t_idx_ << "," << (t_idx_ * dt_);
+  for (int i = 0; i < robot_.nq(); ++i) q_optimal_file_ << "," << (!x_optimal.empty() ? x_optimal[0](i) : x_applied(i));
+  q_optimal_file_ << std::endl;
+  u_optimal_file_ << t_idx_ << "," << (t_idx_ * dt_);
+  if (!u_optimal.empty()) { for (long i = 0; i < u_optimal[0].size(); ++i) u_optimal_file_ << "," << u_optimal[0](i); }
+  else { for (long i = 0; i < u_applied.size(); ++i) u_optimal_file_ << "," << u_applied(i); }
+  u_optimal_file_ << std::endl;
 }
 void MPC::finalizeOptimalTrajectoryLog() {
-  if (q_optimal_file_.is_open()) q_optimal_file_.close();
-  if (u_optimal_file_.is_open()) u_optimal_file_.close();
+  if (q_optimal_file_.is_open()) { q_optimal_file_.flush(); q_optimal_file_.close(); }
+  if (u_optimal_file_.is_open()) { u_optimal_file_.flush(); u_optimal_file_.close(); }
+  std::cout << "Optimal trajectory logs finalized: " << trajectory_base_path_ << "/q_optimal.csv and u_optimal.csv" << std::endl;
 }

@@ -9,7 +9,7 @@
 #include <stdexcept>
 
 RobotUtils::RobotUtils()
-    : loaded_(false), nx_(0), nu_(0), dt_(0.01), query_(nullptr), diag_ok_(true), w_com_(0.0), w_com_vel_(0.0),
+    : loaded_(false), model_version_(0), nx_(0), nu_(0), dt_(0.01), query_(nullptr), diag_ok_(true), w_com_(0.0), w_com_vel_(0.0),
       w_ee_pos_(0.0), w_ee_vel_(0.0), w_joint_limits_(500.0), w_control_limits_(1000.0), w_upright_(0.0), w_balance_(0.0) {
   std::memset(&model_, 0, sizeof(model_));
   std::memset(&data_, 0, sizeof(data_));
@@ -17,8 +17,17 @@ RobotUtils::RobotUtils()
 
 RobotUtils::~RobotUtils() { if (query_) h1ilqr_destroy(query_); }
 
-bool RobotUtils::ensure_query() {
-  if (query_) return true;
+void RobotUtils::model_changed() {   // the dynamics model is baked into device handles: drop ours, let the solver notice
+  ++model_version_;
+  if (query_) { h1ilqr_destroy(query_); query_ = nullptr; }
+}
+
+bool RobotUtils::ensure_query() const {
+  if (query_) {   // the limit penalties / stage costs read the handle's weights: keep them current
+    H1Weights w = weights();
+    h1ilqr_set_weights(query_, &w);
+    return true;
+  }
   H1SolverOptions o;
   h1ilqr_default_options(&o);
   if (h1ilqr_create(&dyn_model_, nullptr, &o, 1, 2, 0, &query_) != H1ILQR_OK) {
@@ -26,6 +35,8 @@ bool RobotUtils::ensure_query() {
     query_ = nullptr;
     return false;
   }
+  H1Weights w = weights();
+  h1ilqr_set_weights(query_, &w);
   return true;
 }
 
@@ -54,13 +65,13 @@ void RobotUtils::setContactImpratio(double impratio) {
 }
 void RobotUtils::setTimeStep(double dt) {
   dt_ = dt; dyn_model_.timestep = dt; model_.opt.timestep = dt;
-  if (query_) { h1ilqr_destroy(query_); query_ = nullptr; }
+  model_changed();
   std::cout << "Set timestep to: " << dt << std::endl;
 }
 void RobotUtils::setGravity(double gx, double gy, double gz) {
   dyn_model_.gravity[0] = gx; dyn_model_.gravity[1] = gy; dyn_model_.gravity[2] = gz;
   model_.opt.gravity[0] = gx; model_.opt.gravity[1] = gy; model_.opt.gravity[2] = gz;
-  if (query_) { h1ilqr_destroy(query_); query_ = nullptr; }
+  model_changed();
   std::cout << "Set gravity to: (" << gx << "," << gy << "," << gz << ")m/s²" << std::endl;
 }
 
@@ -85,6 +96,58 @@ void RobotUtils::rolloutOneStep(const Eigen::VectorXd& x, const Eigen::VectorXd&
   if (h1ilqr_dynamics_step(query_, 1, x.data(), u.data(), x_next.data()) != H1ILQR_OK)
     throw std::runtime_error(std::string("h1ilqr_dynamics_step: ") + h1ilqr_last_error());
 }
+void RobotUtils::linearizeDynamicsFD(const Eigen::VectorXd& x, const Eigen::VectorXd& u, Eigen::MatrixXd& A,
+                                     Eigen::MatrixXd& B, double eps) {
+  if (!loaded_ || !ensure_query()) return;
+  A.resize(nx_, nx_); B.resize(nx_, nu_);   // column-major like the C ABI
+  if (h1ilqr_linearize_state(query_, H1ILQR_LIN_FD, eps, x.data(), u.data(), A.data(), B.data()) != H1ILQR_OK)
+    throw std::runtime_error(std::string("h1ilqr_linearize_state: ") + h1ilqr_last_error());
+}
+
+double RobotUtils::constraintCost(const Eigen::VectorXd& x, const Eigen::VectorXd& u) const {
+  if (!loaded_ || !ensure_query()) return 0.0;
+  double c = 0.0;
+  if (h1ilqr_limit_penalties(query_, 1, x.data(), u.data(), &c, nullptr, nullptr, nullptr, nullptr) != H1ILQR_OK)
+    throw std::runtime_error(std::string("h1ilqr_limit_penalties: ") + h1ilqr_last_error());
+  return c;
+}
+void RobotUtils::constraintGradients(const Eigen::VectorXd& x, const Eigen::VectorXd& u, Eigen::VectorXd& grad_x,
+                                     Eigen::VectorXd& grad_u) const {
+  if (!loaded_ || !ensure_query()) return;
+  grad_x.setZero(nx_); grad_u.setZero(nu_);
+  if (h1ilqr_limit_penalties(query_, 1, x.data(), u.data(), nullptr, grad_x.data(), grad_u.data(), nullptr, nullptr) != H1ILQR_OK)
+    throw std::runtime_error(std::string("h1ilqr_limit_penalties: ") + h1ilqr_last_error());
+}
+void RobotUtils::constraintHessians(const Eigen::VectorXd& x, const Eigen::VectorXd& u, Eigen::MatrixXd& hess_xx,
+                                    Eigen::MatrixXd& hess_uu) const {
+  if (!loaded_ || !ensure_query()) return;
+  hess_xx.resize(nx_, nx_); hess_xx.setZero(); hess_uu.resize(nu_, nu_); hess_uu.setZero();
+  std::vector<double> hx(nx_), hu(nu_);
+  if (h1ilqr_limit_penalties(query_, 1, x.data(), u.data(), nullptr, nullptr, nullptr, hx.data(), hu.data()) != H1ILQR_OK)
+    throw std::runtime_error(std::string("h1ilqr_limit_penalties: ") + h1ilqr_last_error());
+  for (int i = 0; i < nx_; ++i) hess_xx(i, i) = hx[i];
+  for (int i = 0; i < nu_; ++i) hess_uu(i, i) = hu[i];
+}
+double RobotUtils::stageCost(int t, const Eigen::VectorXd& x, const Eigen::VectorXd& u) const {
+  if (!loaded_ || x_ref_full_.empty() || !ensure_query()) return 0.0;
+  // rows past the tables use the last one (robot_utils.cpp:163-166)
+  const int xi = std::min(t, (int)x_ref_full_.size() - 1), ui = std::min(t, (int)u_ref_full_.size() - 1);
+  const int ci = std::min(t, (int)com_ref_full_.size() - 1);
+  double c = 0.0;
+  if (h1ilqr_stage_cost(query_, 1, x.data(), u.data(), x_ref_full_[xi].data(), u_ref_full_[ui].data(),
+                        com_ref_full_.empty() ? nullptr : com_ref_full_[ci].data(), &c) != H1ILQR_OK)
+    throw std::runtime_error(std::string("h1ilqr_stage_cost: ") + h1ilqr_last_error());
+  return c;
+}
+double RobotUtils::terminalCost(const Eigen::VectorXd& x) const {
+  if (!loaded_ || x_ref_full_.empty() || !ensure_query()) return 0.0;
+  double c = 0.0;
+  if (h1ilqr_stage_cost(query_, 1, x.data(), nullptr, x_ref_full_.back().data(), nullptr,
+                        com_ref_full_.empty() ? nullptr : com_ref_full_.back().data(), &c) != H1ILQR_OK)
+    throw std::runtime_error(std::string("h1ilqr_stage_cost: ") + h1ilqr_last_error());
+  return c;
+}
+
 void RobotUtils::step() {
   if (!loaded_) return;
   Eigen::VectorXd x(nx_), u(nu_), xn(nx_);
@@ -134,6 +197,7 @@ bool RobotUtils::loadReferences(const std::string& q_ref_path, const std::string
   if (!q_file.is_open()) { std::cerr << "Failed to open position reference file: " << q_ref_path << std::endl; return false; }
   if (!v_file.is_open()) { std::cerr << "Failed to open velocity reference file: " << v_ref_path << std::endl; return false; }
   x_ref_full_.clear(); u_ref_full_.clear(); com_ref_full_.clear(); com_vel_ref_full_.clear(); ee_pos_ref_full_.clear();
+  ee_vel_ref_full_.clear();
   std::string q_line, v_line;
   std::vector<double> flat;
   while (std::getline(q_file, q_line) && std::getline(v_file, v_line)) {
@@ -151,16 +215,21 @@ bool RobotUtils::loadReferences(const std::string& q_ref_path, const std::string
   // per-row CoM (subtree_com of the root) and ankle body positions on the dynamics model, on the GPU
   if (!ensure_query()) return false;
   const int T = (int)x_ref_full_.size();
-  std::vector<double> com(3 * T), ee(6 * T);
-  if (h1ilqr_reference_kinematics(query_, T, flat.data(), com.data(), ee.data()) != H1ILQR_OK) {
+  // (CoM velocity = J_subtreeCom * qvel and ankle velocities = jac_pos * qvel per row too, robot_utils.cpp:388-412)
+  std::vector<double> com(3 * T), ee(6 * T), cv(3 * T), ev(6 * T);
+  if (h1ilqr_reference_kinematics(query_, T, flat.data(), com.data(), ee.data()) != H1ILQR_OK ||
+      h1ilqr_reference_com_velocity(query_, T, flat.data(), cv.data()) != H1ILQR_OK ||
+      h1ilqr_reference_ee_velocity(query_, T, flat.data(), ev.data()) != H1ILQR_OK) {
     std::cerr << "reference kinematics failed: " << h1ilqr_last_error() << std::endl;
     return false;
   }
   for (int t = 0; t < T; ++t) {
     com_ref_full_.push_back(Eigen::Vector3d(com[3 * t], com[3 * t + 1], com[3 * t + 2]));
-    com_vel_ref_full_.push_back(Eigen::Vector3d::Zero());
+    com_vel_ref_full_.push_back(Eigen::Vector3d(cv[3 * t], cv[3 * t + 1], cv[3 * t + 2]));
     ee_pos_ref_full_.push_back({Eigen::Vector3d(ee[6 * t], ee[6 * t + 1], ee[6 * t + 2]),
                                 Eigen::Vector3d(ee[6 * t + 3], ee[6 * t + 4], ee[6 * t + 5])});
+    ee_vel_ref_full_.push_back({Eigen::Vector3d(ev[6 * t], ev[6 * t + 1], ev[6 * t + 2]),
+                                Eigen::Vector3d(ev[6 * t + 3], ev[6 * t + 4], ev[6 * t + 5])});
   }
   std::cout << "Loaded " << x_ref_full_.size() << " reference states" << std::endl;
   return true;
@@ -209,13 +278,39 @@ Eigen::Vector3d RobotUtils::getEEReference(int t, int ee_idx) const {
     throw std::runtime_error("Invalid reference index: t=" + std::to_string(t) + ", ee_idx=" + std::to_string(ee_idx));
   return ee_pos_ref_full_[t][ee_idx];
 }
+Eigen::Vector3d RobotUtils::getEEVelReference(int t, int ee_idx) const {
+  if (t >= (int)ee_vel_ref_full_.size() || ee_idx >= (int)ee_vel_ref_full_[t].size())
+    throw std::runtime_error("Invalid velocity reference index: t=" + std::to_string(t) + ", ee_idx=" + std::to_string(ee_idx));
+  return ee_vel_ref_full_[t][ee_idx];
+}
+int RobotUtils::jointId(const std::string& name) const {
+  // MuJoCo joint ids of the MJCF (h1.xml:49-179): 0 is the unnamed free joint, 1..19 the hinges in body order
+  static const char* const names[H1_NU] = {
+      "left_hip_yaw_joint", "left_hip_roll_joint", "left_hip_pitch_joint", "left_knee_joint", "left_ankle_joint",
+      "right_hip_yaw_joint", "right_hip_roll_joint", "right_hip_pitch_joint", "right_knee_joint", "right_ankle_joint",
+      "torso_joint", "left_shoulder_pitch_joint", "left_shoulder_roll_joint", "left_shoulder_yaw_joint", "left_elbow_joint",
+      "right_shoulder_pitch_joint", "right_shoulder_roll_joint", "right_shoulder_yaw_joint", "right_elbow_joint"};
+  if (!loaded_) return -1;
+  for (int i = 0; i < H1_NU; ++i) if (name == names[i]) return i + 1;
+  return -1;
+}
+void RobotUtils::resetToReference(int t) {
+  if (t >= 0 && t < (int)x_ref_full_.size()) setState(x_ref_full_[t]);
+}
+void RobotUtils::scaleRobotMass(double scale_factor) {
+  if (!loaded_) return;
+  for (int b = 0; b < H1_NB; ++b) dyn_model_.mass[b] *= scale_factor;   // body_mass only, as the reference (robot_utils.cpp:835-842)
+  dyn_model_.total_mass *= scale_factor;
+  model_changed();
+  std::cout << "Scaled robot mass by factor: " << scale_factor << std::endl;
+}
 Eigen::Vector3d RobotUtils::getCoMVelReference(int t) const {
   if (t >= (int)com_vel_ref_full_.size()) throw std::runtime_error("Invalid CoM velocity reference index: t=" + std::to_string(t));
   return com_vel_ref_full_[t];
 }
 Eigen::Vector3d RobotUtils::computeCoM(const Eigen::VectorXd& x) const {
   Eigen::Vector3d c;
-  if (!loaded_ || !const_cast<RobotUtils*>(this)->ensure_query()) return c;
+  if (!loaded_ || !ensure_query()) return c;
   double com[3], ee[6];
   h1ilqr_reference_kinematics(query_, 1, x.data(), com, ee);
   return Eigen::Vector3d(com[0], com[1], com[2]);
