@@ -20,7 +20,8 @@ EXPORTS = [
     "h1ilqr_horizon", "h1ilqr_set_weights", "h1ilqr_set_reference_window", "h1ilqr_initialize", "h1ilqr_solve",
     "h1ilqr_mpc_step", "h1ilqr_mpc_reset", "h1ilqr_rollout_nominal", "h1ilqr_linearize", "h1ilqr_cost_quadratics",
     "h1ilqr_backward_pass", "h1ilqr_line_search", "h1ilqr_total_cost", "h1ilqr_dynamics_step", "h1ilqr_bias_forces",
-    "h1ilqr_reference_kinematics", "h1ilqr_reference_com_velocity", "h1ilqr_get_status", "h1ilqr_sole_points", "h1ilqr_set_trajectory", "h1ilqr_get_trajectory", "h1ilqr_get_gains",
+    "h1ilqr_reference_kinematics", "h1ilqr_reference_com_velocity", "h1ilqr_reference_ee_velocity", "h1ilqr_linearize_state",
+    "h1ilqr_limit_penalties", "h1ilqr_stage_cost", "h1ilqr_get_status", "h1ilqr_sole_points", "h1ilqr_set_trajectory", "h1ilqr_get_trajectory", "h1ilqr_get_gains",
     "h1ilqr_set_gains", "h1ilqr_get_linearization", "h1ilqr_set_linearization", "h1ilqr_get_cost_quadratics",
     "h1ilqr_set_cost_quadratics", "h1ilqr_set_previous_solution", "h1ilqr_get_previous_solution", "h1ilqr_get_regularization", "h1ilqr_set_regularization", "h1ilqr_get_solve_trace",
     "h1ilqr_upload_inputs", "h1ilqr_host_register", "h1ilqr_host_unregister", "h1ilqr_run_resident_steps", "h1ilqr_time_stage", "h1ilqr_set_reference_table", "h1ilqr_run_closed_loop", "h1ilqr_measure_fp64_peak", "h1ilqr_measure_fp64_mma_peak", "h1ilqr_enable_stage_timing", "h1ilqr_set_kernel_policy", "h1ilqr_get_stage_times", "h1ilqr_stream", "h1_default_dynamics_model",
@@ -230,6 +231,39 @@ class H1IlqrBatch:
         cv = np.empty((x.shape[0], 3))
         _check(lib().h1ilqr_reference_com_velocity(self._h, C.c_int(x.shape[0]), dptr(x), dptr(cv)))
         return cv
+
+    def reference_ee_velocity(self, x):
+        """World velocity [n][2][3] of the two ankle-body origins (robot_utils.cpp:405-412)."""
+        x = _f(x).reshape(-1, NX)
+        ev = np.empty((x.shape[0], 2, 3))
+        _check(lib().h1ilqr_reference_ee_velocity(self._h, C.c_int(x.shape[0]), dptr(x), dptr(ev)))
+        return ev
+
+    def linearize_state(self, x, u, mode=0, eps=1e-5):
+        """(A [51][51], B [51][19]) of one (x, u) pair, row-major numpy views of the column-major C arrays transposed:
+        A[i, j] = d x_next_i / d x_j. mode 1 = RobotUtils::linearizeDynamicsFD (forward differences, eps)."""
+        A = np.empty((NX, NX)); B = np.empty((NU, NX))
+        _check(lib().h1ilqr_linearize_state(self._h, C.c_int(mode), C.c_double(eps), dptr(_f(x).reshape(NX)), dptr(_f(u).reshape(NU)),
+                                            dptr(A), dptr(B)))
+        return A.T, B.T
+
+    def limit_penalties(self, x, u=None):
+        """constraintCost / Gradients / Hessian diagonals of n (x, u) pairs (robot_utils.cpp:615-778)."""
+        x = _f(x).reshape(-1, NX); n = x.shape[0]
+        uu = _f(u).reshape(n, NU) if u is not None else None
+        c = np.empty(n); gx = np.empty((n, NX)); gu = np.empty((n, NU)); hx = np.empty((n, NX)); hu = np.empty((n, NU))
+        _check(lib().h1ilqr_limit_penalties(self._h, C.c_int(n), dptr(x), dptr(uu), dptr(c), dptr(gx), dptr(gu), dptr(hx), dptr(hu)))
+        return c, gx, gu, hx, hu
+
+    def stage_cost(self, x, u, x_ref, u_ref=None, com_ref=None):
+        """RobotUtils::stageCost (u given) / terminalCost (u None) of n states against reference rows."""
+        x = _f(x).reshape(-1, NX); n = x.shape[0]
+        uu = _f(u).reshape(n, NU) if u is not None else None
+        ur = _f(u_ref).reshape(n, NU) if u_ref is not None else None
+        cr = _f(com_ref).reshape(n, 3) if com_ref is not None else None
+        c = np.empty(n)
+        _check(lib().h1ilqr_stage_cost(self._h, C.c_int(n), dptr(x), dptr(uu), dptr(_f(x_ref).reshape(n, NX)), dptr(ur), dptr(cr), dptr(c)))
+        return c
 
     def sole_points(self, x):
         """World positions [n][8][3] of the sole contact points (left foot's four first)."""
