@@ -124,3 +124,28 @@ def load_config_from_file(path: str) -> Config:
     p.joint_limit_weight = float(m["constraints"]["joint_limit_weight"])
     p.torque_limit_weight = float(m["constraints"]["torque_limit_weight"])
     return cfg
+
+
+def dump_config_yaml(cfg: Config) -> str:
+    """The reference's config.yaml schema (config.cpp:4-64) for `cfg` — what loadConfigFromFile / load_config_from_file
+    read back."""
+    c, m = cfg.mpc.costs, cfg.mpc
+    lines = [
+        "robot:", "  name: h1", f'  model_path: "{cfg.model_path}"', f'  urdf_path: "{cfg.urdf_path}"',
+        "reference_trajectory:", f'  q_ref: "{cfg.q_ref_path}"', f'  v_ref: "{cfg.v_ref_path}"',
+        f'  contact_schedule: "{cfg.contact_schedule_path}"',
+        "mpc:", f"  horizon: {m.horizon}", f"  dt: {m.dt}", f"  physics_dt: {m.physics_dt}",
+        f"  gravity: [{m.gravity[0]}, {m.gravity[1]}, {m.gravity[2]}]", f"  sim_steps: {m.sim_steps}",
+        f"  contact_impratio: {m.contact_impratio}", "  cost_weights:"]
+    for k in ("Q_position_x", "Q_position_y", "Q_position_z", "Q_quat_w"):
+        lines.append(f"    {k}: {getattr(c, k)}")
+    lines.append(f"    Q_quat_xyz: [{c.Q_quat_xyz[0]}, {c.Q_quat_xyz[1]}, {c.Q_quat_xyz[2]}]")
+    for k in ("Q_joint_pos", "Q_vel_x", "Q_vel_y", "Q_vel_z", "Q_ang_vel", "Q_joint_vel", "R_control", "Qf_multiplier",
+              "Qf_position_x", "Qf_position_y", "Qf_position_z", "Qf_vel_z"):
+        lines.append(f"    {k}: {getattr(c, k)}")
+    lines += [f"    W_com_pos: {c.W_com}", f"    W_com_vel: {c.W_com_vel}", f"    W_foot: {c.W_foot}", f"    W_foot_vel: {c.W_foot_vel}",
+              f"    W_upright: {c.W_upright}", f"    w_balance: {c.w_balance}", "  constraints:",
+              f"    joint_limit_weight: {m.joint_limit_weight}", f"    torque_limit_weight: {m.torque_limit_weight}",
+              "logging:", f'  results_path: "{cfg.results_path}"', f"  verbose: {'true' if cfg.verbose else 'false'}",
+              f"  save_trajectories: {'true' if cfg.save_trajectories else 'false'}", ""]
+    return "\n".join(lines)
