@@ -43,9 +43,11 @@ H1_HD int q4_body(int g, int i) { return g < 2 ? 1 + SEQ_LEG_LEN * g + i : (i ==
 
 #if defined(__CUDACC__)
 struct QuadWarp {   // exchange between the 4 lanes of an evaluation (lanes 4c .. 4c+3 of a warp)
-  __device__ __forceinline__ double xor1(double v) const { return __shfl_xor_sync(0xffffffffu, v, 1); }
-  __device__ __forceinline__ double xor2(double v) const { return __shfl_xor_sync(0xffffffffu, v, 2); }
-  __device__ __forceinline__ void sync() const { __syncwarp(); }
+  unsigned mask;    // lanes that take part: the whole warp (line search: every quad is busy) or this quad only
+  __device__ __forceinline__ explicit QuadWarp(unsigned m = 0xffffffffu) : mask(m) {}
+  __device__ __forceinline__ double xor1(double v) const { return __shfl_xor_sync(mask, v, 1); }
+  __device__ __forceinline__ double xor2(double v) const { return __shfl_xor_sync(mask, v, 2); }
+  __device__ __forceinline__ void sync() const { __syncwarp(mask); }
 };
 #endif
 

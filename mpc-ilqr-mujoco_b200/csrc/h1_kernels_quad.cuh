@@ -67,6 +67,85 @@ __device__ __forceinline__ double knot_cost_quad(const DynModel& md, const H1Wei
   return acc;
 }
 
+// ---- nominal rollout on the quad-cooperative f_D: four lanes per instance, eight instances per warp. Same contract as
+//      k_rollout / k_rollout_seq without the factor output (iLQR::forwardRolloutNominal, ilqr.cpp:119-124, and the baseline
+//      computeTotalCost): xbar[t+1] = f_D(xbar[t], ubar[t]) for t >= t_begin (from x0 when given), cost of the whole
+//      trajectory when cost_out != nullptr. One thread per instance (k_rollout_seq) left 128 warps of 25 dependent 20 k-
+//      instruction evaluations on the GPU; here an instance is four lanes and an evaluation a quarter as long. ----
+constexpr int RQ_WARPS = 2;   // 16 instances per CTA
+struct RQWarpSmem {
+  double xs[H1ILQR_NALPHA][Q4_XS];
+  double us[H1ILQR_NALPHA][Q4_US];
+  double st[Q4_STORE][32];
+};
+__global__ void __launch_bounds__(RQ_WARPS * 32)
+k_rollout_quad(const DynModel* gmd, const H1Weights* gw, RefTable refs, int B, int N, int t_begin,
+               const int* __restrict__ active, const double* __restrict__ x0, double* __restrict__ xbar,
+               const double* __restrict__ ubar, double* __restrict__ cost_out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const DynModel* md;
+  unsigned char* p = stage_model(smem, gmd, &md);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = lane >> 2, g = lane & 3;
+  const int inst = (blockIdx.x * RQ_WARPS + warp) * 8 + q;
+  if (inst >= B) return;
+  if (active && !active[inst]) return;
+  RQWarpSmem& ws = reinterpret_cast<RQWarpSmem*>(p)[warp];
+  const QuadWarp cx(0xfu << (4 * q));     // quads of a warp finish independently (mask / batch edge)
+  double* xs = ws.xs[q];
+  double* us = ws.us[q];
+  double* st = &ws.st[0][lane];
+  double* xb = xbar + (size_t)inst * (N + 1) * NX;
+  const double* ub = ubar + (size_t)inst * N * NU;
+  const RefView r = refs.view(inst);
+  for (int i = g; i < NX; i += 4) { const double v = x0 ? x0[(size_t)inst * NX + i] : xb[i]; xs[i] = v; if (x0) xb[i] = v; }
+  double total = 0.0;
+  cx.sync();
+#pragma unroll 1
+  for (int t = 0; t < N; ++t) {
+    for (int i = g; i < NU; i += 4) us[i] = ub[t * NU + i];
+    cx.sync();
+    double com[3];
+    if (t >= t_begin) {
+      double qn[Q4_CHAIN], vn[Q4_CHAIN], bn[13];
+      dyn_step_quad(*md, cx, g, xs, us, st, 32, qn, vn, bn, com);
+      if (cost_out) total += knot_cost_quad(*md, *gw, r, t, g, xs, us, com, false);
+      cx.sync();
+#pragma unroll
+      for (int i = 0; i < Q4_CHAIN; ++i) {
+        if (g == 3 && i == 0) continue;
+        const int b = q4_body(g, i);
+        xs[6 + b] = qn[i]; xs[NQ + 5 + b] = vn[i];
+      }
+      if (g == 0) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) xs[i] = bn[i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) xs[NQ + i] = bn[7 + i];
+      }
+      cx.sync();
+      double* xnext = xb + (t + 1) * NX;
+      for (int i = g; i < NX; i += 4) xnext[i] = xs[i];
+    } else {
+      if (cost_out) {
+        dyn_com_quad(*md, cx, g, xs, com);
+        total += knot_cost_quad(*md, *gw, r, t, g, xs, us, com, false);
+      }
+      cx.sync();
+      const double* xnext = xb + (t + 1) * NX;
+      for (int i = g; i < NX; i += 4) xs[i] = xnext[i];
+      cx.sync();
+    }
+  }
+  if (cost_out) {
+    double com[3];
+    dyn_com_quad(*md, cx, g, xs, com);
+    total += knot_cost_quad(*md, *gw, r, N, g, xs, nullptr, com, true);
+    total = quad_sum(cx, total);
+    if (g == 0) cost_out[inst] = total;
+  }
+}
+
 template <int Q4_WARPS>
 __global__ void __launch_bounds__(Q4_WARPS * 32, 1)
 k_line_search_quad(const DynModel* gmd, const H1Weights* gw, const H1SolverOptions* gopt, RefTable refs, int B, int N,

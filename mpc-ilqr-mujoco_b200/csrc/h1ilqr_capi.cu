@@ -58,6 +58,8 @@ struct H1Ilqr {
                             // measured break-even with the warp-per-evaluation kernels: between 512 and 1024 instances
   size_t smem_seq = 0, smem_seq_ls = 0, smem_lint = 0, smem_linf = 0, smem_q4 = 0;
   int q4_warps = 8;         // instances per CTA of k_line_search_quad
+  bool roll_quad = true;    // batched nominal rollout: quad-cooperative kernel; false = one thread per instance
+  size_t smem_rq = 0;
   bool ls_quad = true;      // batched line search: quad-cooperative kernel (h1_kernels_quad.cuh); false = thread-sequential one
   bool seq_ok = false;      // the model has the chain structure the thread-sequential f_D is specialised for
   long lin_cols_min_knots = 148 * 32;   // AUTO: B*N at or above which the direction-uniform linearization (32 knots per CTA) fills the GPU;
@@ -207,6 +209,9 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   h->smem_q4 = mdl + (size_t)h->q4_warps * sizeof(Q4WarpSmem);
   CUH(cudaFuncSetAttribute(k_line_search_quad<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(mdl + 8 * sizeof(Q4WarpSmem))));
   CUH(cudaFuncSetAttribute(k_line_search_quad<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(mdl + 1 * sizeof(Q4WarpSmem))));
+  h->smem_rq = mdl + (size_t)RQ_WARPS * sizeof(RQWarpSmem);
+  CUH(cudaFuncSetAttribute(k_rollout_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_rq));
+  if (const char* e = getenv("H1_ROLL_SEQ")) h->roll_quad = atoi(e) == 0;
   if (const char* e = getenv("H1_LS_SEQ")) h->ls_quad = atoi(e) == 0;   // A/B measurements against the thread-sequential kernel
   CUH(cudaFuncSetAttribute(k_rollout_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_seq));
   CUH(cudaFuncSetAttribute(k_dyn_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
@@ -278,8 +283,17 @@ static bool use_batched(const H1Ilqr* h, long units, long auto_min_units) {
   if (h->policy == H1ILQR_KERNELS_BATCHED) return true;
   return units >= auto_min_units;
 }
+static void launch_factors(H1Ilqr* h, const int* mask);
 static void launch_rollout(H1Ilqr* h, const int* mask, const double* x0_dev, int t_begin, double* cost_out,
                            bool keep_factors = false) {
+  if (h->seq_ok && h->roll_quad && use_batched(h, h->B, h->seq_min_batch)) {   // four lanes per instance; factors knot-parallel
+    const int per_cta = RQ_WARPS * 8;
+    k_rollout_quad<<<(h->B + per_cta - 1) / per_cta, RQ_WARPS * 32, h->smem_rq, h->stream>>>(
+        h->d_dyn, h->d_w, ref_table(h), h->B, h->N, t_begin, mask, x0_dev, h->xbar, h->ubar, cost_out);
+    LAUNCHED();
+    if (keep_factors) launch_factors(h, mask);
+    return;
+  }
   if (h->seq_ok && use_batched(h, h->B, h->seq_min_batch)) {   // one thread per instance
     k_rollout_seq<<<(h->B + SEQ_ROLL_THREADS - 1) / SEQ_ROLL_THREADS, SEQ_ROLL_THREADS, h->smem_seq, h->stream>>>(
         h->d_dyn, h->d_w, ref_table(h), h->B, h->N, t_begin, mask, x0_dev, h->xbar, h->ubar, cost_out,

@@ -14,8 +14,8 @@ s.set_kernel_policy(int(os.environ.get("H1_POLICY", "0")))
 refs = ReferenceSet(d["walking_q"], d["walking_v"], d["walking_contact"], s.reference_kinematics)
 ug = np.zeros(19); ug[:18] = s.bias_forces(standing_state()[None])[0][7:25]
 if os.environ.get("H1_PROF_WORKLOAD", "standing") == "bench":   # the bench.py workload (per-instance walking windows)
-    import bench
-    win, x0 = bench.workload(B, 0, s.reference_kinematics)
+    from mpc_ilqr_mujoco_b200 import workloads as wl
+    win, x0, _ = wl.walking_instances(np.arange(B), s.reference_kinematics)
     s.set_reference_window(*win, shared=False)
 else:
     s.set_reference_window(*refs.window(0, 25), shared=True)
