@@ -35,6 +35,39 @@ def load_qv_csv(q_path, v_path):
     return np.asarray(qs, dtype=np.float64), np.asarray(vs, dtype=np.float64)
 
 
+def pinocchio_to_mujoco_q(q_pin):
+    """Configuration rows in Pinocchio order [x y z | qx qy qz qw | joints] -> MuJoCo order [x y z | qw qx qy qz | joints]
+    (the conversion of the reference's tooling, get_contacts.py:18-41; data/h1_walking_pin.csv, the file BASELINE config 2
+    names, is stored in Pinocchio order). Works on one row or a [T][26] array."""
+    q = np.array(q_pin, dtype=np.float64, copy=True)
+    src = np.asarray(q_pin, dtype=np.float64)
+    q[..., 3] = src[..., 6]
+    q[..., 4] = src[..., 3]
+    q[..., 5] = src[..., 4]
+    q[..., 6] = src[..., 5]
+    return q
+
+
+def load_q_pin_csv(q_pin_path):
+    """A Pinocchio-ordered configuration CSV (h1_walking_pin.csv) as MuJoCo-ordered rows [T][26]; rows whose column
+    count is not 26 are skipped like loadReferences does. The file carries no velocities: pair it with a v CSV through
+    load_qv_csv semantics, or use `finite_difference_velocities` for rows beyond the shipped v_ref2.csv (400 rows)."""
+    rows = []
+    with open(q_pin_path) as f:
+        for line in f:
+            vals = []
+            for tok in line.strip().split(","):
+                try:
+                    vals.append(float(tok))
+                except ValueError:
+                    continue
+            if len(vals) == NQ:
+                rows.append(vals)
+    if not rows:
+        raise RuntimeError("No valid reference states loaded")
+    return pinocchio_to_mujoco_q(np.asarray(rows, dtype=np.float64))
+
+
 def load_contact_csv(path):
     rows = []
     with open(path) as f:

@@ -151,3 +151,20 @@ def test_no_cpu_fallback_without_gpu():
     from mpc_ilqr_mujoco_b200 import gpu
     with pytest.raises(gpu.H1IlqrError):
         gpu.H1IlqrBatch(Config().build_weights(), N=25, batch=1)
+
+
+def test_pinocchio_order_reference_loader(tmp_path):
+    """h1_walking_pin.csv (BASELINE config 2) is stored in Pinocchio order; its rows convert exactly to the MuJoCo-ordered
+    q_ref2_mj.csv that the shipped config uses (get_contacts.py:18-41). Fixture: the first 64 rows of the file."""
+    from mpc_ilqr_mujoco_b200.references import load_q_pin_csv, pinocchio_to_mujoco_q
+    d = np.load(os.path.join(ROOT, "data", "h1_refs.npz"))
+    pin = d["walking_pin_q_head"]
+    assert pin.shape == (64, 26) and abs(np.linalg.norm(pin[0, 3:7]) - 1) < 1e-5 and pin[0, 6] > 0.99    # qw last
+    mj = pinocchio_to_mujoco_q(pin)
+    assert np.abs(mj - d["walking_q"][:64]).max() == 0.0
+    assert (pinocchio_to_mujoco_q(pin[5]) == mj[5]).all()
+    p = tmp_path / "pin.csv"
+    np.savetxt(p, pin, delimiter=",", fmt="%.6f")
+    with open(p, "a") as f:
+        f.write("1,2,3\n")                                   # malformed row: skipped
+    assert np.abs(load_q_pin_csv(str(p)) - mj).max() < 1e-12

@@ -20,4 +20,8 @@ for tag, q, v, c in (("walking", "q_ref2_mj.csv", "v_ref2.csv", "contact_walking
     out[f"{tag}_q"], out[f"{tag}_v"] = Q, V
     out[f"{tag}_contact"] = load_contact_csv(f"{REF}/data/{c}")
     print(tag, Q.shape, V.shape, out[f"{tag}_contact"].shape)
+# first rows of the Pinocchio-ordered walking file (BASELINE config 2 names it): fixture of the order conversion test
+import csv
+with open(f"{REF}/data/h1_walking_pin.csv") as f:
+    out["walking_pin_q_head"] = np.array([[float(t) for t in row] for _, row in zip(range(64), csv.reader(f))])
 np.savez_compressed("data/h1_refs.npz", **out)
