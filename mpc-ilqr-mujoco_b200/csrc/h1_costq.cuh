@@ -24,6 +24,10 @@ constexpr int CQ_SETS = 3;     // 0: CoM, 1: left ankle frame, 2: right ankle fr
 constexpr int CQ_ROWS = 20;    // Jacobian rows: per set P(3) then U(3) -> 18, + 2 balance residual rows
 constexpr int CQ_MAXOUTER = 28;
 constexpr int CQ_LD = NX + 1;   // leading dimension of the Jacobian rows: = 4 (mod 8) doubles, conflict-free DMMA fragment loads
+// TWO warps work on one knot (lanes 0..63 share one CostWarp): the kernel is issue-latency bound per warp and its
+// occupancy is set by the 25.8 KB of per-knot scratch, so two warps per scratch block double the warps an SM holds
+// (measured: 8 -> 12 resident warps); the phases are loops over columns / joint pairs / tiles that split evenly.
+constexpr int CQ_LANES = 64;
 
 struct CostWarp {
   double xt[NX];                 // Pinocchio-ordered state
@@ -68,7 +72,7 @@ H1_DEV bool cq_is_anc(const CostModel& cm, int k, int l) {  // k ancestor-or-sel
 
 // ---- phase 0: stage the state in Pinocchio order (convertMuJoCoToPinocchio), sin/cos ----
 H1_DEV void ph_cq_load(int lane, CostWarp& w, const double* x) {
-  for (int i = lane; i < NX; i += 32) {
+  for (int i = lane; i < NX; i += CQ_LANES) {
     int src = i;
     if (i >= 3 && i < 6) src = i + 1; else if (i == 6) src = 3;
     w.xt[i] = x[src];
@@ -114,7 +118,7 @@ H1_DEV void ph_cq_walk(int lane, const CostModel& cm, CostWarp& w) {
   }
 }
 
-// ---- phase 2: per point set, r_l = a_l x mu_l (lane <-> joint l); set centroids on lanes 20..22 ----
+// ---- phase 2: per point set, r_l = a_l x mu_l (lane <-> joint l); set centroids / base rotation on lanes 32..35 ----
 H1_DEV void ph_cq_sets(int lane, const CostModel& cm, CostWarp& w) {
   if (lane >= 1 && lane < NB) {
     const int l = lane;
@@ -135,16 +139,16 @@ H1_DEV void ph_cq_sets(int lane, const CostModel& cm, CostWarp& w) {
       }
     }
   }
-  if (lane == 20) {
+  if (lane == 32) {
     double s[3] = {0, 0, 0};
     for (int i = 0; i < NB; ++i) { const double m = cm.wmass[i]; s[0] += m * w.c[i][0]; s[1] += m * w.c[i][1]; s[2] += m * w.c[i][2]; }
     w.rr[0][0] = s[0]; w.rr[0][1] = s[1]; w.rr[0][2] = s[2];
   }
-  if (lane == 21 || lane == 22) {
-    const int f = lane - 21, fb = cm.foot_body[f];
+  if (lane == 33 || lane == 34) {
+    const int f = lane - 33, fb = cm.foot_body[f];
     for (int i = 0; i < 3; ++i) w.rr[1 + f][i] = w.o[fb][i];
   }
-  if (lane == 23) {
+  if (lane == 35) {
     const double* xi = &w.xt[3];
     const double x = xi[0], y = xi[1], z = xi[2], q = xi[3];
     const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
@@ -157,7 +161,7 @@ H1_DEV void ph_cq_sets(int lane, const CostModel& cm, CostWarp& w) {
   }
 }
 
-// ---- phase 3: D_l, u_theta_l per set (lane <-> joint); set velocities u on lanes 20..22 ----
+// ---- phase 3: D_l, u_theta_l per set (lane <-> joint); set velocities u on lanes 32..34 ----
 H1_DEV void ph_cq_vel(int lane, const CostModel& cm, CostWarp& w) {
   const double* vb = &w.xt[NQ];
   const double* wb = &w.xt[NQ + 3];
@@ -177,8 +181,8 @@ H1_DEV void ph_cq_vel(int lane, const CostModel& cm, CostWarp& w) {
       w.uth[s][l][0] = t1[0] + t2[0]; w.uth[s][l][1] = t1[1] + t2[1]; w.uth[s][l][2] = t1[2] + t2[2];
     }
   }
-  if (lane >= 20 && lane < 20 + CQ_SETS) {
-    const int s = lane - 20;
+  if (lane >= 32 && lane < 32 + CQ_SETS) {
+    const int s = lane - 32;
     double acc[3];
     cross3(wb, w.rr[s], acc);
     acc[0] += vb[0]; acc[1] += vb[1]; acc[2] += vb[2];
@@ -279,7 +283,7 @@ H1_DEV void ph_cq_terms(int lane, const H1Weights& wt, const KnotTargets& kt, Co
 // ---- phase 5: Jacobian rows (lane <-> state column) and the contraction tables (lane <-> joint pairs) ----
 H1_DEV void ph_cq_rows(int lane, const CostModel& cm, CostWarp& w) {
   // rows: J_P(s) = [I | Ra rr | R r_l | 0],  J_U(s) = [0 | Ra u | R uth_l | R, R(e_m x rr), R r_j]
-  for (int i = lane; i < NX; i += 32) {
+  for (int i = lane; i < NX; i += CQ_LANES) {
     for (int s = 0; s < CQ_SETS; ++s) {
       double cp[3] = {0, 0, 0}, cu[3] = {0, 0, 0};
       if (i < 3) { cp[0] = (i == 0) ? 1.0 : 0.0; cp[1] = (i == 1) ? 1.0 : 0.0; cp[2] = (i == 2) ? 1.0 : 0.0; }
@@ -298,7 +302,7 @@ H1_DEV void ph_cq_rows(int lane, const CostModel& cm, CostWarp& w) {
   }
 }
 H1_DEV void ph_cq_rows2(int lane, CostWarp& w) {  // balance residual rows (need the CoM rows complete)
-  for (int i = lane; i < NX; i += 32) {
+  for (int i = lane; i < NX; i += CQ_LANES) {
     double a = 0.0, b = 0.0;
     if (w.bal_on) {
       a = w.rows[0][i] + w.bal_sg * w.rows[3][i] + w.bal_k0 * w.rows[2][i];
@@ -315,7 +319,7 @@ H1_DEV void ph_cq_tables(int lane, const CostModel& cm, CostWarp& w) {
   for (int s = 0; s < CQ_SETS; ++s) { mtv3(w.R, w.lamP[s], RtP[s]); mtv3(w.R, w.lamU[s], RtU[s]); }
   // (theta_k, theta_l), (theta_k, thdot_l): lane <-> ordered pair index
   // (pairs k <= l from the model's list: the ancestor-or-self pairs come first, the others only store zeros)
-  for (int idx = lane; idx < CQ_NPAIRS; idx += 32) {
+  for (int idx = lane; idx < CQ_NPAIRS; idx += CQ_LANES) {
     const int k = cm.pair_k[idx], l = cm.pair_l[idx];
     double jj = 0.0, jv = 0.0;
     if (idx < cm.n_anc_pairs) {
@@ -356,9 +360,9 @@ H1_DEV void ph_cq_tables(int lane, const CostModel& cm, CostWarp& w) {
       w.QJ[a][k] = v;
     }
   }
-  // (xi_a, v) : lanes 0..24 <-> velocity entry ; (xi_a, xi_b): lanes 25..31 + wrap
-  if (lane < NV) {
-    const int m = lane;
+  // (xi_a, v) : lanes 32..56 <-> velocity entry ; (xi_a, xi_b): lanes 16..31
+  if (lane >= 32 && lane < 32 + NV) {
+    const int m = lane - 32;
     for (int a = 0; a < 4; ++a) {
       double v = 0.0;
       for (int s = 0; s < CQ_SETS; ++s) {
@@ -376,7 +380,7 @@ H1_DEV void ph_cq_tables(int lane, const CostModel& cm, CostWarp& w) {
       w.QV[a][m] = v;
     }
   }
-  if (lane >= 16) {  // 16 (a,b) pairs on lanes 16..31; d2R/dxi_a dxi_b = dR/dxi_a evaluated at e_b
+  if (lane >= 16 && lane < 32) {  // 16 (a,b) pairs on lanes 16..31; d2R/dxi_a dxi_b = dR/dxi_a evaluated at e_b
     const int a = (lane - 16) >> 2, b = (lane - 16) & 3;
     double e[4] = {0, 0, 0, 0};
     if (b == 0) e[0] = 1.0; else if (b == 1) e[1] = 1.0; else if (b == 2) e[2] = 1.0; else e[3] = 1.0;
@@ -412,7 +416,7 @@ H1_DEV void limit_d(double val, double lo, double hi, double wgt, double* g, dou
 H1_DEV void ph_cq_grad(int lane, const DynModel& md, const H1Weights& wt, CostWarp& w, const double* x,
                        const double* x_ref, bool terminal, double* lx) {
   const double* Qd = terminal ? wt.Qfdiag : wt.Qdiag;
-  for (int i = lane; i < NX; i += 32) {
+  for (int i = lane; i < NX; i += CQ_LANES) {
     double g = Qd[i] * (x[i] - x_ref[i]);
     double hd = Qd[i];
     for (int r = 0; r < CQ_ROWS; ++r)
@@ -436,7 +440,8 @@ H1_DEV void ph_cq_store(int lane, const DynModel& md, const H1Weights& wt, const
   // contraction dimension: 8 x 8 tiles of the lower triangle on the fp64 tensor core (DMMA m8n8k4), <= 7 k-steps.
   {
     constexpr int KS = (CQ_MAXOUTER + 3) / 4;
-    const int g = lane >> 2, t4 = lane & 3, nks = (no + 3) >> 2;
+    const int wl = lane & 31, half = lane >> 5;     // lane within its warp; which of the two warps
+    const int g = wl >> 2, t4 = wl & 3, nks = (no + 3) >> 2;
     const double* ra[KS]; const double* rb[KS]; double cc[KS];
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
@@ -453,7 +458,7 @@ H1_DEV void ph_cq_store(int lane, const DynModel& md, const H1Weights& wt, const
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) af[ks] = (ks < nks) ? cc[ks] * ra[ks][ia] : 0.0;
 #pragma unroll 1
-      for (int jt = 0; jt <= it; ++jt) {
+      for (int jt = (it + half) & 1; jt <= it; jt += 2) {   // tiles of a row strip alternate between the two warps (14 tiles each)
         const int jb = min(8 * jt + g, NX - 1);
         double c0 = 0.0, c1 = 0.0;
 #pragma unroll
@@ -466,8 +471,9 @@ H1_DEV void ph_cq_store(int lane, const DynModel& md, const H1Weights& wt, const
           if (i < NX && j <= i) {
             double h = (q ? c1 : c0) + cq_block(w, i, j);
             if (i == j) h = diag_terms(i, h);
-            lxx[j * NX + i] = h;
-            lxx[i * NX + j] = h;
+            lxx[j * NX + i] = h;      // LOWER triangle only (column-major, rows >= column): the backward pass reads nothing else,
+                                      // h1ilqr_get_cost_quadratics mirrors it for the caller; the strided mirror stores were half
+                                      // of this kernel's store instructions and 10 KB of its 24 KB of output per knot
           }
         }
       }
@@ -475,7 +481,7 @@ H1_DEV void ph_cq_store(int lane, const DynModel& md, const H1Weights& wt, const
   }
 #else
   for (int j = 0; j < NX; ++j) {      // lower triangle column by column, mirrored on store
-    for (int i = j + lane; i < NX; i += 32) {
+    for (int i = j + lane; i < NX; i += CQ_LANES) {
       double h = cq_block(w, i, j);
       for (int k = 0; k < no; ++k) h += w.outer_c[k] * w.rows[w.outer_a[k]][i] * w.rows[w.outer_b[k]][j];
       if (i == j) h = diag_terms(i, h);
@@ -485,7 +491,7 @@ H1_DEV void ph_cq_store(int lane, const DynModel& md, const H1Weights& wt, const
   }
 #endif
   if (!terminal) {   // luu = diag(R + control-limit curvature): zeros first, then the diagonal by its own lanes
-    for (int e = lane; e < NU * NU; e += 32) {
+    for (int e = lane; e < NU * NU; e += CQ_LANES) {
       const int i = e % NU, j = e / NU;
       if (i != j) luu[e] = 0.0;
     }
@@ -501,10 +507,11 @@ H1_DEV void ph_cq_store(int lane, const DynModel& md, const H1Weights& wt, const
 }
 
 #if defined(__CUDACC__)
-#define H1_CQ_PHASE(call) { call; __syncwarp(); }
-#define H1_CQ_LANE const int lane = threadIdx.x & 31;
+// the two warps of a knot meet at a named barrier (ids 1.. : one per knot slot of the CTA)
+#define H1_CQ_PHASE(call) { call; asm volatile("bar.sync %0, 64;" ::"r"(1 + (int)(threadIdx.x >> 6)) : "memory"); }
+#define H1_CQ_LANE const int lane = threadIdx.x & (CQ_LANES - 1);
 #else
-#define H1_CQ_PHASE(call) { for (int lane = 0; lane < 32; ++lane) { call; } }
+#define H1_CQ_PHASE(call) { for (int lane = 0; lane < CQ_LANES; ++lane) { call; } }
 #define H1_CQ_LANE
 #endif
 

@@ -6,9 +6,13 @@
 
 namespace h1 {
 
-// ---- cost quadratics: one warp per (instance, knot) incl. the terminal knot ----
+// ---- cost quadratics: two warps per (instance, knot) incl. the terminal knot; two knots per CTA ----
 constexpr int CQ_WARPS = 4;
-__global__ void __launch_bounds__(CQ_WARPS * 32)
+constexpr int CQ_KNOTS = CQ_WARPS * 32 / CQ_LANES;
+#ifndef H1_CQ_MINB
+#define H1_CQ_MINB 4   // 16 resident warps at 128 registers (r02t: 4.77 ms per 8192-instance launch; 3 CTAs / 165 registers: 5.42 ms)
+#endif
+__global__ void __launch_bounds__(CQ_WARPS * 32, H1_CQ_MINB)
 k_cost_quadratics(const CostModel* gcm, const DynModel* gmd, const H1Weights* gw, RefTable refs, int B, int N,
                   const int* __restrict__ active, const double* __restrict__ xbar, const double* __restrict__ ubar,
                   double* __restrict__ lx, double* __restrict__ lu, double* __restrict__ lxx,
@@ -16,8 +20,8 @@ k_cost_quadratics(const CostModel* gcm, const DynModel* gmd, const H1Weights* gw
   extern __shared__ __align__(16) unsigned char smem[];
   const CostModel* cm;
   unsigned char* p = stage_model(smem, gcm, &cm);
-  CostWarp& w = reinterpret_cast<CostWarp*>(p)[threadIdx.x >> 5];
-  const long gwarp = (long)blockIdx.x * CQ_WARPS + (threadIdx.x >> 5);
+  CostWarp& w = reinterpret_cast<CostWarp*>(p)[threadIdx.x / CQ_LANES];
+  const long gwarp = (long)blockIdx.x * CQ_KNOTS + (threadIdx.x / CQ_LANES);   // knot slot (both warps of a pair leave together)
   if (gwarp >= (long)B * (N + 1)) return;
   const int inst = (int)(gwarp / (N + 1)), t = (int)(gwarp % (N + 1));
   if (active && !active[inst]) return;
@@ -274,6 +278,16 @@ __global__ void k_copy_x0(int B, int N, const double* __restrict__ xbar, double*
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   for (int k = 0; k < NX; ++k) x0[(size_t)i * NX + k] = xbar[(size_t)i * (N + 1) * NX + k];
+}
+// lxx is kept as its lower triangle on the device (k_cost_quadratics): fill the upper one for a caller that wants the matrix
+__global__ void k_mirror_lower(long nmat, double* __restrict__ lxx) {
+  const long m = blockIdx.x;
+  if (m >= nmat) return;
+  double* M = lxx + m * NX * NX;
+  for (int i = threadIdx.x; i < NX * NX; i += blockDim.x) {
+    const int c = i / NX, r = i - c * NX;
+    if (r < c) M[i] = M[r * NX + c];
+  }
 }
 __global__ void k_fill_int(int n, int* p, int v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

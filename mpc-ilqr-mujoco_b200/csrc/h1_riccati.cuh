@@ -204,7 +204,10 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
   __syncthreads();
   prefetch_ab(N - 1, tid, nt);
   for (int i = tid; i < LDX; i += nt) s.Vx[i] = (i < NX) ? lxN[i] : 0.0;
-  for (int i = tid; i < NX * NX; i += nt) { const int c = i / NX, r = i - c * NX; s.V[c * LDX + r] = lxxN[i]; }
+  for (int i = tid; i < NX * NX; i += nt) {   // lxx holds its LOWER triangle (k_cost_quadratics): mirrored on load
+    const int c = i / NX, r = i - c * NX;
+    s.V[c * LDX + r] = lxxN[min(c, r) * NX + max(c, r)];
+  }
   bool nonfinite = false;
   double* const G = s.W + RIC_G_OFF;
   // Operand fetches are branch-free: out-of-range rows / columns are redirected to zero pads (a divergent branch around a
@@ -392,7 +395,7 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
       asm volatile("bar.sync 1, 224;" ::: "memory");
       if (t > 0) prefetch_ab(t - 1, tid, 7 * 32);
       const double* Lt = lxx + ((size_t)inst * (N + 1) + t) * NX * NX;
-      for (int i = tid; i < NX * NX; i += 7 * 32) cp_async8(&Lpre[i], Lt + i);
+      for (int i = tid; i < NX * NX; i += 7 * 32) { const int c = i / NX, r = i - c * NX; if (r >= c) cp_async8(&Lpre[i], Lt + i); }   // lower triangle: all G5 reads
     } else {
       if (quu_ldlt(s)) {          // Eigen::LLT failed: Quu += 1e-4 I once, no re-check (quirk Q9), refactor
         for (int i = lane; i < NU; i += 32) s.Quu[i * LDU + i] += 1e-4;

@@ -188,7 +188,7 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   h->smem_dyn4 = mdl + 4 * sizeof(DynWarp);
   h->smem_lin = mdl + LIN_WARPS * sizeof(DynWarp) + (LIN_EVALS * NX + NX + NU) * sizeof(double);
   h->smem_lina = mdl + LINA_WARPS * sizeof(TanWarpT<Dual>) + sizeof(PrimalFactor) + (NX + NU) * sizeof(double);
-  h->smem_cq = cml + CQ_WARPS * sizeof(CostWarp);
+  h->smem_cq = cml + CQ_KNOTS * sizeof(CostWarp);
   h->smem_ls = mdl + H1ILQR_NALPHA * sizeof(DynWarp) + (H1ILQR_NALPHA + H1ILQR_NALPHA * (NX + NU)) * sizeof(double);
   h->smem_ric = sizeof(RiccatiSmem);
   h->smem_seq = mdl;
@@ -359,8 +359,8 @@ static void launch_linearize(H1Ilqr* h, const int* mask, bool factors_ready = fa
   LAUNCHED();
 }
 static void launch_cost_quadratics(H1Ilqr* h, const int* mask) {
-  const long warps = (long)h->B * (h->N + 1);
-  const int blocks = (int)((warps + CQ_WARPS - 1) / CQ_WARPS);
+  const long warps = (long)h->B * (h->N + 1);   // knots (two warps each)
+  const int blocks = (int)((warps + CQ_KNOTS - 1) / CQ_KNOTS);
   k_cost_quadratics<<<blocks, CQ_WARPS * 32, h->smem_cq, h->stream>>>(h->d_cost, h->d_dyn, h->d_w, ref_table(h), h->B,
                                                                      h->N, mask, h->xbar, h->ubar, h->lx, h->lu, h->lxx,
                                                                      h->luu);
@@ -1120,7 +1120,11 @@ int h1ilqr_get_cost_quadratics(H1Ilqr* h, double* lx, double* lu, double* lxx, d
   GUARD(h);
   if (lx) D2H(lx, h->lx, SZ((h->N + 1) * NX) * sizeof(double));
   if (lu) D2H(lu, h->lu, SZ(h->N * NU) * sizeof(double));
-  if (lxx) D2H(lxx, h->lxx, SZ((h->N + 1) * NX * NX) * sizeof(double));
+  if (lxx) {   // the device keeps the lower triangle: mirror it for the caller
+    k_mirror_lower<<<(unsigned)SZ(h->N + 1), 128, 0, h->stream>>>((long)SZ(h->N + 1), h->lxx);
+    LAUNCHED();
+    D2H(lxx, h->lxx, SZ((h->N + 1) * NX * NX) * sizeof(double));
+  }
   if (luu) D2H(luu, h->luu, SZ(h->N * NU * NU) * sizeof(double));
   SYNC(); return 0;
 }
