@@ -1,6 +1,6 @@
 TAG=r02q; O=gpurun_out; mkdir -p $O /tmp/nc
-H1_PROF_WORKLOAD=bench timeout 900 ncu --set full --clock-control none --import-source on -c 16 \
-    --kernel-name 'regex:k_rollout_seq|k_linearize|k_cost_quadratics|k_backward|k_line_search|k_primal_factor_seq' \
+H1_PROF_WORKLOAD=bench timeout 900 ncu --set full --clock-control none --import-source on -c 18 \
+    --kernel-name 'regex:k_rollout|k_linearize|k_cost_quadratics|k_backward|k_line_search|k_primal_factor_seq' \
     -o /tmp/nc/full -f python tools/prof_run.py 4096 > $O/${TAG}_ncu.log 2>&1
 tail -3 $O/${TAG}_ncu.log
 python tools/ncu_kernels.py /tmp/nc/full.ncu-rep > $O/${TAG}_ncu_top_kernels.txt 2>&1

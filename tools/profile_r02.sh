@@ -6,8 +6,8 @@ TAG=${1:-r02}
 O=gpurun_out; mkdir -p $O /tmp/nc
 (time timeout 900 python -m pytest tests -m gpu -q) > $O/${TAG}_tests.log 2>&1; tail -4 $O/${TAG}_tests.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; tail -2 $O/${TAG}_smoke.log
-H1_PROF_WORKLOAD=bench timeout 900 ncu --set full --clock-control none --import-source on -c 16 \
-    --kernel-name 'regex:k_rollout_seq|k_linearize|k_cost_quadratics|k_backward|k_line_search|k_primal_factor_seq' \
+H1_PROF_WORKLOAD=bench timeout 900 ncu --set full --clock-control none --import-source on -c 18 \
+    --kernel-name 'regex:k_rollout|k_linearize|k_cost_quadratics|k_backward|k_line_search|k_primal_factor_seq' \
     -o /tmp/nc/full -f python tools/prof_run.py 4096 > $O/${TAG}_ncu.log 2>&1
 python tools/ncu_kernels.py /tmp/nc/full.ncu-rep > $O/${TAG}_ncu_top_kernels.txt 2>&1
 python tools/ncu_kernel_metrics.py /tmp/nc/full.ncu-rep 4096 $O/${TAG}_kernel_metrics.json
