@@ -470,13 +470,13 @@ def main():
 # Riccati backward pass: algorithmic flops of one knot (the five contractions with shared products, the
 # factorisation and the solves) and its algorithmic bytes (A, B, lx, lu, lxx, luu read; K, kff written).
 BWD_FLOPS_PER_KNOT = 1.153e6
-BWD_ALG_BYTES_PER_KNOT = 52816.0 + 7904.0
+BWD_ALG_BYTES_PER_KNOT = 52816.0 - (51 * 51 - 51 * 52 // 2) * 8.0 + 7904.0   # (lxx: lower triangle only, 1326 of 2601 entries)
 BWD_TRAFFIC_BYTES_PER_KNOT = (5.500e9 + 0.817e9) / (4096 * 25)      # fallback when profiles/r02_kernel_metrics.json is absent (r01i capture)
 # Linearization: algorithmic bytes per knot — A_k, B_k written; x_k, u_k and the factor (L, D, a) read; the parked tangents
 # written and read once
 LIN_ALG_BYTES_PER_KNOT = (51 * 51 + 51 * 19 + 51 + 19) * 8.0 + (25 * 11 + 25 + 25) * 8.0 + 2 * 48 * 25 * 8.0
-# Cost quadratics: lx, lu, lxx, luu written; x, u read (per knot, incl. the terminal one)
-CQ_ALG_BYTES_PER_KNOT = (51 + 19 + 51 * 51 + 19 * 19 + 51 + 19) * 8.0
+# Cost quadratics: lx, lu, lxx (lower triangle), luu written; x, u read (per knot, incl. the terminal one)
+CQ_ALG_BYTES_PER_KNOT = (51 + 19 + 51 * 52 // 2 + 19 * 19 + 51 + 19) * 8.0
 # Line search: fp64 operations executed per f_D evaluation of the quad kernel (fallback; the ncu figure replaces it)
 LS_FLOPS_PER_EVAL = 3.2e4
 
