@@ -84,6 +84,13 @@ int h1ilqr_horizon(const H1Ilqr* h);
 /* Replaces RobotUtils::setCostWeights + set*Weight + setConstraintWeights. */
 int h1ilqr_set_weights(H1Ilqr* h, const H1Weights* w);
 
+/* Full symmetric cost matrices: RobotUtils::setCostWeights stores whole Q, R, Qf and iLQR multiplies them
+ * (ilqr.cpp:145-150: lx = Q (x - x_ref), lxx = Q, lu = R (u - u_ref), luu = R; :372-373, :441: 0.5 e'Qe in the line-search
+ * cost). Column-major Q [51 x 51], R [19 x 19], Qf [51 x 51]; they must be symmetric (H1ILQR_EARG otherwise). Their diagonals
+ * replace Qdiag / Rdiag / Qfdiag of the last h1ilqr_set_weights, which in turn keeps any off-diagonal parts set here. All
+ * three NULL = diagonal weights again. */
+int h1ilqr_set_weight_matrices(H1Ilqr* h, const double* Q, const double* R, const double* Qf);
+
 /* Reference window for every instance. Replaces MPC::extractReferenceWindow /
  * RobotUtils::getReferenceWindow (src/ilqr/mpc.cpp:163-166, robot_utils.cpp:422-443) plus the
  * horizon-local lookups isStance / getEEReference / getCoMVelReference (robot_utils.cpp:494-549).

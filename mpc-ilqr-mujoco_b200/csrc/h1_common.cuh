@@ -26,6 +26,25 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 #endif
 
 constexpr int NB = H1_NB, NQ = H1_NQ, NV = H1_NV, NX = H1_NX, NU = H1_NU;
+
+// Device-side weights: the C-ABI struct (diagonals of Q / R / Qf + scalar task weights) followed by an optional pointer to
+// the OFF-DIAGONAL parts of symmetric full Q, R, Qf (iLQR multiplies full matrices, ilqr.cpp:145-150, 372-373, 441):
+// [Qoff 51x51 | Roff 19x19 | Qfoff 51x51], column-major, zero diagonals; nullptr = the matrices are diagonal (what
+// Config::buildCostMatrices builds). Every kernel receives `const H1Weights*` that points at the first member of one of
+// these, so the cost functions reach the pointer without a change of their signatures.
+struct DevWeights {
+  H1Weights w;
+  const double* qoff;
+};
+constexpr int QOFF_R = NX * NX, QOFF_QF = NX * NX + NU * NU, QOFF_SIZE = 2 * NX * NX + NU * NU;
+H1_HD const double* weights_offdiag(const H1Weights& wt) {
+#if defined(__CUDACC__)
+  return reinterpret_cast<const DevWeights&>(wt).qoff;
+#else
+  (void)wt;
+  return nullptr;   // (emulation builds hand over a bare H1Weights)
+#endif
+}
 constexpr int MAXSLOT = 11;  // base 6 + longest hinge chain 5
 constexpr int NCPT = H1_NFOOT * H1_NCP;
 

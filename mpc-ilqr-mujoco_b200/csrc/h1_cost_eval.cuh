@@ -75,6 +75,19 @@ __device__ __forceinline__ double knot_cost_warp(const DynModel& md, const DynWa
     const double e = xi - r.x_ref[t * NX + i];
     acc += 0.5 * e * Qd[i] * e;
   }
+  if (const double* qo = weights_offdiag(wt)) {   // off-diagonal parts of full Q / R / Qf (0.5 e'Qe, ilqr.cpp:372-373, 441)
+    const double* Qo = qo + (terminal ? QOFF_QF : 0);
+    for (int i = lane; i < NX; i += 32) {
+      double sacc = 0.0;
+      for (int j = 0; j < NX; ++j) sacc += Qo[j * NX + i] * (((j < NQ) ? w.q[j] : w.v[j - NQ]) - r.x_ref[t * NX + j]);
+      acc += 0.5 * (((i < NQ) ? w.q[i] : w.v[i - NQ]) - r.x_ref[t * NX + i]) * sacc;
+    }
+    if (!terminal && lane < NU) {
+      double sacc = 0.0;
+      for (int j = 0; j < NU; ++j) sacc += qo[QOFF_R + j * NU + lane] * (u[j] - r.u_ref[t * NU + j]);
+      acc += 0.5 * (u[lane] - r.u_ref[t * NU + lane]) * sacc;
+    }
+  }
   if (lane < NU) {
     const double ui = terminal ? 0.0 : u[lane];
     if (!terminal) { const double e = ui - r.u_ref[t * NU + lane]; acc += 0.5 * e * wt.Rdiag[lane] * e; }

@@ -413,12 +413,15 @@ H1_DEV void limit_d(double val, double lo, double hi, double wgt, double* g, dou
   if (val > hi_s || val < lo_s) *h += 2.0 * wgt;
 }
 // gradient lx and the diagonal additions of lxx (kept in w.hdiag for the assembly: no global loads inside the tile loop)
-H1_DEV void ph_cq_grad(int lane, const DynModel& md, const H1Weights& wt, CostWarp& w, const double* x,
+template <bool FULLQ>
+H1_DEV void ph_cq_grad(int lane, const DynModel& md, const H1Weights& wt, const double* qo, CostWarp& w, const double* x,
                        const double* x_ref, bool terminal, double* lx) {
   const double* Qd = terminal ? wt.Qfdiag : wt.Qdiag;
+  const double* Qo = (FULLQ && qo) ? qo + (terminal ? QOFF_QF : 0) : nullptr;
   for (int i = lane; i < NX; i += CQ_LANES) {
     double g = Qd[i] * (x[i] - x_ref[i]);
     double hd = Qd[i];
+    if (FULLQ && Qo) for (int j = 0; j < NX; ++j) g += Qo[j * NX + i] * (x[j] - x_ref[j]);   // lx = Q (x - x_ref) with a full Q (ilqr.cpp:145)
     for (int r = 0; r < CQ_ROWS; ++r)
       if (w.gcoef[r] != 0.0) g += w.gcoef[r] * w.rows[r][i];
     if (i >= 3 && i < 7) g += w.gq[i - 3];
@@ -430,7 +433,8 @@ H1_DEV void ph_cq_grad(int lane, const DynModel& md, const H1Weights& wt, CostWa
     w.hdiag[i] = hd;
   }
 }
-H1_DEV void ph_cq_store(int lane, const DynModel& md, const H1Weights& wt, const CostWarp& w, const double* x,
+template <bool FULLQ>
+H1_DEV void ph_cq_store(int lane, const DynModel& md, const H1Weights& wt, const double* qo, const CostWarp& w, const double* x,
                         const double* u, const double* x_ref, const double* u_ref, bool terminal, double* lx,
                         double* lu, double* lxx, double* luu) {
   const int no = w.n_outer;
@@ -440,6 +444,7 @@ H1_DEV void ph_cq_store(int lane, const DynModel& md, const H1Weights& wt, const
   // contraction dimension: 8 x 8 tiles of the lower triangle on the fp64 tensor core (DMMA m8n8k4), <= 7 k-steps.
   {
     constexpr int KS = (CQ_MAXOUTER + 3) / 4;
+    const double* Qo = (FULLQ && qo) ? qo + (terminal ? QOFF_QF : 0) : nullptr;
     const int wl = lane & 31, half = lane >> 5;     // lane within its warp; which of the two warps
     const int g = wl >> 2, t4 = wl & 3, nks = (no + 3) >> 2;
     const double* ra[KS]; const double* rb[KS]; double cc[KS];
@@ -471,6 +476,7 @@ H1_DEV void ph_cq_store(int lane, const DynModel& md, const H1Weights& wt, const
           if (i < NX && j <= i) {
             double h = (q ? c1 : c0) + cq_block(w, i, j);
             if (i == j) h = diag_terms(i, h);
+            else if (FULLQ && Qo) h += Qo[j * NX + i];                     // lxx = Q + ... with a full Q (ilqr.cpp:149)
             lxx[j * NX + i] = h;      // LOWER triangle only (column-major, rows >= column): the backward pass reads nothing else,
                                       // h1ilqr_get_cost_quadratics mirrors it for the caller; the strided mirror stores were half
                                       // of this kernel's store instructions and 10 KB of its 24 KB of output per knot
@@ -491,13 +497,15 @@ H1_DEV void ph_cq_store(int lane, const DynModel& md, const H1Weights& wt, const
   }
 #endif
   if (!terminal) {   // luu = diag(R + control-limit curvature): zeros first, then the diagonal by its own lanes
+    const double* Ro = (FULLQ && qo) ? qo + QOFF_R : nullptr;
     for (int e = lane; e < NU * NU; e += CQ_LANES) {
       const int i = e % NU, j = e / NU;
-      if (i != j) luu[e] = 0.0;
+      if (i != j) luu[e] = (FULLQ && Ro) ? Ro[e] : 0.0;                     // luu = R + ... (ilqr.cpp:150)
     }
     if (lane < NU) {
       const int i = lane;
       double g = wt.Rdiag[i] * (u[i] - u_ref[i]);
+      if (FULLQ && Ro) for (int j = 0; j < NU; ++j) g += Ro[j * NU + i] * (u[j] - u_ref[j]);   // lu = R (u - u_ref) (ilqr.cpp:146)
       double h = wt.Rdiag[i];
       limit_d(u[i], md.ctrl_lo[i], md.ctrl_hi[i], wt.w_control_limits, &g, &h);
       lu[i] = g;
@@ -515,9 +523,11 @@ H1_DEV void ph_cq_store(int lane, const DynModel& md, const H1Weights& wt, const
 #define H1_CQ_LANE
 #endif
 
+template <bool FULLQ = true>   // FULLQ = false: compiled without the full-matrix branches (the kernel used for diagonal weights)
 H1_DEV void cost_quadratics_warp(const CostModel& cm, const DynModel& md, const H1Weights& wt, CostWarp& w,
                                  const double* x, const double* u, const double* x_ref, const double* u_ref,
-                                 const KnotTargets& kt, double* lx, double* lu, double* lxx, double* luu) {
+                                 const KnotTargets& kt, double* lx, double* lu, double* lxx, double* luu,
+                                 const double* qo = nullptr) {   // qo: off-diagonal parts of full Q / R / Qf (DevWeights::qoff) or nullptr
   H1_CQ_LANE
   H1_CQ_PHASE(ph_cq_load(lane, w, x))
   H1_CQ_PHASE(ph_cq_walk(lane, cm, w))
@@ -527,8 +537,8 @@ H1_DEV void cost_quadratics_warp(const CostModel& cm, const DynModel& md, const 
   H1_CQ_PHASE(ph_cq_rows(lane, cm, w))
   H1_CQ_PHASE(ph_cq_rows2(lane, w))
   H1_CQ_PHASE(ph_cq_tables(lane, cm, w))
-  H1_CQ_PHASE(ph_cq_grad(lane, md, wt, w, x, x_ref, kt.terminal, lx))
-  H1_CQ_PHASE(ph_cq_store(lane, md, wt, w, x, u, x_ref, u_ref, kt.terminal, lx, lu, lxx, luu))
+  H1_CQ_PHASE(ph_cq_grad<FULLQ>(lane, md, wt, qo, w, x, x_ref, kt.terminal, lx))
+  H1_CQ_PHASE(ph_cq_store<FULLQ>(lane, md, wt, qo, w, x, u, x_ref, u_ref, kt.terminal, lx, lu, lxx, luu))
 }
 
 }  // namespace h1

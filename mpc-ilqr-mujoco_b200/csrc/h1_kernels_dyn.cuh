@@ -146,6 +146,19 @@ __global__ void k_stage_cost(const DynModel* gmd, const H1Weights* gw, int n, co
     const double lo = md->jnt_lo[lane], hi = md->jnt_hi[lane];
     if (isfinite(lo) && isfinite(hi) && lo < hi) acc += limit_pen(x[(size_t)i * NX + 7 + lane], lo, hi, gw->w_joint_limits);
   }
+  if (const double* qo = weights_offdiag(*gw)) {   // off-diagonal parts of full Q / R / Qf
+    const double* Qo = qo + (terminal ? QOFF_QF : 0);
+    for (int k = lane; k < NX; k += 32) {
+      double sacc = 0.0;
+      for (int j = 0; j < NX; ++j) sacc += Qo[j * NX + k] * (x[(size_t)i * NX + j] - x_ref[(size_t)i * NX + j]);
+      acc += 0.5 * (x[(size_t)i * NX + k] - x_ref[(size_t)i * NX + k]) * sacc;
+    }
+    if (!terminal && lane < NU) {
+      double sacc = 0.0;
+      for (int j = 0; j < NU; ++j) sacc += qo[QOFF_R + j * NU + lane] * (u[(size_t)i * NU + j] - (u_ref ? u_ref[(size_t)i * NU + j] : 0.0));
+      acc += 0.5 * (u[(size_t)i * NU + lane] - (u_ref ? u_ref[(size_t)i * NU + lane] : 0.0)) * sacc;
+    }
+  }
   if (lane < 3 && gw->w_com > 0.0 && com_ref) {
     const double e = w.com[lane] - com_ref[(size_t)i * 3 + lane];
     acc += 0.5 * gw->w_com * e * e;

@@ -31,6 +31,25 @@ __device__ __forceinline__ double knot_cost_quad(const DynModel& md, const H1Wei
   const double* Qd = terminal ? wt.Qfdiag : wt.Qdiag;
   const double* xr = r.x_ref + t * NX;
   double acc = 0.0;
+  if (const double* qo = weights_offdiag(wt)) {   // off-diagonal parts of full Q / R / Qf: rows i = g (mod 4) on this lane
+    const double* Qo = qo + (terminal ? QOFF_QF : 0);
+#pragma unroll 1
+    for (int i = g; i < NX; i += 4) {
+      double sacc = 0.0;
+#pragma unroll 1
+      for (int j = 0; j < NX; ++j) sacc += Qo[j * NX + i] * (x[j] - xr[j]);
+      acc += 0.5 * (x[i] - xr[i]) * sacc;
+    }
+    if (!terminal) {
+#pragma unroll 1
+      for (int i = g; i < NU; i += 4) {
+        double sacc = 0.0;
+#pragma unroll 1
+        for (int j = 0; j < NU; ++j) sacc += qo[QOFF_R + j * NU + i] * (u[j] - r.u_ref[t * NU + j]);
+        acc += 0.5 * (u[i] - r.u_ref[t * NU + i]) * sacc;
+      }
+    }
+  }
 #pragma unroll
   for (int i = 0; i < Q4_CHAIN; ++i) {
     if (g == 3 && i == 0) continue;   // the torso is lane 2's

@@ -22,6 +22,25 @@ __device__ __forceinline__ double knot_cost_seq(const DynModel& md, const H1Weig
     const double e = x[i] - xr[i];
     acc += 0.5 * e * Qd[i] * e;
   }
+  if (const double* qo = weights_offdiag(wt)) {   // off-diagonal parts of full Q / R / Qf
+    const double* Qo = qo + (terminal ? QOFF_QF : 0);
+#pragma unroll 1
+    for (int i = 0; i < NX; ++i) {
+      double sacc = 0.0;
+#pragma unroll 1
+      for (int j = 0; j < NX; ++j) sacc += Qo[j * NX + i] * (x[j] - xr[j]);
+      acc += 0.5 * (x[i] - xr[i]) * sacc;
+    }
+    if (!terminal) {
+#pragma unroll 1
+      for (int i = 0; i < NU; ++i) {
+        double sacc = 0.0;
+#pragma unroll 1
+        for (int j = 0; j < NU; ++j) sacc += qo[QOFF_R + j * NU + i] * (u[j] - r.u_ref[t * NU + j]);
+        acc += 0.5 * (u[i] - r.u_ref[t * NU + i]) * sacc;
+      }
+    }
+  }
 #pragma unroll 1
   for (int i = 0; i < NU; ++i) {
     const double ui = terminal ? 0.0 : u[i];

@@ -12,11 +12,12 @@ constexpr int CQ_KNOTS = CQ_WARPS * 32 / CQ_LANES;
 #ifndef H1_CQ_MINB
 #define H1_CQ_MINB 4   // 16 resident warps at 128 registers (r02t: 4.77 ms per 8192-instance launch; 3 CTAs / 165 registers: 5.42 ms)
 #endif
+template <bool FULLQ>
 __global__ void __launch_bounds__(CQ_WARPS * 32, H1_CQ_MINB)
 k_cost_quadratics(const CostModel* gcm, const DynModel* gmd, const H1Weights* gw, RefTable refs, int B, int N,
                   const int* __restrict__ active, const double* __restrict__ xbar, const double* __restrict__ ubar,
                   double* __restrict__ lx, double* __restrict__ lu, double* __restrict__ lxx,
-                  double* __restrict__ luu) {
+                  double* __restrict__ luu, const double* __restrict__ qoff) {
   extern __shared__ __align__(16) unsigned char smem[];
   const CostModel* cm;
   unsigned char* p = stage_model(smem, gcm, &cm);
@@ -32,10 +33,10 @@ k_cost_quadratics(const CostModel* gcm, const DynModel* gmd, const H1Weights* gw
   KnotTargets kt;
   kt.com_ref = r.com_ref + 3 * t; kt.com_vel_ref = r.com_vel_ref + 3 * t; kt.ee_ref = r.ee_ref + 6 * t;
   kt.stance = r.stance + 2 * t; kt.terminal = terminal;
-  cost_quadratics_warp(*cm, *gmd, *gw, w, x, u, r.x_ref + t * NX, terminal ? nullptr : r.u_ref + t * NU, kt,
+  cost_quadratics_warp<FULLQ>(*cm, *gmd, *gw, w, x, u, r.x_ref + t * NX, terminal ? nullptr : r.u_ref + t * NU, kt,
                        lx + ((size_t)inst * (N + 1) + t) * NX, terminal ? nullptr : lu + ((size_t)inst * N + t) * NU,
                        lxx + ((size_t)inst * (N + 1) + t) * NX * NX,
-                       terminal ? nullptr : luu + ((size_t)inst * N + t) * NU * NU);
+                       terminal ? nullptr : luu + ((size_t)inst * N + t) * NU * NU, qoff);
 }
 
 // ---- line search: one CTA per instance, one warp per alpha candidate, every candidate rolled out

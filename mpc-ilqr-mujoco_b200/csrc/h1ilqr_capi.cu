@@ -32,6 +32,8 @@ struct H1Ilqr {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   H1SolverOptions opt;
   DynModel* d_dyn = nullptr; CostModel* d_cost = nullptr; H1Weights* d_w = nullptr; H1SolverOptions* d_opt = nullptr;
+  DevWeights* d_dw = nullptr;   // d_w points at its first member; qoff (below) = off-diagonal parts of full Q / R / Qf or nullptr
+  double* d_qoff = nullptr; bool qoff_on = false;
   double *xbar = nullptr, *ubar = nullptr, *K = nullptr, *kff = nullptr, *A = nullptr, *Bm = nullptr;
   double *lx = nullptr, *lu = nullptr, *lxx = nullptr, *luu = nullptr, *xnew = nullptr, *unew = nullptr;
   double *x0 = nullptr, *u_init = nullptr, *u_apply = nullptr, *prev_xbar = nullptr, *prev_ubar = nullptr;
@@ -153,7 +155,9 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   CUH(cudaEventCreate(&h->ev[0])); CUH(cudaEventCreate(&h->ev[1]));
   CUH(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)); CUH(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   const size_t B = batch, N1 = N + 1;
-  CUH(dalloc(h, &h->d_dyn, 1)); CUH(dalloc(h, &h->d_cost, 1)); CUH(dalloc(h, &h->d_w, 1)); CUH(dalloc(h, &h->d_opt, 1));
+  CUH(dalloc(h, &h->d_dyn, 1)); CUH(dalloc(h, &h->d_cost, 1)); CUH(dalloc(h, &h->d_dw, 1)); CUH(dalloc(h, &h->d_opt, 1));
+  h->d_w = &h->d_dw->w;   // (zero-initialised: qoff == nullptr -> diagonal weights)
+  CUH(dalloc(h, &h->d_qoff, (size_t)QOFF_SIZE));
   CUH(cudaMemcpyAsync(h->d_dyn, &dm, sizeof(dm), cudaMemcpyHostToDevice, h->stream));
   CUH(cudaMemcpyAsync(h->d_cost, &cm, sizeof(cm), cudaMemcpyHostToDevice, h->stream));
   CUH(cudaMemcpyAsync(h->d_opt, &h->opt, sizeof(h->opt), cudaMemcpyHostToDevice, h->stream));
@@ -221,7 +225,8 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   CUH(cudaFuncSetAttribute(k_primal_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn4));
   CUH(cudaFuncSetAttribute(k_linearize_fd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_lin));
   CUH(cudaFuncSetAttribute(k_linearize_analytic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_lina));
-  CUH(cudaFuncSetAttribute(k_cost_quadratics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_cq));
+  CUH(cudaFuncSetAttribute(k_cost_quadratics<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_cq));
+  CUH(cudaFuncSetAttribute(k_cost_quadratics<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_cq));
   CUH(cudaFuncSetAttribute(k_line_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_ls));
   CUH(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_ric));
   CUH(cudaStreamSynchronize(h->stream));
@@ -248,6 +253,49 @@ int h1ilqr_set_weights(H1Ilqr* h, const H1Weights* w) {
   if (!w) return set_err(H1ILQR_EARG, "null weights");
   H2D(h->d_w, w, sizeof(*w));
   SYNC();
+  return 0;
+}
+
+// Full symmetric Q / R / Qf (RobotUtils::setCostWeights keeps whole matrices and iLQR multiplies them, ilqr.cpp:145-150,
+// 372-373, 441). The diagonals go to the H1Weights arrays, the off-diagonal parts to a device table that every cost kernel
+// adds when present. Column-major 51x51 / 19x19 / 51x51; NULL for all three = back to diagonal weights.
+int h1ilqr_set_weight_matrices(H1Ilqr* h, const double* Q, const double* R, const double* Qf) {
+  GUARD(h);
+  if (!Q && !R && !Qf) {
+    const double* none = nullptr;
+    H2D(&h->d_dw->qoff, &none, sizeof(none));
+    SYNC();
+    if (h->qoff_on) invalidate_graphs(h);
+    h->qoff_on = false;
+    return 0;
+  }
+  if (!Q || !R || !Qf) return set_err(H1ILQR_EARG, "h1ilqr_set_weight_matrices: give all three matrices or none");
+  auto symmetric = [](const double* M, int n) {
+    for (int j = 0; j < n; ++j) for (int i = 0; i < j; ++i) if (M[j * n + i] != M[i * n + j]) return false;
+    return true;
+  };
+  if (!symmetric(Q, NX) || !symmetric(R, NU) || !symmetric(Qf, NX))
+    return set_err(H1ILQR_EARG, "h1ilqr_set_weight_matrices: Q, R, Qf must be symmetric");
+  H1Weights w;
+  CU(cudaMemcpyAsync(&w, h->d_w, sizeof(w), cudaMemcpyDeviceToHost, h->stream));
+  SYNC();
+  std::vector<double> off(QOFF_SIZE);
+  for (int j = 0; j < NX; ++j) for (int i = 0; i < NX; ++i) {
+    off[j * NX + i] = (i == j) ? 0.0 : Q[j * NX + i];
+    off[QOFF_QF + j * NX + i] = (i == j) ? 0.0 : Qf[j * NX + i];
+  }
+  for (int j = 0; j < NU; ++j) for (int i = 0; i < NU; ++i) off[QOFF_R + j * NU + i] = (i == j) ? 0.0 : R[j * NU + i];
+  for (int i = 0; i < NX; ++i) { w.Qdiag[i] = Q[i * NX + i]; w.Qfdiag[i] = Qf[i * NX + i]; }
+  for (int i = 0; i < NU; ++i) w.Rdiag[i] = R[i * NU + i];
+  bool any = false;
+  for (double v : off) any |= (v != 0.0);
+  H2D(h->d_w, &w, sizeof(w));
+  H2D(h->d_qoff, off.data(), off.size() * sizeof(double));
+  const double* ptr = any ? h->d_qoff : nullptr;
+  H2D(&h->d_dw->qoff, &ptr, sizeof(ptr));
+  SYNC();
+  if (h->qoff_on != any) invalidate_graphs(h);   // the table pointer is a kernel argument of the cost-quadratics launch
+  h->qoff_on = any;
   return 0;
 }
 
@@ -361,9 +409,12 @@ static void launch_linearize(H1Ilqr* h, const int* mask, bool factors_ready = fa
 static void launch_cost_quadratics(H1Ilqr* h, const int* mask) {
   const long warps = (long)h->B * (h->N + 1);   // knots (two warps each)
   const int blocks = (int)((warps + CQ_KNOTS - 1) / CQ_KNOTS);
-  k_cost_quadratics<<<blocks, CQ_WARPS * 32, h->smem_cq, h->stream>>>(h->d_cost, h->d_dyn, h->d_w, ref_table(h), h->B,
-                                                                     h->N, mask, h->xbar, h->ubar, h->lx, h->lu, h->lxx,
-                                                                     h->luu);
+  if (h->qoff_on)
+    k_cost_quadratics<true><<<blocks, CQ_WARPS * 32, h->smem_cq, h->stream>>>(h->d_cost, h->d_dyn, h->d_w, ref_table(h), h->B, h->N, mask, h->xbar,
+                                                                             h->ubar, h->lx, h->lu, h->lxx, h->luu, h->d_qoff);
+  else
+    k_cost_quadratics<false><<<blocks, CQ_WARPS * 32, h->smem_cq, h->stream>>>(h->d_cost, h->d_dyn, h->d_w, ref_table(h), h->B, h->N, mask, h->xbar,
+                                                                              h->ubar, h->lx, h->lu, h->lxx, h->luu, nullptr);
   LAUNCHED();
 }
 static void launch_backward(H1Ilqr* h, const int* mask) {

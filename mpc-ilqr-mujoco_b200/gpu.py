@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("H1ILQR_LIB") or os.path.join(_HERE, "lib", "libh1ilqr
 
 EXPORTS = [
     "h1ilqr_default_options", "h1ilqr_create", "h1ilqr_destroy", "h1ilqr_last_error", "h1ilqr_batch",
-    "h1ilqr_horizon", "h1ilqr_set_weights", "h1ilqr_set_reference_window", "h1ilqr_initialize", "h1ilqr_solve",
+    "h1ilqr_horizon", "h1ilqr_set_weights", "h1ilqr_set_weight_matrices", "h1ilqr_set_reference_window", "h1ilqr_initialize", "h1ilqr_solve",
     "h1ilqr_mpc_step", "h1ilqr_mpc_reset", "h1ilqr_rollout_nominal", "h1ilqr_linearize", "h1ilqr_cost_quadratics",
     "h1ilqr_backward_pass", "h1ilqr_line_search", "h1ilqr_total_cost", "h1ilqr_dynamics_step", "h1ilqr_bias_forces",
     "h1ilqr_reference_kinematics", "h1ilqr_reference_com_velocity", "h1ilqr_reference_ee_velocity", "h1ilqr_linearize_state",
@@ -107,6 +107,12 @@ class H1IlqrBatch:
     # ---- configuration ----
     def set_weights(self, w: H1Weights):
         _check(lib().h1ilqr_set_weights(self._h, C.byref(w)))
+
+    def set_weight_matrices(self, Q=None, R=None, Qf=None):
+        """Full symmetric Q [51,51], R [19,19], Qf [51,51] (ilqr.cpp:145-150); all None = diagonal weights again."""
+        cm = lambda M, n: np.ascontiguousarray(np.asarray(M, dtype=np.float64).reshape(n, n).T) if M is not None else None
+        q, r, f = cm(Q, NX), cm(R, NU), cm(Qf, NX)     # column-major copies, alive across the call
+        _check(lib().h1ilqr_set_weight_matrices(self._h, dptr(q), dptr(r), dptr(f)))
 
     def set_reference_window(self, x_ref, u_ref, com_ref, ee_ref, stance, com_vel_ref=None, shared=True):
         n = 1 if shared else self.B

@@ -86,7 +86,8 @@ class RobotUtils {
   const H1Model& dynamics_model() const { return dyn_model_; }
   int model_version() const { return model_version_; }            // bumped by setTimeStep / setGravity / scaleRobotMass
   H1Weights weights() const;                                      // current Q/R/Qf diagonals + task weights
-  bool weights_are_diagonal() const { return diag_ok_; }
+  bool weights_are_diagonal() const { return diag_ok_; }          // (kept name) true when Q, R, Qf are symmetric
+  bool push_weights(H1Ilqr* h) const;                             // set_weights (+ set_weight_matrices for full Q / R / Qf)
   int reference_rows() const { return static_cast<int>(x_ref_full_.size()); }
   const std::vector<std::vector<int>>& contact_schedule() const { return contact_schedule_; }
   void refresh_bias();                                            // data_.qfrc_bias <- GPU
@@ -104,7 +105,7 @@ class RobotUtils {
   mjData data_;
   std::vector<double> qpos_, qvel_, ctrl_, qfrc_bias_;
   Eigen::MatrixXd Q_, R_, Qf_;
-  bool diag_ok_;
+  bool diag_ok_, full_weights_;
   double w_com_, w_com_vel_, w_ee_pos_, w_ee_vel_, w_joint_limits_, w_control_limits_, w_upright_, w_balance_;
   std::vector<Eigen::VectorXd> x_ref_full_, u_ref_full_;
   std::vector<Eigen::Vector3d> com_ref_full_, com_vel_ref_full_;

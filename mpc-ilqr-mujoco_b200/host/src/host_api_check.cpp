@@ -43,6 +43,13 @@ int main(int argc, char** argv) {
   for (int i = 0; i < nu; ++i) hu[i] = Huu(i, i);
   const double cc = robot.constraintCost(x, u), sc = robot.stageCost(T, x, u), sc_far = robot.stageCost(100000, x, u), tc = robot.terminalCost(x);
   Eigen::Vector3d ev0 = robot.getEEVelReference(T, 0), ev1 = robot.getEEVelReference(T, 1), cv = robot.getCoMVelReference(T);
+  // whole symmetric Q / R / Qf (off-diagonal entries) through setCostWeights
+  Eigen::MatrixXd Qs = config.Q, Rs = config.R, Qfs = config.Qf;
+  Qs(0, 1) = Qs(1, 0) = 7.0; Qs(30, 8) = Qs(8, 30) = -3.0; Rs(2, 5) = Rs(5, 2) = 0.0004; Qfs(10, 40) = Qfs(40, 10) = 11.0;
+  robot.setCostWeights(Qs, Rs, Qfs);
+  const double sc_full = robot.stageCost(T, x, u), tc_full = robot.terminalCost(x);
+  robot.setCostWeights(config.Q, config.R, config.Qf);
+  const double sc_back = robot.stageCost(T, x, u);
   Eigen::VectorXd xn(nx), xn_heavy(nx);
   robot.rolloutOneStep(x, u, xn);
   robot.scaleRobotMass(1.5);
@@ -53,7 +60,8 @@ int main(int argc, char** argv) {
   arr("grad_x", gx.data(), nx); arr("grad_u", gu.data(), nu); arr("hess_xx_diag", hx.data(), nx); arr("hess_uu_diag", hu.data(), nu);
   arr("ee_vel_0", ev0.data(), 3); arr("ee_vel_1", ev1.data(), 3); arr("com_vel", cv.data(), 3);
   arr("x_next", xn.data(), nx); arr("x_next_heavy", xn_heavy.data(), nx);
-  std::cout << "\"constraint_cost\": " << cc << ", \"stage_cost\": " << sc << ", \"stage_cost_far\": " << sc_far << ", \"terminal_cost\": " << tc
+  std::cout << "\"constraint_cost\": " << cc << ", \"stage_cost\": " << sc << ", \"stage_cost_far\": " << sc_far << ", \"terminal_cost\": " << tc << ", \"stage_cost_fullq\": " << sc_full << ", \"terminal_cost_fullq\": " << tc_full
+            << ", \"stage_cost_back\": " << sc_back
             << ", \"joint_id_torso\": " << robot.jointId("torso_joint") << ", \"joint_id_left_knee\": " << robot.jointId("left_knee_joint")
             << ", \"joint_id_unknown\": " << robot.jointId("nope") << ", \"t\": " << T << "}" << std::endl;
   return 0;

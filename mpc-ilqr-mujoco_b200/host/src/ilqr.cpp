@@ -66,8 +66,7 @@ bool iLQR::upload_window(const std::vector<Eigen::VectorXd>& x_ref, const std::v
     if (robot_.getCoMVelWeight() > 0.0) { Eigen::Vector3d v = robot_.getCoMVelReference(t); for (int i = 0; i < 3; ++i) cv[t * 3 + i] = v(i); }
     if (t < N_) for (int i = 0; i < nu; ++i) ur[t * nu + i] = u_ref[t](i);
   }
-  H1Weights w = robot_.weights();
-  if (h1ilqr_set_weights(h_, &w) != H1ILQR_OK) return false;
+  if (!robot_.push_weights(h_)) return false;
   return h1ilqr_set_reference_window(h_, xr.data(), ur.data(), cr.data(), er.data(), st.data(), cv.data(), 1) == H1ILQR_OK;
 }
 
@@ -116,7 +115,7 @@ bool iLQR::solve(const Eigen::VectorXd& x0, const std::vector<Eigen::VectorXd>& 
     return false;
   }
   sync_model();
-  if (!robot_.weights_are_diagonal()) throw std::runtime_error("non-diagonal Q/R/Qf are not supported by the GPU solver core");
+  if (!robot_.weights_are_diagonal()) throw std::runtime_error("Q, R and Qf must be symmetric");
   if (!upload_window(x_ref, u_ref, com_ref)) throw std::runtime_error(std::string("iLQR upload: ") + h1ilqr_last_error());
   int status = 0, iters = 0;
   int rc = h1ilqr_solve(h_, x0.data(), &cost_out, &iters, &status);

@@ -9,7 +9,7 @@
 #include <stdexcept>
 
 RobotUtils::RobotUtils()
-    : loaded_(false), model_version_(0), nx_(0), nu_(0), dt_(0.01), query_(nullptr), diag_ok_(true), w_com_(0.0), w_com_vel_(0.0),
+    : loaded_(false), model_version_(0), nx_(0), nu_(0), dt_(0.01), query_(nullptr), diag_ok_(true), full_weights_(false), w_com_(0.0), w_com_vel_(0.0),
       w_ee_pos_(0.0), w_ee_vel_(0.0), w_joint_limits_(500.0), w_control_limits_(1000.0), w_upright_(0.0), w_balance_(0.0) {
   std::memset(&model_, 0, sizeof(model_));
   std::memset(&data_, 0, sizeof(data_));
@@ -24,8 +24,7 @@ void RobotUtils::model_changed() {   // the dynamics model is baked into device 
 
 bool RobotUtils::ensure_query() const {
   if (query_) {   // the limit penalties / stage costs read the handle's weights: keep them current
-    H1Weights w = weights();
-    h1ilqr_set_weights(query_, &w);
+    push_weights(query_);
     return true;
   }
   H1SolverOptions o;
@@ -35,9 +34,16 @@ bool RobotUtils::ensure_query() const {
     query_ = nullptr;
     return false;
   }
-  H1Weights w = weights();
-  h1ilqr_set_weights(query_, &w);
+  push_weights(query_);
   return true;
+}
+
+// current weights -> a device handle: diagonals + task weights, and the off-diagonal parts when Q / R / Qf are full
+bool RobotUtils::push_weights(H1Ilqr* h) const {
+  H1Weights w = weights();
+  if (h1ilqr_set_weights(h, &w) != H1ILQR_OK) return false;
+  if (full_weights_) return h1ilqr_set_weight_matrices(h, Q_.data(), R_.data(), Qf_.data()) == H1ILQR_OK;
+  return h1ilqr_set_weight_matrices(h, nullptr, nullptr, nullptr) == H1ILQR_OK;
 }
 
 bool RobotUtils::loadModel(const std::string& xml_path) {
@@ -162,12 +168,13 @@ void RobotUtils::setCostWeights(const Eigen::MatrixXd& Q, const Eigen::MatrixXd&
   if (R.rows() != nu_ || R.cols() != nu_) { std::cerr << "ERROR: R matrix dimension mismatch! Expected " << nu_ << "x" << nu_ << ", got " << R.rows() << "x" << R.cols() << std::endl; return; }
   if (Qf.rows() != nx_ || Qf.cols() != nx_) { std::cerr << "ERROR: Qf matrix dimension mismatch! Expected " << nx_ << "x" << nx_ << ", got " << Qf.rows() << "x" << Qf.cols() << std::endl; return; }
   Q_ = Q; R_ = R; Qf_ = Qf;
-  diag_ok_ = true;
+  // whole symmetric matrices are supported (the off-diagonal parts travel through h1ilqr_set_weight_matrices); an
+  // asymmetric one has no consistent quadratic model and is refused when the solver uploads it
   auto offdiag = [](const Eigen::MatrixXd& M) { for (long j = 0; j < M.cols(); ++j) for (long i = 0; i < M.rows(); ++i) if (i != j && M(i, j) != 0.0) return true; return false; };
-  if (offdiag(Q) || offdiag(R) || offdiag(Qf)) {
-    diag_ok_ = false;
-    std::cerr << "ERROR: the GPU solver core supports diagonal Q/R/Qf only (as Config::buildCostMatrices builds them)" << std::endl;
-  }
+  auto symmetric = [](const Eigen::MatrixXd& M) { for (long j = 0; j < M.cols(); ++j) for (long i = 0; i < j; ++i) if (M(i, j) != M(j, i)) return false; return true; };
+  full_weights_ = offdiag(Q) || offdiag(R) || offdiag(Qf);
+  diag_ok_ = symmetric(Q) && symmetric(R) && symmetric(Qf);
+  if (!diag_ok_) std::cerr << "ERROR: Q, R and Qf must be symmetric" << std::endl;
   std::cout << "Cost weights set successfully" << std::endl;
 }
 void RobotUtils::setConstraintWeights(double wj, double wc) {

@@ -45,6 +45,9 @@ struct Problem {
   std::vector<double> x_ref, u_ref, com_ref, ee_ref, com_vel_ref;  // [(N+1)*51], [N*19], [(N+1)*3], [(N+1)*6], [(N+1)*3]
   std::vector<int> stance;                                        // [(N+1)*2]
   bool use_ad = false;  // cost derivatives through the AD path instead of the analytic path
+  // full symmetric Q, R, Qf (column-major; empty = the diagonal matrices of `w`): iLQR multiplies whole matrices
+  // (/root/reference/src/ilqr/ilqr.cpp:145-150, 372-373, 441)
+  std::vector<double> Qfull, Rfull, Qffull;
 };
 
 struct Solver {

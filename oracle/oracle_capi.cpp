@@ -71,6 +71,13 @@ void* orc_create(const H1Model* dyn, const H1Model* cost, const H1Weights* w, co
   for (auto& s : h->solvers) s.init(&h->prob);
   return h;
 }
+// whole cost matrices (column-major); NULL = back to the diagonals of the weights struct
+void orc_set_weight_matrices(void* hv, const double* Q, const double* R, const double* Qf) {
+  Problem& p = static_cast<Handle*>(hv)->prob;
+  p.Qfull.clear(); p.Rfull.clear(); p.Qffull.clear();
+  if (!Q || !R || !Qf) return;
+  p.Qfull.assign(Q, Q + H1_NX * H1_NX); p.Rfull.assign(R, R + H1_NU * H1_NU); p.Qffull.assign(Qf, Qf + H1_NX * H1_NX);
+}
 void orc_destroy(void* hv) { delete static_cast<Handle*>(hv); }
 void orc_use_ad(void* hv, int use) { static_cast<Handle*>(hv)->prob.use_ad = use != 0; }
 

@@ -88,8 +88,21 @@ void cost_quadratics(Solver& s) {
     double* lx = &s.lx[t * NX]; double* lu = &s.lu[t * NU];
     double* lxx = &s.lxx[t * NX * NX]; double* luu = &s.luu[t * NU * NU];
     std::fill(lxx, lxx + NX * NX, 0.0); std::fill(luu, luu + NU * NU, 0.0);
-    for (int i = 0; i < NX; ++i) { lx[i] = p.w.Qdiag[i] * (x[i] - p.x_ref[t * NX + i]); lxx[i * NX + i] = p.w.Qdiag[i]; }
-    for (int i = 0; i < NU; ++i) { lu[i] = p.w.Rdiag[i] * (u[i] - p.u_ref[t * NU + i]); luu[i * NU + i] = p.w.Rdiag[i]; }
+    if (p.Qfull.empty()) {
+      for (int i = 0; i < NX; ++i) { lx[i] = p.w.Qdiag[i] * (x[i] - p.x_ref[t * NX + i]); lxx[i * NX + i] = p.w.Qdiag[i]; }
+      for (int i = 0; i < NU; ++i) { lu[i] = p.w.Rdiag[i] * (u[i] - p.u_ref[t * NU + i]); luu[i * NU + i] = p.w.Rdiag[i]; }
+    } else {   // lx = Q (x - x_ref), lxx = Q, lu = R (u - u_ref), luu = R with whole matrices (ilqr.cpp:145-150)
+      for (int i = 0; i < NX; ++i) {
+        double a = 0;
+        for (int j = 0; j < NX; ++j) { a += p.Qfull[j * NX + i] * (x[j] - p.x_ref[t * NX + j]); lxx[j * NX + i] = p.Qfull[j * NX + i]; }
+        lx[i] = a;
+      }
+      for (int i = 0; i < NU; ++i) {
+        double a = 0;
+        for (int j = 0; j < NU; ++j) { a += p.Rfull[j * NU + i] * (u[j] - p.u_ref[t * NU + j]); luu[j * NU + i] = p.Rfull[j * NU + i]; }
+        lu[i] = a;
+      }
+    }
     kinematic_terms(p, t, false, x, lx, lxx);
     limit_derivs(p.dyn, p.w, x, u, gx, gu, hx, hu);
     for (int i = 0; i < NX; ++i) { lx[i] += gx[i]; lxx[i * NX + i] += hx[i]; }
@@ -98,7 +111,15 @@ void cost_quadratics(Solver& s) {
   const double* x = &s.xbar[N * NX];
   double* lx = &s.lx[N * NX]; double* lxx = &s.lxx[N * NX * NX];
   std::fill(lxx, lxx + NX * NX, 0.0);
-  for (int i = 0; i < NX; ++i) { lx[i] = p.w.Qfdiag[i] * (x[i] - p.x_ref[N * NX + i]); lxx[i * NX + i] = p.w.Qfdiag[i]; }
+  if (p.Qffull.empty()) {
+    for (int i = 0; i < NX; ++i) { lx[i] = p.w.Qfdiag[i] * (x[i] - p.x_ref[N * NX + i]); lxx[i * NX + i] = p.w.Qfdiag[i]; }
+  } else {
+    for (int i = 0; i < NX; ++i) {
+      double a = 0;
+      for (int j = 0; j < NX; ++j) { a += p.Qffull[j * NX + i] * (x[j] - p.x_ref[N * NX + j]); lxx[j * NX + i] = p.Qffull[j * NX + i]; }
+      lx[i] = a;
+    }
+  }
   kinematic_terms(p, N, true, x, lx, lxx);
   double uz[NU] = {0};
   limit_derivs(p.dyn, p.w, x, uz, gx, gu, hx, hu);
@@ -252,14 +273,26 @@ double total_cost(const Solver& s, const double* xt, const double* ut) {
   for (int t = 0; t < N; ++t) {
     const double* x = xt + t * NX; const double* u = ut + t * NU;
     double qx = 0, qu = 0;
-    for (int i = 0; i < NX; ++i) { double e = x[i] - p.x_ref[t * NX + i]; qx += e * p.w.Qdiag[i] * e; }
-    for (int i = 0; i < NU; ++i) { double e = u[i] - p.u_ref[t * NU + i]; qu += e * p.w.Rdiag[i] * e; }
+    if (p.Qfull.empty()) {
+      for (int i = 0; i < NX; ++i) { double e = x[i] - p.x_ref[t * NX + i]; qx += e * p.w.Qdiag[i] * e; }
+      for (int i = 0; i < NU; ++i) { double e = u[i] - p.u_ref[t * NU + i]; qu += e * p.w.Rdiag[i] * e; }
+    } else {
+      for (int i = 0; i < NX; ++i) for (int j = 0; j < NX; ++j)
+        qx += (x[i] - p.x_ref[t * NX + i]) * p.Qfull[j * NX + i] * (x[j] - p.x_ref[t * NX + j]);
+      for (int i = 0; i < NU; ++i) for (int j = 0; j < NU; ++j)
+        qu += (u[i] - p.u_ref[t * NU + i]) * p.Rfull[j * NU + i] * (u[j] - p.u_ref[t * NU + j]);
+    }
     total += 0.5 * qx; total += 0.5 * qu;
     upright_balance(t, x);
   }
   const double* xN = xt + N * NX;
   double qf = 0;
-  for (int i = 0; i < NX; ++i) { double e = xN[i] - p.x_ref[N * NX + i]; qf += e * p.w.Qfdiag[i] * e; }
+  if (p.Qffull.empty()) {
+    for (int i = 0; i < NX; ++i) { double e = xN[i] - p.x_ref[N * NX + i]; qf += e * p.w.Qfdiag[i] * e; }
+  } else {
+    for (int i = 0; i < NX; ++i) for (int j = 0; j < NX; ++j)
+      qf += (xN[i] - p.x_ref[N * NX + i]) * p.Qffull[j * NX + i] * (xN[j] - p.x_ref[N * NX + j]);
+  }
   total += 0.5 * qf;
   upright_balance(N, xN);
   for (int t = 0; t < N; ++t) total += limit_cost(p.dyn, p.w, xt + t * NX, ut + t * NU);

@@ -149,6 +149,15 @@ class OracleSolver:
             lib().orc_destroy(self.h)
             self.h = None
 
+    def set_weight_matrices(self, Q=None, R=None, Qf=None):
+        """Whole cost matrices Q [51,51], R [19,19], Qf [51,51] (ilqr.cpp:145-150); all None = diagonal weights."""
+        if Q is None:
+            lib().orc_set_weight_matrices(self.h, None, None, None)
+            return
+        cm = lambda M, n: np.ascontiguousarray(np.asarray(M, dtype=np.float64).reshape(n, n).T)
+        q, r, f = cm(Q, NX), cm(R, NU), cm(Qf, NX)
+        lib().orc_set_weight_matrices(self.h, dptr(q), dptr(r), dptr(f))
+
     def use_ad(self, flag):
         lib().orc_use_ad(self.h, C.c_int(int(flag)))
 

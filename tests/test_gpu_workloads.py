@@ -352,3 +352,55 @@ def test_warm_start_baseline(gpu, oracle):
             assert (at[i] == at_o).all(), (policy, i, at[i][:3].tolist(), pre, post)
             assert it[i] == 3 and abs(c1[i] - co) <= 1e-9 * abs(co)
         assert higher >= 1, "no instance exercises the case pre-rollout cost > post-rollout cost"
+
+
+def test_full_weight_matrices(gpu, oracle):
+    """Whole symmetric Q / R / Qf (RobotUtils::setCostWeights keeps matrices and iLQR multiplies them: lx = Q (x - x_ref),
+    lxx = Q, lu = R (u - u_ref), luu = R, 0.5 e'Qe in the line-search cost; ilqr.cpp:145-150, 372-373, 441): cost quadratics,
+    total cost, line search and a full solve against the oracle on both kernel families; asymmetric matrices are refused;
+    NULL restores the diagonal weights."""
+    w = Config().build_weights()
+    rng = np.random.default_rng(5)
+
+    def spd(diag, scale):
+        n = len(diag)
+        M = rng.normal(size=(n, n)) * scale
+        M = 0.5 * (M + M.T)
+        np.fill_diagonal(M, 0.0)
+        return M + np.diag(np.asarray(diag) + np.abs(M).sum(axis=1))      # diagonally dominant -> positive definite
+    Q, R, Qf = spd(np.array(w.Qdiag), 1.5), spd(np.array(w.Rdiag), 2e-4), spd(np.array(w.Qfdiag), 3.0)
+    so, _, win = make_oracle("walking")
+    so.set_weight_matrices(Q, R, Qf)
+    sg = gpu.H1IlqrBatch(w, N=25, batch=2)
+    sg.set_reference_window(*win, shared=True)
+    with pytest.raises(gpu.H1IlqrError):
+        sg.set_weight_matrices(Q + np.triu(np.ones((51, 51)), 1), R, Qf)
+    sg.set_weight_matrices(Q, R, Qf)
+    xb = win[0] + rng.normal(size=win[0].shape) * 0.05
+    ub = rng.uniform(-60, 60, (25, 19))
+    so.set("xbar", xb); so.set("ubar", ub); so.cost_quadratics()
+    two = lambda a: np.stack([a, a])
+    sg.set_trajectory(xbar=two(xb), ubar=two(ub)); sg.cost_quadratics()
+    lx, lu, lxx, luu = sg.get_cost_quadratics()
+    for t in range(26):
+        assert rel_err(lx[0, t], so.get("lx")[t]) < 1e-9 and rel_err(lxx[0, t], so.get("lxx")[t]) < 1e-9, t
+    assert rel_err(lu[0], so.get("lu")) < 1e-9 and rel_err(luu[0], so.get("luu")) < 1e-9
+    assert np.abs(luu[0, 3] - luu[0, 3].T).max() == 0.0 and np.abs(luu[0, 3, 0, 1]) > 0
+    x0 = win[0][0].copy(); ug = grav_comp_guess(standing_state())
+    for policy in (1, 2):
+        sg.set_kernel_policy(policy)
+        sg.set_trajectory(xbar=two(xb), ubar=two(ub))
+        so.set("xbar", xb); so.set("ubar", ub)
+        assert abs(sg.total_cost()[0] - so.total_cost()) <= 1e-12 * abs(so.total_cost()), policy
+        so.mpc_reset(); so.initialize(x0, False, ug); so.solve(x0)
+        sg.mpc_reset(); sg.initialize(two(x0), None, ug)
+        cg, it, st = sg.solve(two(x0))
+        ct, at = sg.solve_trace(); xg, ugp = sg.get_trajectory()
+        print("full Q/R/Qf solve, policy", policy, compare_solve(so, cg[0], it[0], ct[0], at[0], xg[0], ugp[0], label="full weights"))
+        assert cg[0] == cg[1]
+    # the off-diagonal parts matter, and NULL brings the diagonal weights back
+    s0, _, _ = make_oracle("walking"); s0.set("xbar", xb); s0.set("ubar", ub)
+    assert abs(s0.total_cost() - so.total_cost()) > 1e-3 * abs(so.total_cost())
+    sg.set_weight_matrices(None, None, None); sg.set_weights(w)
+    sg.set_trajectory(xbar=two(xb), ubar=two(ub))
+    assert abs(sg.total_cost()[0] - s0.total_cost()) <= 1e-12 * abs(s0.total_cost())

@@ -165,6 +165,14 @@ def test_robot_utils_remaining_public_surface(tmp_path, oracle):
     e = x - refs.x_ref_full[-1]
     term = 0.5 * e @ (Qf * e) + 0.5 * w.w_com * np.sum((com - refs.com_ref_full[-1]) ** 2) + sum(p[0] for p in pq)
     assert abs(r["terminal_cost"] - term) <= 1e-11 * term
+    # whole symmetric matrices through setCostWeights (off-diagonal entries set in host_api_check.cpp), and back to diagonal
+    eu = u
+    extra = e0 = x - refs.x_ref_full[T]
+    full_stage = stage(T) + (7.0 * e0[0] * e0[1] + -3.0 * e0[30] * e0[8]) + 0.0004 * eu[2] * eu[5]
+    assert abs(r["stage_cost_fullq"] - full_stage) <= 1e-11 * abs(full_stage)
+    full_term = term + 11.0 * e[10] * e[40]
+    assert abs(r["terminal_cost_fullq"] - full_term) <= 1e-11 * abs(full_term)
+    assert r["stage_cost_back"] == r["stage_cost"]
     # per-row velocity targets (robot_utils.cpp:388-412)
     xr = refs.x_ref_full[T]
     assert np.abs(np.array(r["com_vel"]) - oracle.dyn_com_vel(xr)).max() < 1e-12
