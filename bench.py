@@ -187,6 +187,11 @@ def host_single_instance(tag, steps):
     d = np.load(os.path.join(ROOT, "data", "h1_refs.npz"))
     with tempfile.TemporaryDirectory() as td:
         os.makedirs(os.path.join(td, "data")); os.makedirs(os.path.join(td, "results"))
+        md = np.load(os.path.join(ROOT, "data", "h1_models.npz"))     # the model files RobotUtils::loadModel / iLQR parse at run time
+        for key, rel in (("mjcf_scene_xml", "robots/h1_description/mjcf/scene.xml"), ("mjcf_h1_xml", "robots/h1_description/mjcf/h1.xml"),
+                         ("urdf_h1_urdf", "robots/h1_description/urdf/h1.urdf")):
+            os.makedirs(os.path.dirname(os.path.join(td, rel)), exist_ok=True)
+            open(os.path.join(td, rel), "wb").write(md[key].tobytes())
         np.savetxt(os.path.join(td, "data", "q.csv"), d[f"{tag}_q"], delimiter=",", fmt="%.17g")
         np.savetxt(os.path.join(td, "data", "v.csv"), d[f"{tag}_v"], delimiter=",", fmt="%.17g")
         with open(os.path.join(td, "data", "c.csv"), "w") as f:

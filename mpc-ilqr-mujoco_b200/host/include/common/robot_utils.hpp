@@ -84,7 +84,10 @@ class RobotUtils {
   // ---- used by the iLQR / MPC shims (not part of the reference API) ----
   H1Ilqr* query_handle() const { return query_; }                 // batch-1 handle for plant / FK queries
   const H1Model& dynamics_model() const { return dyn_model_; }
-  int model_version() const { return model_version_; }            // bumped by setTimeStep / setGravity / scaleRobotMass
+  int model_version() const { return model_version_; }
+  bool model_from_file() const { return model_from_file_; }       // loadModel parsed the MJCF (otherwise: built-in tables)
+  const std::vector<std::string>& joint_names() const { return joint_names_; }
+  const std::vector<std::string>& body_names() const { return body_names_; }            // bumped by setTimeStep / setGravity / scaleRobotMass
   H1Weights weights() const;                                      // current Q/R/Qf diagonals + task weights
   bool weights_are_diagonal() const { return diag_ok_; }          // (kept name) true when Q, R, Qf are symmetric
   bool push_weights(H1Ilqr* h) const;                             // set_weights (+ set_weight_matrices for full Q / R / Qf)
@@ -97,6 +100,8 @@ class RobotUtils {
   void model_changed();
   bool loaded_;
   int model_version_;
+  bool model_from_file_ = false;
+  std::vector<std::string> joint_names_, body_names_;
   int nx_, nu_;
   double dt_;
   H1Model dyn_model_;

@@ -42,6 +42,8 @@ class iLQR {
   H1SolverOptions opt_;
   H1Ilqr* h_;
   int model_version_ = -1;
+  H1Model cost_model_;
+  bool cost_from_file_ = false;
   std::vector<Eigen::VectorXd> xbar_, ubar_, kff_;
   std::vector<Eigen::MatrixXd> K_;
 };

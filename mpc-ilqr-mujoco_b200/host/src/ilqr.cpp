@@ -1,11 +1,22 @@
 // iLQR shim over the C ABI (reference: src/ilqr/ilqr.cpp). All numerical stages run on the GPU.
 #include "ilqr/ilqr.hpp"
+#include "common/model_loader.hpp"
 #include <iostream>
 #include <stdexcept>
 
 iLQR::iLQR(RobotUtils& robot, int N, double dt, const std::string& urdf_path)
     : robot_(robot), N_(N), dt_(dt), h_(nullptr) {
-  (void)urdf_path;  // the cost (URDF) model tables are compiled in; see tools/gen_h1_model.py
+  // The cost model is read from the URDF at run time (reference: symDerivatives builds its Pinocchio model from urdf_path,
+  // derivatives.cpp:26-39), keyed by the joint names of the MJCF the robot parsed; otherwise the built-in tables are used.
+  std::string err;
+  if (robot_.model_from_file() &&
+      load_urdf_model(urdf_path, *h1_default_cost_model(), robot_.joint_names(), robot_.body_names(), &cost_model_, &err)) {
+    cost_from_file_ = true;
+    std::cout << "Parsed URDF cost model: " << urdf_path << std::endl;
+  } else {
+    cost_from_file_ = false;
+    if (robot_.model_from_file()) std::cerr << "Note: " << urdf_path << " not usable (" << err << "); using the built-in H1 cost model" << std::endl;
+  }
   h1ilqr_default_options(&opt_);
   const int nx = robot_.nx(), nu = robot_.nu();
   xbar_.assign(N_ + 1, Eigen::VectorXd::Zero(nx));
@@ -24,7 +35,7 @@ bool iLQR::recreate() {
   if (h_) h1ilqr_get_regularization(h_, &lambda);
   H1Model dm = robot_.dynamics_model();
   H1Ilqr* fresh = nullptr;
-  if (h1ilqr_create(&dm, nullptr, &opt_, 1, N_, 0, &fresh) != H1ILQR_OK) return false;
+  if (h1ilqr_create(&dm, cost_from_file_ ? &cost_model_ : nullptr, &opt_, 1, N_, 0, &fresh) != H1ILQR_OK) return false;
   if (h1ilqr_set_regularization(fresh, &lambda, 1) != H1ILQR_OK) { h1ilqr_destroy(fresh); return false; }
   if (h_) h1ilqr_destroy(h_);
   h_ = fresh;

@@ -1,6 +1,7 @@
 // RobotUtils on top of the C ABI (reference: src/common/robot_utils.cpp). The plant is the GPU dynamics map f_D;
 // references and the contact schedule are parsed with the reference's rules (robot_utils.cpp:281-347, 445-492).
 #include "common/robot_utils.hpp"
+#include "common/model_loader.hpp"
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -47,10 +48,20 @@ bool RobotUtils::push_weights(H1Ilqr* h) const {
 }
 
 bool RobotUtils::loadModel(const std::string& xml_path) {
-  // The H1 tree is compiled in from the reference's MJCF (tools/gen_h1_model.py); the path is only checked.
-  std::ifstream f(xml_path);
-  if (!f.is_open()) std::cerr << "Note: " << xml_path << " not found; using the built-in H1 model tables" << std::endl;
-  dyn_model_ = *h1_default_dynamics_model();
+  // The MJCF is read at run time (reference: mj_loadXML, robot_utils.cpp:19-33); when the file is missing or is not an
+  // H1-class model the tables generated from the reference's h1.xml at build time (tools/gen_h1_model.py) are used.
+  std::string err;
+  H1Model parsed;
+  if (load_mjcf_model(xml_path, *h1_default_dynamics_model(), &parsed, &joint_names_, &body_names_, &err)) {
+    dyn_model_ = parsed;
+    model_from_file_ = true;
+    std::cout << "Parsed MJCF model: " << xml_path << std::endl;
+  } else {
+    std::cerr << "Note: " << xml_path << " not usable (" << err << "); using the built-in H1 model tables" << std::endl;
+    dyn_model_ = *h1_default_dynamics_model();
+    model_from_file_ = false;
+    joint_names_.clear(); body_names_.clear();
+  }
   nx_ = H1_NX; nu_ = H1_NU; dt_ = dyn_model_.timestep;
   loaded_ = true;
   qpos_.assign(H1_NQ, 0.0); qvel_.assign(H1_NV, 0.0); ctrl_.assign(H1_NU, 0.0); qfrc_bias_.assign(H1_NV + 1, 0.0);
@@ -298,6 +309,10 @@ int RobotUtils::jointId(const std::string& name) const {
       "torso_joint", "left_shoulder_pitch_joint", "left_shoulder_roll_joint", "left_shoulder_yaw_joint", "left_elbow_joint",
       "right_shoulder_pitch_joint", "right_shoulder_roll_joint", "right_shoulder_yaw_joint", "right_elbow_joint"};
   if (!loaded_) return -1;
+  if ((int)joint_names_.size() == H1_NU) {   // names of the MJCF that was parsed at run time
+    for (int i = 0; i < H1_NU; ++i) if (name == joint_names_[i]) return i + 1;
+    return -1;
+  }
   for (int i = 0; i < H1_NU; ++i) if (name == names[i]) return i + 1;
   return -1;
 }

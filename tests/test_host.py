@@ -168,3 +168,45 @@ def test_pinocchio_order_reference_loader(tmp_path):
     with open(p, "a") as f:
         f.write("1,2,3\n")                                   # malformed row: skipped
     assert np.abs(load_q_pin_csv(str(p)) - mj).max() < 1e-12
+
+
+def _unpack_models(tmp_path):
+    """The reference's scene.xml / h1.xml / h1.urdf from data/h1_models.npz laid out like robots/h1_description/."""
+    d = np.load(os.path.join(ROOT, "data", "h1_models.npz"))
+    mj = tmp_path / "robots" / "h1_description" / "mjcf"; ur = tmp_path / "robots" / "h1_description" / "urdf"
+    mj.mkdir(parents=True); ur.mkdir(parents=True)
+    (mj / "scene.xml").write_bytes(d["mjcf_scene_xml"].tobytes()); (mj / "h1.xml").write_bytes(d["mjcf_h1_xml"].tobytes())
+    (ur / "h1.urdf").write_bytes(d["urdf_h1_urdf"].tobytes())
+    return str(mj / "scene.xml"), str(ur / "h1.urdf")
+
+
+def test_runtime_model_loader_matches_generated_tables(tmp_path):
+    """RobotUtils::loadModel / iLQR parse the MJCF (through scene.xml's <include>) and the URDF at run time
+    (host/src/model_loader.cpp; reference: robot_utils.cpp:19-55, derivatives.cpp:26-39). The parsed H1Model tables equal
+    the ones tools/gen_h1_model.py generated from the same files at build time; a non-H1 file is rejected."""
+    import json
+    import subprocess
+    from mpc_ilqr_mujoco_b200 import gpu
+    exe = os.path.join(ROOT, "mpc-ilqr-mujoco_b200", "host", "bin", "model_load_check")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "mpc-ilqr-mujoco_b200", "host")], stdout=subprocess.DEVNULL)
+    scene, urdf = _unpack_models(tmp_path)
+    out = subprocess.run([exe, scene, urdf], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    r = json.loads(out.stdout)
+    assert r["joints"][0] == "left_hip_yaw_joint" and r["joints"][10] == "torso_joint" and len(r["joints"]) == 19
+    for key, ref in (("dynamics", gpu.default_dynamics_model()), ("cost", gpu.default_cost_model())):
+        m = r[key]
+        assert m["parent"] == list(ref.parent) and m["axis"] == list(ref.axis) and m["has_rfix"] == list(ref.has_rfix)
+        assert m["foot_body"] == list(ref.foot_body) == [5, 10]
+        for name, val in (("pos", ref.pos), ("rfix", ref.rfix), ("mass", ref.mass), ("ipos", ref.ipos), ("inertia", ref.inertia),
+                          ("armature", ref.armature), ("damping", ref.damping), ("jnt_range", ref.jnt_range),
+                          ("ctrl_range", ref.ctrl_range), ("foot_pts", ref.foot_pts), ("gravity", ref.gravity)):
+            a, b = np.array(m[name]), np.array(val).ravel()
+            assert np.abs(a - b).max() <= 1e-15 * max(np.abs(b).max(), 1.0), (key, name)
+        assert np.allclose(m["scalars"], [ref.timestep, ref.contact_kn, ref.contact_bn, ref.contact_bt, ref.contact_eps, ref.total_mass], rtol=1e-15)
+    # a file that is not an H1-class model
+    bad = tmp_path / "bad.xml"
+    bad.write_text('<mujoco><worldbody><body name="a"><inertial pos="0 0 0" mass="1" diaginertia="1 1 1"/><freejoint/></body></worldbody></mujoco>')
+    out = subprocess.run([exe, str(bad), urdf], capture_output=True, text=True)
+    assert out.returncode == 1 and "expected 20 bodies" in out.stderr

@@ -19,6 +19,8 @@ def _workdir(tmp_path, steps, tag="standing"):
     d = np.load(os.path.join(ROOT, "data", "h1_refs.npz"))
     (tmp_path / "data").mkdir()
     (tmp_path / "results").mkdir()
+    from test_host import _unpack_models
+    _unpack_models(tmp_path)     # robots/h1_description/{mjcf,urdf}: parsed at run time by RobotUtils::loadModel / iLQR
     np.savetxt(tmp_path / "data" / "q.csv", d[f"{tag}_q"], delimiter=",", fmt="%.17g")
     np.savetxt(tmp_path / "data" / "v.csv", d[f"{tag}_v"], delimiter=",", fmt="%.17g")
     with open(tmp_path / "data" / "c.csv", "w") as f:
@@ -51,6 +53,7 @@ def test_demo_binary_matches_oracle_closed_loop(tmp_path, oracle):
     _workdir(tmp_path, steps)
     out = subprocess.run([exe, "config.yaml", str(steps)], cwd=tmp_path, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
+    assert "Parsed MJCF model" in out.stdout and "Parsed URDF cost model" in out.stdout    # run-time model loading
     costs = [float(m) for m in re.findall(r"Cost: ([-+0-9.eE]+)", out.stdout)]
     ref = _oracle_costs(oracle, steps)
     assert len(costs) == steps

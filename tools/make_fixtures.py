@@ -25,3 +25,10 @@ import csv
 with open(f"{REF}/data/h1_walking_pin.csv") as f:
     out["walking_pin_q_head"] = np.array([[float(t) for t in row] for _, row in zip(range(64), csv.reader(f))])
 np.savez_compressed("data/h1_refs.npz", **out)
+# the reference's model files (robots/h1_description/mjcf/{scene,h1}.xml, urdf/h1.urdf) as byte arrays: inputs of the run-time
+# model loader test (host/src/model_loader.cpp) and of bench / demo runs that want RobotUtils::loadModel to parse real files
+models = {}
+for key, rel in (("mjcf_scene_xml", "robots/h1_description/mjcf/scene.xml"), ("mjcf_h1_xml", "robots/h1_description/mjcf/h1.xml"),
+                 ("urdf_h1_urdf", "robots/h1_description/urdf/h1.urdf")):
+    models[key] = np.frombuffer(open(f"{REF}/{rel}", "rb").read(), dtype=np.uint8)
+np.savez_compressed("data/h1_models.npz", **models)
