@@ -559,6 +559,7 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
           dmma884(acc[q][0], acc[q][1], own[q] ? a1 : a2, c < NX ? gv : 0.0);
         }
       }
+      __syncwarp();   // the (discarded) clamped / upper-triangle reads of the accumulator init touch elements other lanes of this warp write below
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
