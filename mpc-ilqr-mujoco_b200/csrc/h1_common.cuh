@@ -36,6 +36,11 @@ struct DevWeights {
   H1Weights w;
   const double* qoff;
 };
+// Per-knot strides of A_k, B_k, lxx_k in device memory: the dense column-major matrices (leading dimension NX) followed by ONE
+// pad double, so that every matrix starts on a 16-byte boundary and spans a multiple of 16 bytes — the Riccati kernel
+// fetches them with one bulk-copy instruction each (cp.async.bulk needs both). The pad is never written (zero).
+constexpr int A_STRIDE = NX * NX + 1, B_STRIDE = NX * NU + 1, LXX_STRIDE = NX * NX + 1;
+static_assert((A_STRIDE * 8) % 16 == 0 && (B_STRIDE * 8) % 16 == 0, "bulk copies need 16-byte multiples");
 constexpr int QOFF_R = NX * NX, QOFF_QF = NX * NX + NU * NU, QOFF_SIZE = 2 * NX * NX + NU * NU;
 H1_HD const double* weights_offdiag(const H1Weights& wt) {
 #if defined(__CUDACC__)

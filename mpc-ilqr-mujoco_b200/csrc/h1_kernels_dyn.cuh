@@ -232,8 +232,8 @@ k_linearize_fd(const DynModel* gmd, int N, double eps, const int* __restrict__ a
   for (int e = warp; e < LIN_EVALS; e += LIN_WARPS)
     dyn_step_warp(*md, ws[warp], xs, xs + NX, fx + e * NX, e - 1, eps);
   __syncthreads();
-  double* Ak = A + ((size_t)inst * N + t) * NX * NX;
-  double* Bk = Bm + ((size_t)inst * N + t) * NX * NU;
+  double* Ak = A + ((size_t)inst * N + t) * A_STRIDE;
+  double* Bk = Bm + ((size_t)inst * N + t) * B_STRIDE;
   const double inv = 1.0 / eps;
   (void)inv;
   for (int i = threadIdx.x; i < NX * (NX + NU); i += blockDim.x) {
@@ -287,8 +287,8 @@ k_linearize_analytic(const DynModel* gmd, int N, const int* __restrict__ active,
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5;
-  double* Ak = A + ((size_t)inst * N + t) * NX * NX;
-  double* Bk = Bm + ((size_t)inst * N + t) * NX * NU;
+  double* Ak = A + ((size_t)inst * N + t) * A_STRIDE;
+  double* Bk = Bm + ((size_t)inst * N + t) * B_STRIDE;
   for (int e = warp; e < NX + NU; e += LINA_WARPS)
     dyn_tangent_id_warp(*md, ws[warp], *pf, xs, xs + NX, e, e < NX ? Ak + e * NX : Bk + (e - NX) * NX);
 }
@@ -328,7 +328,7 @@ k_linearize_dirs(const DynModel* gmd, long nknots, int N, const int* __restrict_
   }
   if (H1TREE) tangent_solve_h1(&pf->Lm[0][0], pf->D, tv);
   else tangent_solve_seq(*md, &pf->Lm[0][0], pf->D, tv);
-  double* col = (MODE == 2) ? Bm + (size_t)knot * NX * NU + (size_t)dir * NX : A + (size_t)knot * NX * NX + (size_t)seed * NX;
+  double* col = (MODE == 2) ? Bm + (size_t)knot * B_STRIDE + (size_t)dir * NX : A + (size_t)knot * A_STRIDE + (size_t)seed * NX;
   integrate_tangent_seq(*md, x, pf->a, seed, tv, col);
 }
 

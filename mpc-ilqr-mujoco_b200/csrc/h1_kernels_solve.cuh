@@ -35,7 +35,7 @@ k_cost_quadratics(const CostModel* gcm, const DynModel* gmd, const H1Weights* gw
   kt.stance = r.stance + 2 * t; kt.terminal = terminal;
   cost_quadratics_warp<FULLQ>(*cm, *gmd, *gw, w, x, u, r.x_ref + t * NX, terminal ? nullptr : r.u_ref + t * NU, kt,
                        lx + ((size_t)inst * (N + 1) + t) * NX, terminal ? nullptr : lu + ((size_t)inst * N + t) * NU,
-                       lxx + ((size_t)inst * (N + 1) + t) * NX * NX,
+                       lxx + ((size_t)inst * (N + 1) + t) * LXX_STRIDE,
                        terminal ? nullptr : luu + ((size_t)inst * N + t) * NU * NU, qoff);
 }
 
@@ -284,7 +284,7 @@ __global__ void k_copy_x0(int B, int N, const double* __restrict__ xbar, double*
 __global__ void k_mirror_lower(long nmat, double* __restrict__ lxx) {
   const long m = blockIdx.x;
   if (m >= nmat) return;
-  double* M = lxx + m * NX * NX;
+  double* M = lxx + m * LXX_STRIDE;
   for (int i = threadIdx.x; i < NX * NX; i += blockDim.x) {
     const int c = i / NX, r = i - c * NX;
     if (r < c) M[i] = M[r * NX + c];

@@ -100,7 +100,7 @@ k_linearize_tangents(const DynModel* gmd, long nknots, int N, const int* __restr
     int col;                                          // column of A_k the tangent is parked in
     if (CLS == 2 && it == 3) {                        // quaternion Jacobians J (28) and rotation map G (12) of each knot
       if (ok) {
-        double* park = A + (size_t)kid[lane] * NX * NX + NV;       // rows 25..50 of column 0, then rows 25.. of column 1
+        double* park = A + (size_t)kid[lane] * A_STRIDE + NV;       // rows 25..50 of column 0, then rows 25.. of column 1
         for (int d = 0; d < QJ_DIRS; ++d) {
           double J4[4];
           quat_step_jac_dir(*md, x, a, d, J4);
@@ -139,7 +139,7 @@ k_linearize_tangents(const DynModel* gmd, long nknots, int N, const int* __restr
 #pragma unroll 1
       for (int e = lane; e < nk * NV; e += 32) {
         const long id = kid[k];
-        if (id >= 0) dst0[(size_t)id * NX * NX + j] = tile[e];
+        if (id >= 0) dst0[(size_t)id * A_STRIDE + j] = tile[e];
         j += 32;
         while (j >= NV) { j -= NV; ++k; }
       }
@@ -177,8 +177,8 @@ k_linearize_finish(const DynModel* __restrict__ md, long nknots, int N, const in
   const long id = lin_knot_id((long)blockIdx.x * LINF_WARPS + warp, nknots, N, active, list);
   if (id < 0) return;                                  // (no block-level barrier below)
   const double h = md->h;
-  double* Ak = A + (size_t)id * NX * NX;
-  double* Bk = Bm + (size_t)id * NX * NU;
+  double* Ak = A + (size_t)id * A_STRIDE;
+  double* Bk = Bm + (size_t)id * B_STRIDE;
   // ---- 1. stage with asynchronous copies in two groups: (A) factor + state, needed at once; (B) the parked tangents,
   //      needed only by the contraction of step 4 — their memory latency hides behind N = L^-1 and Mhat^-1.
   //      Columns 0, 1, 6 and the pad rows of T are zero ----

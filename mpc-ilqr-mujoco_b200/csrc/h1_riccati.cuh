@@ -16,6 +16,15 @@
 // Shared memory per CTA is 107 KB so that TWO instances are resident per SM: while one is in its sequential
 // section (pivoted LDLT, triangular solves) the other one keeps the tensor pipe busy.
 // Leading dimensions are = 4 (mod 8) doubles: every m8n8k4 fragment load is bank-conflict free.
+//
+// STRUCT = true (the linearization came from the analytic kernels): f_D is semi-implicit Euler, p+ = p + h v+,
+// theta+ = theta + h thetadot+, so 22 of the 26 position rows of [A|B] are  e_r' + h * (their velocity row), exactly.
+// With R = the 29 rows that carry information (4 quaternion rows, 25 velocity rows), [A|B] = P + E R, P = the unit
+// entries, E = selection + h * (position partner). Every contraction over the 51 state rows then runs over the 29
+// reduced ones:  V [A|B] = V P + (V E) R,   A'[W|Vx] = P'[W|Vx] + R_A'(E'[W|Vx]),   B'[W_B|Vx] = R_B'(E'[W_B|Vx]);
+// V E and E'W are formed in the fragment loads (one extra load + multiply-add), the P terms are one addition in the
+// epilogues: 8 k-steps instead of 13 in G1, G2, G3 (1428 instead of 2028 DMMA per knot). The dense form stays for
+// forward-difference and caller-supplied linearizations, which satisfy the relation only to their own accuracy.
 #pragma once
 #include "h1_common.cuh"
 #include <type_traits>
@@ -30,7 +39,8 @@ constexpr int LDU = 20;       // leading dimension of 19-row operands (row 19 is
 
 struct RiccatiSmem {
   double V[LDX * LDX];        // Vxx (pad row/column zero); from G2 on: Qxx, then M, then the next Vxx
-  double AB[LDX * NXU];       // [A | B] of the current knot, refilled by cp.async after G2/G3
+  double AB[LDX * NXU];       // [A_t | pad | B_t | pad] exactly as they lie in global memory (dense columns, leading dimension NX,
+                              // one pad double behind each: A_STRIDE + B_STRIDE doubles), refilled by two bulk copies after G2
   double W[LDX * NXU];        // Vxx [A | B]; after G2/G3: G (LDU x 51) followed by the prefetched lxx (51 x 51 dense)
   double Qxu[LDX * NU];
   double Kt[LDU * 56];        // solves: columns 0..50 -> K(:,j), column 51 -> kff; pad row 19 stays zero
@@ -40,19 +50,48 @@ struct RiccatiSmem {
   double Li[LDU * LDU];       // its inverse (unit lower), row-major; pad row / column 19 stay zero
   double Vx[LDX], Qx[NX], Qu[NU], D[NU], Dinv[NU], tmp[NU];   // Vx[51] is a zero pad (Vx rides along as an extra column of W)
   double lq[NX + NU + NU * NU + 1];   // lx_t, lu_t, luu_t of the current knot (prefetched with [A|B])
+  unsigned long long mbar[2];         // transaction barriers of the bulk copies: [0] lxx_t -> W, [1] [A|B] of the next knot -> AB
   int perm[NU];
 };
 constexpr int RIC_G_OFF = 0;              // G inside W
 constexpr int RIC_LXX_OFF = LDU * NX;     // prefetched lxx inside W (dense, ld 51)
-static_assert(RIC_LXX_OFF + NX * NX <= LDX * NXU, "lxx prefetch must fit behind G");
+static_assert(RIC_LXX_OFF + LXX_STRIDE <= LDX * NXU, "lxx prefetch must fit behind G");
+static_assert(A_STRIDE + B_STRIDE <= LDX * NXU, "[A|B] staging");
+static_assert((LDX * LDX * 8) % 16 == 0 && (RIC_LXX_OFF * 8) % 16 == 0, "bulk-copy destinations are 16-byte aligned");
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc));
 }
+// Bulk asynchronous copy global -> shared (SASS UBLKCP: ONE instruction per matrix, executed by the copy engine) that
+// signals a transaction barrier. Source, destination and size are multiples of 16 bytes (padded strides, h1_common.cuh).
+// Measured on B200: the same bytes as 8-byte cp.async (global columns of a 51-row matrix are only 8-byte aligned) cost the
+// issuing warps ~5 k cycles per knot — a fifth of the knot.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tRIC_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra RIC_DONE;\n\tbra RIC_WAIT;\n\tRIC_DONE:\n\t}\n"
+               ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
+// reduced row index k (0..31) -> row of [A|B] / W / column of V that carries it: quaternion rows 3..6, the 25 velocity rows,
+// then the zero pad row 51; and the position row whose tangent is h times velocity row k (pad row if there is none)
+__device__ __forceinline__ int ric_row_v(int k) { return k < 4 ? 3 + k : min(22 + k, NX); }
+__device__ __forceinline__ int ric_row_q(int k) { const int j = k - 4; return (j >= 0 && j < 3) ? j : ((j >= 6 && j < NV) ? j + 1 : NX); }
+__device__ __forceinline__ bool ric_unit_row(int r) { return r < 3 || (r >= 7 && r < NQ); }   // rows of P: d q+_r / d q_r = 1
+
 // One warp accumulates an 8 x (8 NT) strip: acc[j] += sum_k A(m0 + g, k) B(k, n0 + 8 j + g'), k < 4 ksteps.
 // fa(row, k) / fb(k, col) return operand elements (they implement padding / clamping).
 template <int NT, class FA, class FB>
@@ -158,11 +197,12 @@ __device__ __forceinline__ bool quu_ldlt(RiccatiSmem& s) {
   return not_pd;
 }
 
-#ifdef RIC_PROF   // debug build only (make NVCC="nvcc -DRIC_PROF"): per-phase cycles of warp 0 / warp 7 of block 0, printed at kernel end
+#ifdef RIC_PROF   // debug build only (tools/ric_prof.sh): per-phase cycles (work before / wait at each block barrier) of warp 0 and warp 7, summed over all blocks
+__device__ unsigned long long ric_prof_sum[2][20];
 #define RP_DECL long long rp_t = clock64(); long long rp_acc[20]; for (int q_ = 0; q_ < 20; ++q_) rp_acc[q_] = 0;
 #define RP_MARK(p) { const long long now_ = clock64(); rp_acc[p] += now_ - rp_t; rp_t = now_; }
 #define RP_SYNC(p) { RP_MARK(2 * (p)); __syncthreads(); { unsigned x_; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(x_) : "r"((unsigned)__cvta_generic_to_shared(&s.perm[0])) : "memory"); rp_acc[19] += x_ & 0; } RP_MARK(2 * (p) + 1); }
-#define RP_PRINT if (blockIdx.x == 0 && lane == 0) printf("ric warp %d work/wait: top %lld/%lld G1b %lld/%lld G3 %lld/%lld P2 %lld/%lld solve %lld/%lld G4 %lld/%lld G5 %lld/%lld sym %lld Linv %lld/%lld\n", warp, rp_acc[0], rp_acc[1], rp_acc[2], rp_acc[3], rp_acc[4], rp_acc[5], rp_acc[6], rp_acc[7], rp_acc[8], rp_acc[9], rp_acc[10], rp_acc[11], rp_acc[12], rp_acc[13], rp_acc[16], rp_acc[14], rp_acc[15]);
+#define RP_PRINT if (lane == 0 && (warp == 0 || warp == 7)) { for (int q_ = 0; q_ < 20; ++q_) atomicAdd(&ric_prof_sum[warp == 7][q_], (unsigned long long)rp_acc[q_]); }
 #else
 #define RP_DECL
 #define RP_MARK(p)
@@ -170,11 +210,12 @@ __device__ __forceinline__ bool quu_ldlt(RiccatiSmem& s) {
 #define RP_PRINT
 #endif
 
+template <bool STRUCT>
 __global__ void __launch_bounds__(RIC_THREADS, 2)
 k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambda, const double* __restrict__ A,
            const double* __restrict__ Bm, const double* __restrict__ lx, const double* __restrict__ lu,
            const double* __restrict__ lxx, const double* __restrict__ luu, double* __restrict__ K,
-           double* __restrict__ kff, int* __restrict__ status) {
+           double* __restrict__ kff, int* __restrict__ status, double h) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RiccatiSmem& s = *reinterpret_cast<RiccatiSmem*>(smem_raw);
   const int inst = blockIdx.x;
@@ -183,26 +224,33 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
   const double lam = lambda[inst];
   const double* lxN = lx + ((size_t)inst * (N + 1) + N) * NX;
-  const double* lxxN = lxx + ((size_t)inst * (N + 1) + N) * NX * NX;
-  auto prefetch_ab = [&](int t, int tid, int nt) {  // A_t, B_t -> s.AB (8-byte async copies; global columns are only 8-byte aligned)
-    const double* At = A + ((size_t)inst * N + t) * NX * NX;      // [A_t | B_t] are NOT contiguous in global memory
-    const double* Bt = Bm + ((size_t)inst * N + t) * NX * NU;
-    for (int i = tid; i < NX * NX; i += nt) { const int c = i / NX, r = i - c * NX; cp_async8(&s.AB[c * LDX + r], At + i); }
-    for (int i = tid; i < NX * NU; i += nt) { const int c = i / NX, r = i - c * NX; cp_async8(&s.AB[(NX + c) * LDX + r], Bt + i); }
-    // the small cost terms of the same knot: read in the epilogues of G2 / G3, where a global load would stall
+  const double* lxxN = lxx + ((size_t)inst * (N + 1) + N) * LXX_STRIDE;
+  // [A_t | B_t] -> s.AB: two bulk copies issued by ONE thread (barrier s.mbar[1]); lx_t, lu_t, luu_t -> s.lq: 8-byte async copies
+  // of the calling warp (their global strides are odd numbers of doubles), read in the epilogues of G2 / G3
+  auto prefetch_ab = [&](int t) {
+    if (lane == 0) {
+      mbar_expect_tx(&s.mbar[1], (A_STRIDE + B_STRIDE) * 8);
+      bulk_g2s(s.AB, A + ((size_t)inst * N + t) * A_STRIDE, A_STRIDE * 8, &s.mbar[1]);
+      bulk_g2s(s.AB + A_STRIDE, Bm + ((size_t)inst * N + t) * B_STRIDE, B_STRIDE * 8, &s.mbar[1]);
+    }
     const double* lxt = lx + ((size_t)inst * (N + 1) + t) * NX;
     const double* lut = lu + ((size_t)inst * N + t) * NU;
     const double* luut = luu + ((size_t)inst * N + t) * NU * NU;
-    for (int i = tid; i < NX + NU + NU * NU; i += nt)
+    for (int i = lane; i < NX + NU + NU * NU; i += 32)
       cp_async8(&s.lq[i], i < NX ? lxt + i : (i < NX + NU ? lut + (i - NX) : luut + (i - NX - NU)));
   };
+  // column c of [A|B] in s.AB (the pad double of A sits between the two blocks); row 51 of a column is the first entry of the next
+  // one (or a pad): finite, and always multiplied by a zero of the other operand (V and W keep their zero pad row / column)
+  auto abcol = [&](int c) -> const double* { return s.AB + c * NX + (c >= NX ? 1 : 0); };
   // zero pads (never written afterwards) and the terminal value function
   for (int i = tid; i < LDX * LDX; i += nt) s.V[i] = 0.0;
-  for (int i = tid; i < NXU; i += nt) s.AB[i * LDX + NX] = 0.0;
+  for (int i = tid; i < LDX * NXU; i += nt) s.AB[i] = 0.0;
+  if (tid == 0) { mbar_init(&s.mbar[0], 1); mbar_init(&s.mbar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
   for (int i = tid; i < LDU * 56; i += nt) s.Kt[i] = 0.0;
   for (int i = tid; i < LDU * LDU; i += nt) { s.Quu[i] = 0.0; s.Li[i] = 0.0; }
+  fence_proxy_async();   // the zero fill above (generic proxy) is ordered before the copy engine's writes
   __syncthreads();
-  prefetch_ab(N - 1, tid, nt);
+  if (warp == 7) prefetch_ab(N - 1);
   for (int i = tid; i < LDX; i += nt) s.Vx[i] = (i < NX) ? lxN[i] : 0.0;
   for (int i = tid; i < NX * NX; i += nt) {   // lxx holds its LOWER triangle (k_cost_quadratics): mirrored on load
     const int c = i / NX, r = i - c * NX;
@@ -219,30 +267,47 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
     const double* lxt = s.lq;
     const double* lut = s.lq + NX;
     const double* luut = s.lq + NX + NU;
-    cp_async_commit_wait_all();
+    cp_async_commit_wait_all();                     // (warp 7: lx, lu, luu of this knot)
+    mbar_wait(&s.mbar[1], (N - 1 - t) & 1);         // [A_t | B_t] have landed
     RP_SYNC(0)
     // ---- G1b: W(:, 48..71) = Vxx [A|B](:, 48..71) — the B block, which Quu needs first (warps 0..6: one 8-row
     //      strip each) ----
     auto w_strip = [&](auto nt_tag, int n0) {
       constexpr int NT = decltype(nt_tag)::value;
-      mma_strip_store<NT>(13, 8 * warp, n0,
-                          [&](int r, int k) { return s.V[k * LDX + min(r, LDX - 1)]; },          // pad row 51 of V is zero
-                          [&](int k, int c) { return (c < NXU ? s.AB + c * LDX : zc)[k]; },
-                          [&](int r, int c, double v) { if (r < LDX && c < NXU) s.W[c * LDX + r] = v; });   // row 51 of W = 0
+      if constexpr (STRUCT) {
+        mma_strip_store<NT>(8, 8 * warp, n0,
+                            [&](int r, int k) {   // (V E)(r, k): column 51 of V is the zero pad
+                              const int rr = min(r, LDX - 1);
+                              return fma(h, s.V[ric_row_q(k) * LDX + rr], s.V[ric_row_v(k) * LDX + rr]);
+                            },
+                            [&](int k, int c) { return (c < NXU ? abcol(c) : zc)[ric_row_v(k)]; },
+                            [&](int r, int c, double v) {
+                              if (r < LDX && c < NXU) s.W[c * LDX + r] = ric_unit_row(c) ? v + s.V[c * LDX + r] : v;   // + (V P)(r, c)
+                            });
+      } else {
+        mma_strip_store<NT>(13, 8 * warp, n0,
+                            [&](int r, int k) { return s.V[k * LDX + min(r, LDX - 1)]; },          // pad row 51 of V is zero
+                            [&](int k, int c) { return (c < NXU ? abcol(c) : zc)[k]; },
+                            [&](int r, int c, double v) { if (r < LDX && c < NXU) s.W[c * LDX + r] = v; });   // row 51 of W = 0
+      }
     };
     if (warp < 7) w_strip(std::integral_constant<int, 3>(), 48);
     RP_SYNC(1)
     // ---- G3: [Quu | B'Vx] = B' [W_B | Vx] + luu + lam I, 9 tiles over the 8 warps; the spare column 19 of the last
     //      tile column carries Vx and yields Qu = lu + B'Vx ----
     {
-      auto fa = [&](int r, int k) { return s.AB[(NX + min(r, NU - 1)) * LDX + k]; };
-      auto fb = [&](int k, int c) { return (c < NU ? s.W + (NX + c) * LDX : (c == NU ? s.Vx : zc))[k]; };
+      auto fa = [&](int r, int k) { return abcol(NX + min(r, NU - 1))[STRUCT ? ric_row_v(k) : k]; };
+      auto fb = [&](int k, int c) {
+        const double* col = c < NU ? s.W + (NX + c) * LDX : (c == NU ? s.Vx : zc);
+        if constexpr (STRUCT) return fma(h, col[ric_row_q(k)], col[ric_row_v(k)]);   // (E'[W_B | Vx])(k, c); W row 51, Vx[51] are zero
+        else return col[k];
+      };
       // one tile per warp: the 6 tiles of the lower triangle (mirrored into the upper one — LLT / LDLT only read one
       // triangle, and B'VxxB is symmetric up to rounding) and the two remaining tiles of the column that carries Qu
       const int mi = warp < 6 ? (warp < 1 ? 0 : (warp < 3 ? 1 : 2)) : warp - 6;
       const int nj = warp < 6 ? (warp < 1 ? 0 : (warp < 3 ? warp - 1 : warp - 3)) : 2;
       double c0, c1;
-      mma_tile_split<13, 4>(8 * mi, 8 * nj, fa, fb, c0, c1);
+      mma_tile_split<STRUCT ? 8 : 13, 4>(8 * mi, 8 * nj, fa, fb, c0, c1);
       const int r = 8 * mi + g;
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
@@ -263,83 +328,9 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
     RP_SYNC(2)
     // ---- warps 0..6: G1a: W(:, 0..47) = Vxx A(:, 0..47), then G2: [Qxx | Qxu | A'Vx] = A' [W | Vx] (Qxx -> s.V,
     //      Qxu -> s.Qxu, the spare column 70 of the last tile carries Vx and yields Qx = lx + A'Vx)
-    //      | warp 7: pivoted LDL^T of Quu, then N = L^-1: the sequential section of the knot, beside both contractions and the
-    //      prefetch (one barrier for the whole phase) ----
+    //      | warp 7: pivoted LDL^T of Quu, then N = L^-1: the sequential section of the knot, beside both contractions
+    //      (one barrier for the whole phase) ----
     if (warp < 7) {
-#ifdef RIC_P3_SIX   // measured on B200 (r02i): 11.05 ms per 8192-instance launch against 9.98 ms for the seven-warp split below — not adopted
-      // Six contraction warps (0,1,2,4,5,6); warp 3 — the one that shares a scheduler sub-partition with the LDL^T warp 7 —
-      // issues no DMMA in this phase: a dependent fp64 operation of the sequential warp otherwise queues behind the 16-cycle
-      // DMMAs of its neighbour at every step of the factorisation, which made the LDL^T (not the contractions) the longest
-      // part of a knot.
-      const int cq = warp < 3 ? warp : warp - 1;       // 0..5 for the contraction warps
-      if (warp != 3) {
-        // G1a by COLUMN tile: W(:, 8 cq .. 8 cq + 7) = Vxx A(:, same), all seven row tiles
-        double acc[7][2];
-#pragma unroll
-        for (int m = 0; m < 7; ++m) acc[m][0] = acc[m][1] = 0.0;
-        const double* const bq = s.AB + (8 * cq + g) * LDX + t4;
-        const double* ar[7];
-#pragma unroll
-        for (int m = 0; m < 7; ++m) ar[m] = s.V + min(8 * m + g, LDX - 1) + t4 * LDX;   // pad row 51 of V is zero
-#pragma unroll 1
-        for (int ks = 0; ks < 13; ++ks) {
-          const double b = bq[4 * ks];
-#pragma unroll
-          for (int m = 0; m < 7; ++m) dmma884(acc[m][0], acc[m][1], ar[m][4 * ks * LDX], b);
-        }
-#pragma unroll
-        for (int m = 0; m < 7; ++m) {
-          const int r = 8 * m + g;
-          if (r < LDX) { s.W[(8 * cq + 2 * t4) * LDX + r] = acc[m][0]; s.W[(8 * cq + 2 * t4 + 1) * LDX + r] = acc[m][1]; }   // row 51 of W = 0
-        }
-      }
-      asm volatile("bar.sync 1, 224;" ::: "memory");   // W complete (warp 3 arrives at once)
-      if (warp != 3) {
-        // G2: the 48 tiles of A' [W | Vx] that are read again (lower triangle of Qxx, all of Qxu and Qx), 8 per warp: column
-        // tiles are paired so that every warp has 8 — {0 (7 rows), 3}, {1 (6), 5 (2)}, {2 (5), 4 (3)}, {6, 3}, {7, 3}, {8, 3};
-        // column tile 3 has 4 tiles (rows 3..6), one for each warp that owns a 7-row column
-        int tr[8], tc[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (cq == 1) { tc[q] = q < 6 ? 1 : 5; tr[q] = q < 6 ? 1 + q : 5 + (q - 6); }
-          else if (cq == 2) { tc[q] = q < 5 ? 2 : 4; tr[q] = q < 5 ? 2 + q : 4 + (q - 5); }
-          else {
-            const int col = cq == 0 ? 0 : 3 + cq;                 // 0, 6, 7, 8
-            const int extra = cq == 0 ? 3 : cq + 1;               // row of the column-3 tile: 3, 4, 5, 6
-            tc[q] = q < 7 ? col : 3; tr[q] = q < 7 ? q : extra;
-          }
-        }
-        const double* bp[8];
-        const double* ap[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int c = 8 * tc[q] + g;
-          bp[q] = (c < NXU ? s.W + c * LDX : (c == NXU ? s.Vx : zc)) + t4;
-          ap[q] = s.AB + (8 * tr[q] + g) * LDX + t4;              // A'(r,k) = A(k,r); rows 51..55: discarded garbage
-        }
-        double acc[8][2];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q][0] = acc[q][1] = 0.0;
-#pragma unroll 1
-        for (int ks = 0; ks < 13; ++ks) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) dmma884(acc[q][0], acc[q][1], ap[q][4 * ks], bp[q][4 * ks]);
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int r = 8 * tr[q] + g;
-          if (r >= NX) continue;
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int c = 8 * tc[q] + 2 * t4 + e;
-            const double v = acc[q][e];
-            if (c < NX) s.V[c * LDX + r] = v;
-            else if (c < NXU) s.Qxu[(c - NX) * LDX + r] = v;
-            else if (c == NXU) s.Qx[r] = lxt[r] + v;
-          }
-        }
-      }
-#else
       w_strip(std::integral_constant<int, 6>(), 0);
       asm volatile("bar.sync 1, 224;" ::: "memory");   // W complete (the seven contraction warps only)
       // G2 tiles: only the lower triangle of Qxx is ever read again (G5 takes r >= c and mirrors), so of the 7 x 9 tiles
@@ -361,18 +352,29 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
 #pragma unroll
         for (int q = 0; q < 7; ++q) {
           const int c = 8 * tc[q] + g;
-          bp[q] = (c < NXU ? s.W + c * LDX : (c == NXU ? s.Vx : zc)) + t4;
+          bp[q] = (c < NXU ? s.W + c * LDX : (c == NXU ? s.Vx : zc)) + (STRUCT ? 0 : t4);
         }
-        const double* const ap1 = s.AB + (8 * warp + g) * LDX + t4;   // A'(r,k) = A(k,r); rows 51..55: discarded garbage
-        const double* const ap2 = s.AB + (8 * par + g) * LDX + t4;
+        const double* const ap1 = abcol(8 * warp + g) + (STRUCT ? 0 : t4);   // A'(r,k) = A(k,r); rows 51..55: discarded garbage
+        const double* const ap2 = abcol(8 * par + g) + (STRUCT ? 0 : t4);
         double acc[7][2];
 #pragma unroll
         for (int q = 0; q < 7; ++q) acc[q][0] = acc[q][1] = 0.0;
+        if constexpr (STRUCT) {
 #pragma unroll 1
-        for (int ks = 0; ks < 13; ++ks) {
-          const double a1 = ap1[4 * ks], a2 = ap2[4 * ks];
+          for (int ks = 0; ks < 8; ++ks) {
+            const int rv = ric_row_v(4 * ks + t4), rq = ric_row_q(4 * ks + t4);
+            const double a1 = ap1[rv], a2 = ap2[rv];                                   // R_A'(r, k)
 #pragma unroll
-          for (int q = 0; q < 7; ++q) dmma884(acc[q][0], acc[q][1], own[q] ? a1 : a2, bp[q][4 * ks]);
+            for (int q = 0; q < 7; ++q)                                                // (E'[W | Vx])(k, c): W row 51, Vx[51], zc are zero
+              dmma884(acc[q][0], acc[q][1], own[q] ? a1 : a2, fma(h, bp[q][rq], bp[q][rv]));
+          }
+        } else {
+#pragma unroll 1
+          for (int ks = 0; ks < 13; ++ks) {
+            const double a1 = ap1[4 * ks], a2 = ap2[4 * ks];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) dmma884(acc[q][0], acc[q][1], own[q] ? a1 : a2, bp[q][4 * ks]);
+          }
         }
 #pragma unroll
         for (int q = 0; q < 7; ++q) {
@@ -382,20 +384,14 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int c = 8 * tc[q] + 2 * t4 + e;
-            const double v = acc[q][e];
+            double v = acc[q][e];
+            if (STRUCT && ric_unit_row(r)) v += c < NXU ? s.W[c * LDX + r] : (c == NXU ? s.Vx[r] : 0.0);   // + (P'[W | Vx])(r, c)
             if (c < NX) s.V[c * LDX + r] = v;
             else if (c < NXU) s.Qxu[(c - NX) * LDX + r] = v;
             else if (c == NXU) s.Qx[r] = lxt[r] + v;
           }
         }
       }
-#endif
-      // s.AB, s.W and s.lq are free once all seven contraction warps are through G2 -> prefetch the next knot's [A|B], lx,
-      // lu, luu and this knot's lxx (consumed by the final pass) while warp 7 is still in its sequential section
-      asm volatile("bar.sync 1, 224;" ::: "memory");
-      if (t > 0) prefetch_ab(t - 1, tid, 7 * 32);
-      const double* Lt = lxx + ((size_t)inst * (N + 1) + t) * NX * NX;
-      for (int i = tid; i < NX * NX; i += 7 * 32) { const int c = i / NX, r = i - c * NX; if (r >= c) cp_async8(&Lpre[i], Lt + i); }   // lower triangle: all G5 reads
     } else {
       if (quu_ldlt(s)) {          // Eigen::LLT failed: Quu += 1e-4 I once, no re-check (quirk Q9), refactor
         for (int i = lane; i < NU; i += 32) s.Quu[i * LDU + i] += 1e-4;
@@ -420,6 +416,7 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
         }
       }
     }
+    fence_proxy_async();   // this phase's generic accesses to s.AB / s.W are ordered before the copy engine overwrites them
     RP_SYNC(7)
     // ---- K = -Quu^-1 Qxu', k = -Quu^-1 Qu with P Quu P' = L D L':  X = P' N' D^-1 N (P R), R = [Qxu' | Qu] (19 x 52).
     //      Each of the warps 0..6 owns one 8-column tile of R: Y = N (P R), Z = D^-1 Y parked in its own columns of
@@ -515,8 +512,15 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
           }
         }
       }
+    } else {
+      // warp 7 has nothing to solve: it starts the copies — s.AB, s.W and s.lq are free since the barrier above: this knot's lxx
+      // (G5 adds it; dense, its lower triangle is what k_cost_quadratics wrote) and the next knot's [A|B], lx, lu, luu
+      if (lane == 0) {
+        mbar_expect_tx(&s.mbar[0], LXX_STRIDE * 8);
+        bulk_g2s(Lpre, lxx + ((size_t)inst * (N + 1) + t) * LXX_STRIDE, LXX_STRIDE * 8, &s.mbar[0]);
+      }
+      if (t > 0) prefetch_ab(t - 1);
     }
-    cp_async_commit_wait_all();   // lxx_t (and the next [A|B]) have landed: G5 adds lxx in its own epilogue
     RP_SYNC(4)
     {   // gains to global
       double* Kt_g = K + ((size_t)inst * N + t) * NU * NX;
@@ -529,6 +533,7 @@ k_backward(int N, const int* __restrict__ mask, const double* __restrict__ lambd
     //      K'G = K'QuuK + 2 K'Qxu' is symmetric up to rounding (K = -S Qxu' with S = P'N'D^-1 N P symmetric by
     //      construction), so the reference's 0.5 (M + M') differs from the mirrored lower triangle by rounding only ----
     if (warp < 7) {
+      mbar_wait(&s.mbar[0], (N - 1 - t) & 1);       // lxx_t has landed
       const int par = 6 - warp;
       int tc[4];
       bool own[4];

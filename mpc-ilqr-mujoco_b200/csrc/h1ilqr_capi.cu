@@ -67,6 +67,11 @@ struct H1Ilqr {
   long lin_cols_min_knots = 148 * 32;   // AUTO: B*N at or above which the direction-uniform linearization (32 knots per CTA) fills the GPU;
                                         // below it the knot-major thread-per-column kernel (k_linearize_dirs) is the faster one
   size_t smem_dyn4 = 0, smem_lin = 0, smem_cq = 0, smem_ls = 0, smem_ric = 0;
+  // Riccati: [A|B] in h->A / h->Bm were written by an analytic linearization kernel (position rows = unit entry + dt * velocity
+  // rows, h1_riccati.cuh) -> the contractions run over the 29 reduced rows. Cleared by the forward-difference kernel and by
+  // h1ilqr_set_linearization; H1_RIC_DENSE=1 keeps the dense kernel (A/B measurements)
+  bool ab_struct = false, ric_struct_ok = true;
+  double dt = 0.0;
   // device-resident closed loop: full reference tables, per-instance time index, step counter, per-step logs
   double *tab_x = nullptr, *tab_com = nullptr, *tab_ee = nullptr, *tab_cv = nullptr;
   int* tab_contact = nullptr;
@@ -148,6 +153,8 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
     delete h; return set_err(H1ILQR_EARG, "model is not a DFS-ordered H1-like tree");
   }
   h->seq_ok = dm.seq_ok != 0;
+  h->dt = dm.h;
+  if (const char* e = getenv("H1_RIC_DENSE")) h->ric_struct_ok = atoi(e) == 0;
   if (const char* e = getenv("H1_SEQ_MIN_BATCH")) h->seq_min_batch = atoi(e);   // tuning experiments
 #define CUH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(H1ILQR_ECUDA, #call, e_); h1ilqr_destroy(h); return H1ILQR_ECUDA; } } while (0)
   CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -164,9 +171,9 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   CUH(cudaStreamSynchronize(h->stream));  // dm / cm are stack objects
   CUH(dalloc(h, &h->xbar, B * N1 * NX)); CUH(dalloc(h, &h->ubar, B * N * NU));
   CUH(dalloc(h, &h->K, B * N * NU * NX)); CUH(dalloc(h, &h->kff, B * N * NU));
-  CUH(dalloc(h, &h->A, B * N * NX * NX)); CUH(dalloc(h, &h->Bm, B * N * NX * NU));
+  CUH(dalloc(h, &h->A, B * N * A_STRIDE)); CUH(dalloc(h, &h->Bm, B * N * B_STRIDE));   // padded per-knot strides (h1_common.cuh)
   CUH(dalloc(h, &h->lx, B * N1 * NX)); CUH(dalloc(h, &h->lu, B * N * NU));
-  CUH(dalloc(h, &h->lxx, B * N1 * NX * NX)); CUH(dalloc(h, &h->luu, B * N * NU * NU));
+  CUH(dalloc(h, &h->lxx, B * N1 * LXX_STRIDE)); CUH(dalloc(h, &h->luu, B * N * NU * NU));
   CUH(dalloc(h, &h->xnew, B * H1ILQR_NALPHA * N1 * NX)); CUH(dalloc(h, &h->unew, B * H1ILQR_NALPHA * N * NU));
   CUH(dalloc(h, &h->x0, B * NX)); CUH(dalloc(h, &h->u_init, B * NU)); CUH(dalloc(h, &h->u_apply, B * NU));
   CUH(dalloc(h, &h->prev_xbar, B * N1 * NX)); CUH(dalloc(h, &h->prev_ubar, B * N * NU));
@@ -228,7 +235,8 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   CUH(cudaFuncSetAttribute(k_cost_quadratics<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_cq));
   CUH(cudaFuncSetAttribute(k_cost_quadratics<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_cq));
   CUH(cudaFuncSetAttribute(k_line_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_ls));
-  CUH(cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_ric));
+  CUH(cudaFuncSetAttribute(k_backward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_ric));
+  CUH(cudaFuncSetAttribute(k_backward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_ric));
   CUH(cudaStreamSynchronize(h->stream));
   CUH(cudaGetLastError());
 #undef CUH
@@ -369,6 +377,7 @@ static void launch_factors(H1Ilqr* h, const int* mask) {
 }
 // `factors_ready`: the factorisations of Mhat of the current trajectory are already in h->pf
 static void launch_linearize(H1Ilqr* h, const int* mask, bool factors_ready = false) {
+  h->ab_struct = h->opt.linearization != H1ILQR_LIN_FD;
   if (h->opt.linearization != H1ILQR_LIN_FD) {
     if (!factors_ready) launch_factors(h, mask);
     const long knots = (long)h->B * h->N;
@@ -418,8 +427,12 @@ static void launch_cost_quadratics(H1Ilqr* h, const int* mask) {
   LAUNCHED();
 }
 static void launch_backward(H1Ilqr* h, const int* mask) {
-  k_backward<<<h->B, RIC_THREADS, h->smem_ric, h->stream>>>(h->N, mask, h->lambda, h->A, h->Bm, h->lx, h->lu, h->lxx,
-                                                           h->luu, h->K, h->kff, h->status);
+  if (h->ab_struct && h->ric_struct_ok)
+    k_backward<true><<<h->B, RIC_THREADS, h->smem_ric, h->stream>>>(h->N, mask, h->lambda, h->A, h->Bm, h->lx, h->lu, h->lxx,
+                                                                   h->luu, h->K, h->kff, h->status, h->dt);
+  else
+    k_backward<false><<<h->B, RIC_THREADS, h->smem_ric, h->stream>>>(h->N, mask, h->lambda, h->A, h->Bm, h->lx, h->lu, h->lxx,
+                                                                    h->luu, h->K, h->kff, h->status, 0.0);
   LAUNCHED();
 }
 static void launch_line_search(H1Ilqr* h, const int* mask) {
@@ -928,6 +941,15 @@ int h1ilqr_rollout_nominal(H1Ilqr* h, const double* x0) {
 }
 int h1ilqr_linearize(H1Ilqr* h) { GUARD(h); launch_linearize(h, nullptr); SYNC(); CU(cudaGetLastError()); return 0; }
 int h1ilqr_cost_quadratics(H1Ilqr* h) { GUARD(h); launch_cost_quadratics(h, nullptr); SYNC(); CU(cudaGetLastError()); return 0; }
+#ifdef RIC_PROF   // debug build only: read and clear the per-phase cycle sums of k_backward (not part of the ABI)
+int h1ilqr_debug_ric_prof(unsigned long long* out40) {
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpyFromSymbol(out40, h1::ric_prof_sum, sizeof(unsigned long long) * 40));
+  static const unsigned long long zeros[40] = {0};
+  CU(cudaMemcpyToSymbol(h1::ric_prof_sum, zeros, sizeof(zeros)));
+  return 0;
+}
+#endif
 int h1ilqr_backward_pass(H1Ilqr* h) { GUARD(h); launch_backward(h, nullptr); SYNC(); CU(cudaGetLastError()); return 0; }
 int h1ilqr_total_cost(H1Ilqr* h, double* cost_out) {
   GUARD(h);
@@ -1149,7 +1171,22 @@ int h1ilqr_sole_points(H1Ilqr* h, int n, const double* x, double* pts) {
 #define SZ(x) ((size_t)h->B * (x))
 COPY_PAIR(h1ilqr_get_trajectory, h1ilqr_set_trajectory, xbar, SZ((h->N + 1) * NX), ubar, SZ(h->N * NU))
 COPY_PAIR(h1ilqr_get_gains, h1ilqr_set_gains, K, SZ(h->N * NU * NX), kff, SZ(h->N * NU))
-COPY_PAIR(h1ilqr_get_linearization, h1ilqr_set_linearization, A, SZ(h->N * NX * NX), Bm, SZ(h->N * NX * NU))
+// A_k, B_k, lxx_k sit at padded per-knot strides on the device (h1_common.cuh); the caller's arrays are dense
+#define D2H_PITCH(dst, src, n, stride, count) CU(cudaMemcpy2DAsync(dst, (size_t)(n) * sizeof(double), src, (size_t)(stride) * sizeof(double), (size_t)(n) * sizeof(double), (size_t)(count), cudaMemcpyDeviceToHost, h->stream))
+#define H2D_PITCH(dst, src, n, stride, count) CU(cudaMemcpy2DAsync(dst, (size_t)(stride) * sizeof(double), src, (size_t)(n) * sizeof(double), (size_t)(n) * sizeof(double), (size_t)(count), cudaMemcpyHostToDevice, h->stream))
+int h1ilqr_get_linearization(H1Ilqr* h, double* A, double* B) {
+  GUARD(h);
+  if (A) D2H_PITCH(A, h->A, NX * NX, A_STRIDE, SZ(h->N));
+  if (B) D2H_PITCH(B, h->Bm, NX * NU, B_STRIDE, SZ(h->N));
+  SYNC(); return 0;
+}
+int h1ilqr_set_linearization(H1Ilqr* h, const double* A, const double* B) {
+  GUARD(h);
+  h->ab_struct = false;   // caller-supplied [A|B]: no structure assumed, dense Riccati contractions
+  if (A) H2D_PITCH(h->A, A, NX * NX, A_STRIDE, SZ(h->N));
+  if (B) H2D_PITCH(h->Bm, B, NX * NU, B_STRIDE, SZ(h->N));
+  SYNC(); return 0;
+}
 
 // previous solution of the MPC loop (MPC::prev_xbar_ / prev_ubar_, mpc.hpp:57-58): the warm start shifts it (k_init_guess)
 int h1ilqr_set_previous_solution(H1Ilqr* h, const double* prev_xbar, const double* prev_ubar) {
@@ -1174,7 +1211,7 @@ int h1ilqr_get_cost_quadratics(H1Ilqr* h, double* lx, double* lu, double* lxx, d
   if (lxx) {   // the device keeps the lower triangle: mirror it for the caller
     k_mirror_lower<<<(unsigned)SZ(h->N + 1), 128, 0, h->stream>>>((long)SZ(h->N + 1), h->lxx);
     LAUNCHED();
-    D2H(lxx, h->lxx, SZ((h->N + 1) * NX * NX) * sizeof(double));
+    D2H_PITCH(lxx, h->lxx, NX * NX, LXX_STRIDE, SZ(h->N + 1));
   }
   if (luu) D2H(luu, h->luu, SZ(h->N * NU * NU) * sizeof(double));
   SYNC(); return 0;
@@ -1183,7 +1220,7 @@ int h1ilqr_set_cost_quadratics(H1Ilqr* h, const double* lx, const double* lu, co
   GUARD(h);
   if (lx) H2D(h->lx, lx, SZ((h->N + 1) * NX) * sizeof(double));
   if (lu) H2D(h->lu, lu, SZ(h->N * NU) * sizeof(double));
-  if (lxx) H2D(h->lxx, lxx, SZ((h->N + 1) * NX * NX) * sizeof(double));
+  if (lxx) H2D_PITCH(h->lxx, lxx, NX * NX, LXX_STRIDE, SZ(h->N + 1));
   if (luu) H2D(h->luu, luu, SZ(h->N * NU * NU) * sizeof(double));
   SYNC(); return 0;
 }

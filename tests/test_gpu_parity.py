@@ -179,6 +179,39 @@ def test_backward_pass_parity(gpu, oracle):
     assert rel(kff[0], so.get("kff")) < 1e-8
 
 
+@pytest.mark.parametrize("policy", [0, 1, 2])
+def test_riccati_structured_contractions(gpu, oracle, policy):
+    """After an analytic linearization the backward pass contracts over the 29 rows of [A|B] that carry information
+    (h1_riccati.cuh, STRUCT): (i) every analytic linearization kernel (AUTO at batch 1: thread per column; cooperative;
+    batched) writes position rows that equal unit entry + dt * velocity row to the last bit or two; (ii) the structured
+    pass, the dense pass on the same [A|B] (caller-supplied linearization -> dense) and the oracle agree."""
+    so, sg, win = _setup_pair(gpu, "walking", policy=policy)
+    x0 = win[0][3].copy()
+    x0[3:7] *= 1.01
+    ug = grav_comp_guess(standing_state())
+    _prepare_iteration(so, x0, ug)
+    so.backward_pass()
+    sg.initialize(x0[None], None, ug)
+    sg.rollout_nominal(x0[None]); sg.linearize(); sg.cost_quadratics()
+    A, B = sg.get_linearization()
+    dt = Config().mpc.dt
+    AB = np.concatenate([A[0], B[0]], axis=1)            # [knot][column][row]
+    for r in list(range(3)) + list(range(7, 26)):
+        v = 26 + (r if r < 3 else r - 1)
+        unit = np.zeros(70); unit[r] = 1.0
+        want = unit + dt * AB[:, :, v]
+        assert (np.abs(AB[:, :, r] - want) <= 4e-16 * np.maximum(1.0, np.abs(want))).all(), r
+    sg.backward_pass()
+    K1, k1 = sg.get_gains()
+    sg.set_linearization(A, B)
+    sg.backward_pass()
+    K2, k2 = sg.get_gains()
+    assert not (K1 == K2).all()                           # two different kernels ran
+    assert rel(K1, K2) < 1e-8 and rel(k1, k2) < 1e-8
+    assert rel(K1[0], so.get("K")) < 1e-8 and rel(k1[0], so.get("kff")) < 1e-8
+    assert rel(K2[0], so.get("K")) < 1e-8 and rel(k2[0], so.get("kff")) < 1e-8
+
+
 def test_line_search_parity(gpu, oracle):
     so, sg, win = _setup_pair(gpu, "walking")
     x0 = standing_state()

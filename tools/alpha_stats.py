@@ -4,15 +4,16 @@ import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import bench
 from mpc_ilqr_mujoco_b200 import Config, gpu
+from mpc_ilqr_mujoco_b200 import workloads as wl
+from mpc_ilqr_mujoco_b200.references import standing_state
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 s = gpu.H1IlqrBatch(Config().build_weights(), N=25, batch=B)
 s.set_kernel_policy(int(os.environ.get("H1_POLICY", "0")))
-win, x0 = bench.workload(B, 0, s.reference_kinematics)
+win, x0, _ = wl.walking_instances(np.arange(B), s.reference_kinematics)
 s.set_reference_window(*win, shared=False)
-ug = np.zeros(19); ug[:18] = s.bias_forces(bench._standing()[None])[0][7:25]
+ug = np.zeros(19); ug[:18] = s.bias_forces(standing_state()[None])[0][7:25]
 s.upload_inputs(x0, ug)
 for _ in range(2):
     ms = s.run_resident_steps(1, True)
