@@ -376,9 +376,16 @@ def main():
         solver.rollout_nominal(x0); solver.linearize(); solver.cost_quadratics(); solver.backward_pass()
         kern = {}
         knots = B * N_HORIZON
-        for st in ("factor", "linearize", "cost_quadratics", "backward", "line_search"):
-            solver.time_stage(st, 1)
-            kern[st] = solver.time_stage(st, 3)
+        # stages interleaved as they are in a solve (a back-to-back train of one kernel is not what the step runs: on a warm
+        # box the DMMA-heavy backward pass alone read 10 % slower that way), median of 5 rounds after one warm-up round
+        stages = ("factor", "linearize", "cost_quadratics", "backward", "line_search")
+        samples = {st: [] for st in stages}
+        for rnd in range(6):
+            for st in stages:
+                ms_st = solver.time_stage(st, 1)
+                if rnd:
+                    samples[st].append(ms_st)
+        kern = {st: float(np.median(samples[st])) for st in stages}
         bwd_s = kern["backward"] * 1e-3
         bwd_tflops = knots * BWD_FLOPS_PER_KNOT / bwd_s / 1e12
         kernels = {
@@ -454,7 +461,8 @@ def main():
                          "hbm": {"achieved": knots * BWD_ALG_BYTES_PER_KNOT / bwd_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": knots * BWD_ALG_BYTES_PER_KNOT / bwd_s / 1e9 / hbm_peak, "peak_source": hbm_src},
                          "note": "achieved = ALGORITHMIC flops (SURVEY 8(d): 1.153 MFLOP per knot, no symmetry credit) x knots of one full-batch launch / its "
-                                 "duration (CUDA events, h1ilqr_time_stage); the kernel executes 2028 DMMA = 1.04 MFLOP per knot (lower triangles of Qxx / Vxx only)"},
+                                 "duration (CUDA events, h1ilqr_time_stage, median of 5 with the stages interleaved); the kernel executes 1428 DMMA = 0.73 MFLOP per knot "
+                                 "(lower triangles of Qxx / Vxx only; contractions over the 29 information-carrying rows of [A|B], h1_riccati.cuh)"},
             "kernels": kernels, "fp64_fma_peak_tflops": fp64_peak, "kernel_metrics_file": km_file,
             "stage_ms_per_solve": stage,
             "warm_closed_loop": warm,
