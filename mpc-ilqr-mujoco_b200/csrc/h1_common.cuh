@@ -82,6 +82,10 @@ struct DynModel {
   int pad_;
   int nchild[NB];            // number of child bodies (branch bodies keep their state in the sequential walks)
   int dir_order[NB - 1];     // hinged bodies by decreasing subtree size (costliest linearization directions first)
+  // work order of the merged tangent kernel (h1_lin_finish.cuh): all 49 direction items of a knot group, class by class
+  // (class << 5 | item of that class), costliest first within a class (model_tables.cpp)
+  unsigned char tan_order[52];
+  int n_tan_items;
   int seq_ok;                // 1: the tree has H1's chain structure the thread-sequential f_D (h1_dyn_seq.cuh) is specialised for
 };
 

@@ -45,6 +45,12 @@ __device__ __forceinline__ long lin_knot_id(long slot, long nslots, int N, const
 //     2: rigid directions: base rotations (3), z, base linear velocity (3); plus one item per CTA that computes the
 //        per-knot Jacobians of the quaternion update and the quaternion -> rotation-vector map for step 2 (parked in
 //        the unused rows 25.. of columns 0 and 1 of A_k)
+//     3: ALL of the above in one launch, the 49 items of a knot group in the order DynModel::tan_order (class by class, costliest
+//        first: model_tables.cpp has the measurements). One launch per class left the eight warps of a CTA idle at the end of every
+//        group, and staged the group's states / accelerations / sines three times.
+#ifdef LINT_PROF   // debug build only (tools/lint_prof.py): cycles per item code, per-warp busy time and CTA makespan, summed over all CTAs
+__device__ unsigned long long lint_prof_item[128], lint_prof_busy, lint_prof_span, lint_prof_stage;
+#endif
 template <int CLS>
 __global__ void __launch_bounds__(LINT_THREADS)
 k_linearize_tangents(const DynModel* gmd, long nknots, int N, const int* __restrict__ active,
@@ -87,6 +93,10 @@ k_linearize_tangents(const DynModel* gmd, long nknots, int N, const int* __restr
     if (kid[k] >= 0) sincos_t(xs[k * NX + 7 + b], &scs[k * LINT_SC + 2 * b], &scs[k * LINT_SC + 2 * b + 1]);
   }
   __syncthreads();
+#ifdef LINT_PROF
+  const long long lp_t0 = clock64();
+  long long lp_busy = 0;
+#endif
   const bool ok = lane < nk && kid[lane] >= 0;
   const double* x = xs + lane * NX;
   const double* a = as + lane * NV;
@@ -96,9 +106,18 @@ k_linearize_tangents(const DynModel* gmd, long nknots, int N, const int* __restr
     int it = 0;
     if (lane == 0) it = atomicAdd(&next_item, 1);
     it = __shfl_sync(0xffffffffu, it, 0);
-    if (it >= lint_nitems(CLS)) break;
+#ifdef LINT_PROF
+    const long long lp_i0 = clock64();
+    const int lp_it = it;
+#endif
+    int cls = CLS;
+    if (CLS == 3) {
+      if (it >= md->n_tan_items) break;
+      const int code = md->tan_order[it];
+      cls = code >> 5; it = code & 31;
+    } else if (it >= lint_nitems(CLS)) break;
     int col;                                          // column of A_k the tangent is parked in
-    if (CLS == 2 && it == 3) {                        // quaternion Jacobians J (28) and rotation map G (12) of each knot
+    if (cls == 2 && it == 3) {                        // quaternion Jacobians J (28) and rotation map G (12) of each knot
       if (ok) {
         double* park = A + (size_t)kid[lane] * A_STRIDE + NV;       // rows 25..50 of column 0, then rows 25.. of column 1
         for (int d = 0; d < QJ_DIRS; ++d) {
@@ -116,10 +135,10 @@ k_linearize_tangents(const DynModel* gmd, long nknots, int N, const int* __restr
     }
     if (ok) {
       double tv[NV];
-      if (CLS == 0) {
+      if (cls == 0) {
         col = 6 + md->dir_order[it];                  // hinges by decreasing subtree size
         id_tangent_sub<Dual, Dual>(*md, x, a, col, col - 6, tv, sc);
-      } else if (CLS == 1) {
+      } else if (cls == 1) {
         if (it < 3) { col = NQ + 3 + it; id_tangent_seq<double, Dual>(*md, x, a, col, tv, sc); }
         else { col = NQ + 5 + md->dir_order[it - 3]; id_tangent_sub<double, Dual>(*md, x, a, col, col - NQ - 5, tv, sc); }
       } else {
@@ -128,8 +147,8 @@ k_linearize_tangents(const DynModel* gmd, long nknots, int N, const int* __restr
       }
       for (int j = 0; j < NV; ++j) tl[j] = tv[j];
     }
-    if (CLS == 0) col = 6 + md->dir_order[it];
-    else if (CLS == 1) col = it < 3 ? NQ + 3 + it : NQ + 5 + md->dir_order[it - 3];
+    if (cls == 0) col = 6 + md->dir_order[it];
+    else if (cls == 1) col = it < 3 ? NQ + 3 + it : NQ + 5 + md->dir_order[it - 3];
     else col = it < 3 ? 3 + it : (it == 4 ? 2 : NQ + it - 5);
     __syncwarp();
     {
@@ -145,7 +164,15 @@ k_linearize_tangents(const DynModel* gmd, long nknots, int N, const int* __restr
       }
     }
     __syncwarp();
+#ifdef LINT_PROF
+    { const long long d = clock64() - lp_i0; lp_busy += d; if (lane == 0) atomicAdd(&lint_prof_item[CLS == 3 ? md->tan_order[lp_it] : (CLS << 5 | lp_it)], (unsigned long long)d); }
+#endif
   }
+#ifdef LINT_PROF
+  if (lane == 0) atomicAdd(&lint_prof_busy, (unsigned long long)lp_busy);
+  __syncthreads();
+  if (tid == 0) { atomicAdd(&lint_prof_span, (unsigned long long)(clock64() - lp_t0)); }
+#endif
 }
 
 // ---- step 2 ----

@@ -71,6 +71,7 @@ struct H1Ilqr {
   // rows, h1_riccati.cuh) -> the contractions run over the 29 reduced rows. Cleared by the forward-difference kernel and by
   // h1ilqr_set_linearization; H1_RIC_DENSE=1 keeps the dense kernel (A/B measurements)
   bool ab_struct = false, ric_struct_ok = true;
+  bool lint_merged = true;   // tangent directions of all three classes in one launch (h1_lin_finish.cuh)
   double dt = 0.0;
   // device-resident closed loop: full reference tables, per-instance time index, step counter, per-step logs
   double *tab_x = nullptr, *tab_com = nullptr, *tab_ee = nullptr, *tab_cv = nullptr;
@@ -208,6 +209,8 @@ int h1ilqr_create(const H1Model* dyn_model, const H1Model* cost_model, const H1S
   CUH(cudaFuncSetAttribute(k_linearize_tangents<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_lint));
   CUH(cudaFuncSetAttribute(k_linearize_tangents<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_lint));
   CUH(cudaFuncSetAttribute(k_linearize_tangents<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_lint));
+  CUH(cudaFuncSetAttribute(k_linearize_tangents<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_lint));
+  if (const char* e = getenv("H1_LINT_SPLIT")) h->lint_merged = atoi(e) == 0;   // A/B measurements: one launch per direction class
   CUH(cudaFuncSetAttribute(k_linearize_finish<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_linf));
   CUH(cudaFuncSetAttribute(k_linearize_finish<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_linf));
   if (const char* e = getenv("H1_SEQ_SMEM_PAD")) h->smem_seq += (size_t)atoi(e) * 1024;   // experiment: limits resident CTAs
@@ -387,7 +390,8 @@ static void launch_linearize(H1Ilqr* h, const int* mask, bool factors_ready = fa
       // tangents parked in A_k, then one dense contraction per knot (h1_lin_finish.cuh)
 #define LINT_LAUNCH(CLS) \
   k_linearize_tangents<CLS><<<kb, LINT_THREADS, h->smem_lint, h->stream>>>(h->d_dyn, knots, h->N, mask, list, cnt, h->xbar, h->pf, h->A)
-      LINT_LAUNCH(0); LINT_LAUNCH(1); LINT_LAUNCH(2);
+      if (h->lint_merged) { LINT_LAUNCH(3); h->launches -= 2; }
+      else { LINT_LAUNCH(0); LINT_LAUNCH(1); LINT_LAUNCH(2); }
 #undef LINT_LAUNCH
       const unsigned fb = (unsigned)((knots + LINF_WARPS - 1) / LINF_WARPS);
       if (h->seq_ok) k_linearize_finish<true><<<fb, LINF_THREADS, h->smem_linf, h->stream>>>(h->d_dyn, knots, h->N, mask, list, cnt, h->xbar, h->ubar, h->pf, h->A, h->Bm);
@@ -941,6 +945,19 @@ int h1ilqr_rollout_nominal(H1Ilqr* h, const double* x0) {
 }
 int h1ilqr_linearize(H1Ilqr* h) { GUARD(h); launch_linearize(h, nullptr); SYNC(); CU(cudaGetLastError()); return 0; }
 int h1ilqr_cost_quadratics(H1Ilqr* h) { GUARD(h); launch_cost_quadratics(h, nullptr); SYNC(); CU(cudaGetLastError()); return 0; }
+#ifdef LINT_PROF   // debug build only: read and clear the per-item cycle sums of k_linearize_tangents (not part of the ABI)
+int h1ilqr_debug_lint_prof(unsigned long long* out131) {
+  CU(cudaDeviceSynchronize());
+  static const unsigned long long zeros[128] = {0};
+  CU(cudaMemcpyFromSymbol(out131, h1::lint_prof_item, sizeof(unsigned long long) * 128));
+  CU(cudaMemcpyFromSymbol(out131 + 128, h1::lint_prof_busy, sizeof(unsigned long long)));
+  CU(cudaMemcpyFromSymbol(out131 + 129, h1::lint_prof_span, sizeof(unsigned long long)));
+  CU(cudaMemcpyToSymbol(h1::lint_prof_item, zeros, sizeof(zeros)));
+  CU(cudaMemcpyToSymbol(h1::lint_prof_busy, zeros, sizeof(unsigned long long)));
+  CU(cudaMemcpyToSymbol(h1::lint_prof_span, zeros, sizeof(unsigned long long)));
+  return 0;
+}
+#endif
 #ifdef RIC_PROF   // debug build only: read and clear the per-phase cycle sums of k_backward (not part of the ABI)
 int h1ilqr_debug_ric_prof(unsigned long long* out40) {
   CU(cudaDeviceSynchronize());

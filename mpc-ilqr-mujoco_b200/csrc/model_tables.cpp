@@ -1,5 +1,6 @@
 // Host-side construction of the device model tables (h1::DynModel / h1::CostModel) from the plain-C
 // H1Model description: ancestor lists, dof-tree levels and subtree ranges used by the lane-parallel kernels.
+#include <cstdlib>
 #include "model_tables.h"
 #include "../../include/h1_model_data.h"
 #include <cstring>
@@ -85,6 +86,25 @@ bool build_dyn_model(const H1Model& m, DynModel* d) {
     for (int sz = NB; sz >= 1; --sz)
       for (int b = 1; b < NB; ++b)
         if (d->chain_end[b] - b + 1 == sz) d->dir_order[n++] = b;
+  }
+  {  // merged tangent kernel (h1_lin_finish.cuh): the 49 direction items of a knot group, class by class — 2 (base rotations, z and
+     // base linear velocity, then the quaternion-Jacobian item), 0 (hinge angles), 1 (base angular velocity, hinge rates) — and
+     // costliest first within a class (hinges in dir_order). Measured on B200 per 8192-instance linearization (tools/lint_prof.py):
+     // one launch per class 8.83 ms (the eight warps of a CTA are busy 82 % of the time), this order 8.26 ms (92 %), 0-2-1 8.33,
+     // 1-0-2 8.55, all items sorted by measured cost 8.49: an item runs ~20 % slower when all eight warps are busy (the 2 KB
+     // stack frames of 256 threads no longer fit L1), and mixing the classes' code in time costs more than the last 3 % of balance.
+    const int nh = NB - 1;
+    const char* seq = "201";
+    if (const char* e = getenv("H1_TAN_ORDER")) seq = e;   // A/B measurements: another class sequence
+    int k = 0;
+    for (const char* c = seq; *c && k <= 49; ++c) {
+      const int cls = *c - '0';
+      if (cls == 0) for (int i = 0; i < nh; ++i) d->tan_order[k++] = (unsigned char)((0 << 5) | i);
+      if (cls == 1) for (int i = 0; i < 3 + nh; ++i) d->tan_order[k++] = (unsigned char)((1 << 5) | i);
+      if (cls == 2) { const int o[8] = {0, 1, 2, 4, 5, 6, 7, 3}; for (int i = 0; i < 8; ++i) d->tan_order[k++] = (unsigned char)((2 << 5) | o[i]); }
+    }
+    if (k != 2 * nh + 11) return false;
+    d->n_tan_items = k;
   }
   // thread-sequential f_D (h1_dyn_seq.cuh): specialised for base + two 5-hinge leg chains ending in the feet
   // (bodies 1-5, 6-10) + torso (11) + two 4-hinge arm chains below the torso (12-15, 16-19)
