@@ -391,7 +391,7 @@ def main():
         kernels = {
             "k_backward": {"ms_per_launch": kern["backward"], "bound": "tensor (fp64 DMMA)", "achieved_tflops": bwd_tflops,
                            "frac": bwd_tflops / max(dmma_peak, 1e-9)},
-            "k_linearize_tangents<0..2> + k_linearize_finish": {
+            "k_linearize_tangents<3> + k_linearize_finish": {
                 "ms_per_launch": kern["linearize"], "bound": "hbm",
                 "achieved_gbs": knots * LIN_ALG_BYTES_PER_KNOT / (kern["linearize"] * 1e-3) / 1e9,
                 "frac": knots * LIN_ALG_BYTES_PER_KNOT / (kern["linearize"] * 1e-3) / 1e9 / hbm_peak},
