@@ -134,7 +134,8 @@ k_linearize_tangents(const DynModel* gmd, long nknots, int N, const int* __restr
       continue;
     }
     if (ok) {
-      double tv[NV];
+      double* const tv = tl;   // straight into this lane's row of the warp's tile (shared memory): a local array here is 200 B more
+                               // of per-thread stack, whose write-back traffic is what this kernel's DRAM writes mostly are
       if (cls == 0) {
         col = 6 + md->dir_order[it];                  // hinges by decreasing subtree size
         id_tangent_sub<Dual, Dual>(*md, x, a, col, col - 6, tv, sc);
@@ -145,7 +146,6 @@ k_linearize_tangents(const DynModel* gmd, long nknots, int N, const int* __restr
         if (it < 3) { col = 3 + it; id_tangent_rot(*md, x, a, it, tv, sc); }
         else { col = it == 4 ? 2 : NQ + it - 5; id_tangent_rigid(*md, x, a, col, tv, sc); }
       }
-      for (int j = 0; j < NV; ++j) tl[j] = tv[j];
     }
     if (cls == 0) col = 6 + md->dir_order[it];
     else if (cls == 1) col = it < 3 ? NQ + 3 + it : NQ + 5 + md->dir_order[it - 3];
