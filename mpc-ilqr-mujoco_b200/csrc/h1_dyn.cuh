@@ -137,7 +137,11 @@ template <class T> H1_DEV void col_of(const T* R, int c, T* o) {
 template <class T> H1_DEV void quat_normalize(const T* q, T* qn) {
   T n = sqrt_t(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   if (n < 1e-12) { qn[0] = T(1.0); qn[1] = qn[2] = qn[3] = T(0.0); }
-  else { qn[0] = q[0] / n; qn[1] = q[1] / n; qn[2] = q[2] / n; qn[3] = q[3] / n; }
+  else {   // one reciprocal, four products (within an ulp of the four quotients; a quaternion is normalised three times per f_D
+           // evaluation and the four fp64 divisions were the top stall line of the line-search kernel)
+    const T inv = T(1.0) / n;
+    qn[0] = q[0] * inv; qn[1] = q[1] * inv; qn[2] = q[2] * inv; qn[3] = q[3] * inv;
+  }
 }
 template <class T> H1_DEV void quat_to_mat(const T* q, T* R) {
   T q00 = q[0] * q[0], q11 = q[1] * q[1], q22 = q[2] * q[2], q33 = q[3] * q[3];
