@@ -66,7 +66,7 @@ struct DynModel {
   double jnt_lo[NU], jnt_hi[NU];
   double foot_pts[NCPT][3];
   double gravity[3];
-  double h, kn, bn, bt, eps, total_mass;
+  double h, kn, bn, bt, eps, total_mass, inv_total_mass;
   int parent[NB], axis[NB], has_rfix[NB], depth[NB];
   int anc_body[NB][6];       // anc_body[b][d]: ancestor of b at depth d (d = depth[b] -> b itself)
   int nlist[NV];             // #slots of dof j: its ancestor dofs root->self, self included

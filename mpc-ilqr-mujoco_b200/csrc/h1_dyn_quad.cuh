@@ -157,8 +157,14 @@ H1_DEV void q4_contact(const DynModel& md, int f, const SeqBodyState& c, double 
     cross_m(c.V, rho, t1);
     const double pd[3] = {c.V[3] + t1[0], c.V[4] + t1[1], c.V[5] + t1[2]};
     const double dd_ = -(qz + rho[2]);
-    const double root = sqrt_t(dd_ * dd_ + md.eps * md.eps);
-    const double sp = 0.5 * (dd_ + root), al = 0.5 * (1.0 + dd_ / root);
+    const double s2 = dd_ * dd_ + md.eps * md.eps;
+#if defined(__CUDA_ARCH__)
+    const double ri = rsqrt(s2);                        // root and dd_ / root from ONE reciprocal square root (each within ~1.5 ulp)
+    const double root = s2 * ri, ratio = dd_ * ri;      // instead of an fp64 square root followed by an fp64 division
+#else
+    const double root = sqrt_t(s2), ratio = dd_ / root;
+#endif
+    const double sp = 0.5 * (dd_ + root), al = 0.5 * (1.0 + ratio);
     const double W[3] = {al * (h * md.bt), al * (h * md.bt), al * (h * md.bn + h * h * md.kn)};
     const double phi[3] = {-(al * md.bt) * pd[0], -(al * md.bt) * pd[1], md.kn * sp - al * (md.bn + h * md.kn) * pd[2]};
     double n[3];
@@ -281,7 +287,7 @@ H1_DEV void dyn_step_quad(const DynModel& md, const CX& cx, int g, const double*
 #pragma unroll
   for (int q = 0; q < 3; ++q) hs[q] = quad_sum(cx, hs[q]);
   {
-    const double inv = 1.0 / md.total_mass;
+    const double inv = md.inv_total_mass;
     com[0] = x[0] + hs[0] * inv; com[1] = x[1] + hs[1] * inv; com[2] = x[2] + hs[2] * inv;
   }
   double ab[6], Ap[6];
@@ -328,9 +334,12 @@ H1_DEV void dyn_step_quad(const DynModel& md, const CX& cx, int g, const double*
     }
     // L'DL of the 6 x 6 block, last dof first (the order of h1_dyn_seq.cuh), fused forward substitution
 #pragma unroll
+    double dinv[6];   // reciprocals of the pivots: reused by the substitution below (fp64 divisions are ~20 instructions each)
+#pragma unroll
     for (int k = 5; k >= 1; --k) {
       double* mk = M + k * (k + 1) / 2;
       const double inv = 1.0 / mk[k];
+      dinv[k] = inv;
       double a[5];
 #pragma unroll
       for (int s = 0; s < 5; ++s) if (s < k) a[s] = mk[s] * inv;
@@ -353,7 +362,7 @@ H1_DEV void dyn_step_quad(const DynModel& md, const CX& cx, int g, const double*
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       const double* mk = M + k * (k + 1) / 2;
-      double a = rhs[k] / mk[k];
+      double a = rhs[k] * (k == 0 ? 1.0 / mk[0] : dinv[k]);
 #pragma unroll
       for (int s = 0; s < k; ++s) a -= mk[s] * ab[s];
       ab[k] = a;
@@ -426,7 +435,7 @@ H1_DEV void dyn_com_quad(const DynModel& md, const CX& cx, int g, const double* 
       for (int k = 0; k < 3; ++k) hs[k] += m * (r[k] + R[3 * k] * ip[0] + R[3 * k + 1] * ip[1] + R[3 * k + 2] * ip[2]);
     }
   }
-  const double inv = 1.0 / md.total_mass;
+  const double inv = md.inv_total_mass;
 #pragma unroll
   for (int k = 0; k < 3; ++k) com[k] = x[k] + quad_sum(cx, hs[k]) * inv;
 }

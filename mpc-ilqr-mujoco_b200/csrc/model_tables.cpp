@@ -50,6 +50,7 @@ bool build_dyn_model(const H1Model& m, DynModel* d) {
   for (int i = 0; i < 3; ++i) d->gravity[i] = m.gravity[i];
   d->h = m.timestep; d->kn = m.contact_kn; d->bn = m.contact_bn; d->bt = m.contact_bt; d->eps = m.contact_eps;
   d->total_mass = m.total_mass;
+  d->inv_total_mass = 1.0 / m.total_mass;
   // dof tree: base dofs 0..5 form a chain, hinge dof 5+b hangs below its parent body's last dof
   for (int j = 0; j < NV; ++j) {
     int n = 0;
