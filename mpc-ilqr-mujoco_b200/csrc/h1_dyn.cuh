@@ -34,21 +34,42 @@ H1_HD Dual operator+(const Dual& a, const Dual& b) { return Dual(a.v + b.v, a.d 
 H1_HD Dual operator-(const Dual& a, const Dual& b) { return Dual(a.v - b.v, a.d - b.d); }
 H1_HD Dual operator-(const Dual& a) { return Dual(-a.v, -a.d); }
 H1_HD Dual operator*(const Dual& a, const Dual& b) { return Dual(a.v * b.v, a.v * b.d + a.d * b.v); }
-H1_HD Dual operator/(const Dual& a, const Dual& b) { double q = a.v / b.v; return Dual(q, (a.d - q * b.d) / b.v); }
+// (quotients through ONE reciprocal: an fp64 division is ~20 instructions on the device; values within an ulp of the quotient)
+H1_HD Dual operator/(const Dual& a, const Dual& b) { const double r = 1.0 / b.v, q = a.v * r; return Dual(q, (a.d - q * b.d) * r); }
 H1_HD Dual operator+(const Dual& a, double b) { return Dual(a.v + b, a.d); }
 H1_HD Dual operator+(double b, const Dual& a) { return Dual(a.v + b, a.d); }
 H1_HD Dual operator-(const Dual& a, double b) { return Dual(a.v - b, a.d); }
 H1_HD Dual operator-(double b, const Dual& a) { return Dual(b - a.v, -a.d); }
 H1_HD Dual operator*(const Dual& a, double b) { return Dual(a.v * b, a.d * b); }
 H1_HD Dual operator*(double b, const Dual& a) { return Dual(a.v * b, a.d * b); }
-H1_HD Dual operator/(const Dual& a, double b) { return Dual(a.v / b, a.d / b); }
-H1_HD Dual operator/(double b, const Dual& a) { double q = b / a.v; return Dual(q, -q * a.d / a.v); }
+H1_HD Dual operator/(const Dual& a, double b) { const double r = 1.0 / b; return Dual(a.v * r, a.d * r); }
+H1_HD Dual operator/(double b, const Dual& a) { const double r = 1.0 / a.v, q = b * r; return Dual(q, -q * a.d * r); }
 H1_HD Dual& operator+=(Dual& a, const Dual& b) { a.v += b.v; a.d += b.d; return a; }
 H1_HD Dual& operator-=(Dual& a, const Dual& b) { a.v -= b.v; a.d -= b.d; return a; }
 H1_HD bool operator<(const Dual& a, double b) { return a.v < b; }
 H1_HD bool operator>(const Dual& a, double b) { return a.v > b; }
 H1_HD double sqrt_t(double a) { return ::sqrt(a); }
 H1_HD Dual sqrt_t(const Dual& a) { double r = ::sqrt(a.v); return Dual(r, 0.5 * a.d / r); }
+// smoothed contact depth: root = sqrt(s2) and ratio = dd / root from one reciprocal square root on the device
+H1_HD void root_and_ratio(double s2, double dd, double* root, double* ratio) {
+#if defined(__CUDA_ARCH__)
+  const double ri = ::rsqrt(s2);
+  *root = s2 * ri; *ratio = dd * ri;
+#else
+  *root = ::sqrt(s2); *ratio = dd / *root;
+#endif
+}
+H1_HD void root_and_ratio(const Dual& s2, const Dual& dd, Dual* root, Dual* ratio) {
+#if defined(__CUDA_ARCH__)
+  const double ri = ::rsqrt(s2.v);
+#else
+  const double ri = 1.0 / ::sqrt(s2.v);
+#endif
+  const double r = s2.v * ri, hd = 0.5 * s2.d * ri;       // d sqrt(s2) = s2' / (2 sqrt(s2))
+  *root = Dual(r, hd);
+  const double q = dd.v * ri;                              // d (dd / root) = (dd' - q root') / root
+  *ratio = Dual(q, (dd.d - q * hd) * ri);
+}
 H1_HD double tangent_of(double) { return 0.0; }
 H1_HD double tangent_of(const Dual& a) { return a.d; }
 H1_HD double val(double a) { return a; }

@@ -158,12 +158,8 @@ H1_DEV void q4_contact(const DynModel& md, int f, const SeqBodyState& c, double 
     const double pd[3] = {c.V[3] + t1[0], c.V[4] + t1[1], c.V[5] + t1[2]};
     const double dd_ = -(qz + rho[2]);
     const double s2 = dd_ * dd_ + md.eps * md.eps;
-#if defined(__CUDA_ARCH__)
-    const double ri = rsqrt(s2);                        // root and dd_ / root from ONE reciprocal square root (each within ~1.5 ulp)
-    const double root = s2 * ri, ratio = dd_ * ri;      // instead of an fp64 square root followed by an fp64 division
-#else
-    const double root = sqrt_t(s2), ratio = dd_ / root;
-#endif
+    double root, ratio;   // from ONE reciprocal square root (each within ~1.5 ulp) instead of an fp64 square root followed by a division
+    root_and_ratio(s2, dd_, &root, &ratio);
     const double sp = 0.5 * (dd_ + root), al = 0.5 * (1.0 + ratio);
     const double W[3] = {al * (h * md.bt), al * (h * md.bt), al * (h * md.bn + h * h * md.kn)};
     const double phi[3] = {-(al * md.bt) * pd[0], -(al * md.bt) * pd[1], md.kn * sp - al * (md.bn + h * md.kn) * pd[2]};

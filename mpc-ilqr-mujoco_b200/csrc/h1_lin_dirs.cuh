@@ -203,8 +203,9 @@ H1_DEV void id_tangent_seq(const DynModel& md, const double* __restrict__ x, con
         const TV pd[3] = {cur.V[3] + t1[0], cur.V[4] + t1[1], cur.V[5] + t1[2]};
         const TK pa[3] = {Va[3] + t2[0], Va[4] + t2[1], Va[5] + t2[2]};
         const TK dd_ = -(qz + rho[2]);
-        const TK root = sqrt_t(dd_ * dd_ + md.eps * md.eps);
-        const TK sp = 0.5 * (dd_ + root), al = 0.5 * (1.0 + dd_ / root);
+        TK root, ratio;
+        root_and_ratio(dd_ * dd_ + md.eps * md.eps, dd_, &root, &ratio);
+        const TK sp = 0.5 * (dd_ + root), al = 0.5 * (1.0 + ratio);
         TV Fc[3];
         Fc[0] = -(al * md.bt) * (pd[0] + h * pa[0]);
         Fc[1] = -(al * md.bt) * (pd[1] + h * pa[1]);
@@ -346,8 +347,9 @@ H1_DEV void id_tangent_sub(const DynModel& md, const double* __restrict__ x, con
         const TV pd[3] = {cur.V[3] + t1[0], cur.V[4] + t1[1], cur.V[5] + t1[2]};
         const TK pa[3] = {Va[3] + t2[0], Va[4] + t2[1], Va[5] + t2[2]};
         const TK dd_ = -(qz + rho[2]);
-        const TK root = sqrt_t(dd_ * dd_ + md.eps * md.eps);
-        const TK sp = 0.5 * (dd_ + root), al = 0.5 * (1.0 + dd_ / root);
+        TK root, ratio;
+        root_and_ratio(dd_ * dd_ + md.eps * md.eps, dd_, &root, &ratio);
+        const TK sp = 0.5 * (dd_ + root), al = 0.5 * (1.0 + ratio);
         TV Fc[3];
         Fc[0] = -(al * md.bt) * (pd[0] + h * pa[0]);
         Fc[1] = -(al * md.bt) * (pd[1] + h * pa[1]);
@@ -454,8 +456,9 @@ H1_DEV void contact_tangent_feet(const DynModel& md, const double* __restrict__ 
       const Dual pd[3] = {V[3] + t1[0], V[4] + t1[1], V[5] + t1[2]};
       const TK pa[3] = {Va[3] + t2[0], Va[4] + t2[1], Va[5] + t2[2]};
       const Dual dd_ = -(qz + rho[2]);
-      const Dual root = sqrt_t(dd_ * dd_ + md.eps * md.eps);
-      const Dual sp = 0.5 * (dd_ + root), al = 0.5 * (1.0 + dd_ / root);
+      Dual root, ratio;
+      root_and_ratio(dd_ * dd_ + md.eps * md.eps, dd_, &root, &ratio);
+      const Dual sp = 0.5 * (dd_ + root), al = 0.5 * (1.0 + ratio);
       Dual Fc[3];
       Fc[0] = -(al * md.bt) * (pd[0] + h * pa[0]);
       Fc[1] = -(al * md.bt) * (pd[1] + h * pa[1]);
