@@ -194,7 +194,8 @@ H1_DEV void ph_cq_vel(int lane, const CostModel& cm, CostWarp& w) {
   }
 }
 
-// ---- phase 4 (lane 0): which terms are active at this knot, their multipliers, the rank-1 list ----
+// ---- phase 4 (ONE lane, the first of the pair's second warp — the first warp builds the Jacobian rows of phase 5 meanwhile,
+//      which need nothing from here): which terms are active at this knot, their multipliers, the rank-1 list ----
 struct KnotTargets {
   const double* com_ref;      // [3]
   const double* com_vel_ref;  // [3]
@@ -203,7 +204,7 @@ struct KnotTargets {
   bool terminal;
 };
 H1_DEV void ph_cq_terms(int lane, const H1Weights& wt, const KnotTargets& kt, CostWarp& w) {
-  if (lane != 0) return;
+  if (lane != 32) return;
   for (int s = 0; s < CQ_SETS; ++s)
     for (int i = 0; i < 3; ++i) { w.lamP[s][i] = 0.0; w.lamU[s][i] = 0.0; }
   for (int r = 0; r < CQ_ROWS; ++r) w.gcoef[r] = 0.0;
@@ -283,7 +284,9 @@ H1_DEV void ph_cq_terms(int lane, const H1Weights& wt, const KnotTargets& kt, Co
 // ---- phase 5: Jacobian rows (lane <-> state column) and the contraction tables (lane <-> joint pairs) ----
 H1_DEV void ph_cq_rows(int lane, const CostModel& cm, CostWarp& w) {
   // rows: J_P(s) = [I | Ra rr | R r_l | 0],  J_U(s) = [0 | Ra u | R uth_l | R, R(e_m x rr), R r_j]
-  for (int i = lane; i < NX; i += CQ_LANES) {
+  // (all 51 columns by the FIRST warp of the pair, two per lane: the second warp's lane 0 runs phase 4 at the same time)
+  if (lane >= 32) return;
+  for (int i = lane; i < NX; i += 32) {
     for (int s = 0; s < CQ_SETS; ++s) {
       double cp[3] = {0, 0, 0}, cu[3] = {0, 0, 0};
       if (i < 3) { cp[0] = (i == 0) ? 1.0 : 0.0; cp[1] = (i == 1) ? 1.0 : 0.0; cp[2] = (i == 2) ? 1.0 : 0.0; }
@@ -301,7 +304,18 @@ H1_DEV void ph_cq_rows(int lane, const CostModel& cm, CostWarp& w) {
     }
   }
 }
+// Ra[a]' lamP[s] and Ra[a]' lamU[s] (4 x 3 x 2 vectors), computed ONCE per knot by 24 lanes of phase 5b instead of by every lane of
+// phase 6 for itself (measured, tools/cq_prof.py: the (xi, v) block alone made the second warp's phase 6 half as long again as
+// the first's). They live in scratch that is dead between the kinematic walk and the gradient phase: sn / cs and hdiag.
+H1_DEV double* cq_RaU(CostWarp& w) { return w.sn; }                 // [4][CQ_SETS][3] = 36 of the 40 doubles of sn, cs
+H1_DEV double* cq_RaP(CostWarp& w) { return w.hdiag; }              // 36 of the 51 doubles of hdiag
+static_assert(4 * CQ_SETS * 3 <= 2 * NB && 4 * CQ_SETS * 3 <= NX, "scratch for the transformed multipliers");
 H1_DEV void ph_cq_rows2(int lane, CostWarp& w) {  // balance residual rows (need the CoM rows complete)
+  if (lane < 4 * CQ_SETS * 2) {
+    const int a = lane / (2 * CQ_SETS), rem = lane - a * 2 * CQ_SETS, s = rem >> 1;
+    if (rem & 1) mtv3(w.Ra[a], w.lamU[s], cq_RaU(w) + (a * CQ_SETS + s) * 3);
+    else mtv3(w.Ra[a], w.lamP[s], cq_RaP(w) + (a * CQ_SETS + s) * 3);
+  }
   for (int i = lane; i < NX; i += CQ_LANES) {
     double a = 0.0, b = 0.0;
     if (w.bal_on) {
@@ -352,11 +366,8 @@ H1_DEV void ph_cq_tables(int lane, const CostModel& cm, CostWarp& w) {
     }
     for (int a = 0; a < 4; ++a) {
       double v = 0.0;
-      for (int s = 0; s < CQ_SETS; ++s) {
-        double RaP[3], RaU[3];
-        mtv3(w.Ra[a], w.lamP[s], RaP); mtv3(w.Ra[a], w.lamU[s], RaU);
-        v += dot3(RaP, w.rj[s][k]) + dot3(RaU, w.uth[s][k]);
-      }
+      for (int s = 0; s < CQ_SETS; ++s)
+        v += dot3(cq_RaP(w) + (a * CQ_SETS + s) * 3, w.rj[s][k]) + dot3(cq_RaU(w) + (a * CQ_SETS + s) * 3, w.uth[s][k]);
       w.QJ[a][k] = v;
     }
   }
@@ -366,8 +377,7 @@ H1_DEV void ph_cq_tables(int lane, const CostModel& cm, CostWarp& w) {
     for (int a = 0; a < 4; ++a) {
       double v = 0.0;
       for (int s = 0; s < CQ_SETS; ++s) {
-        double RaU[3];
-        mtv3(w.Ra[a], w.lamU[s], RaU);
+        const double* RaU = cq_RaU(w) + (a * CQ_SETS + s) * 3;
         if (m < 3) v += RaU[m];
         else if (m < 6) {
           const int mm = m - 3;
@@ -463,7 +473,9 @@ H1_DEV void ph_cq_store(int lane, const DynModel& md, const H1Weights& wt, const
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) af[ks] = (ks < nks) ? cc[ks] * ra[ks][ia] : 0.0;
 #pragma unroll 1
-      for (int jt = (it + half) & 1; jt <= it; jt += 2) {   // tiles of a row strip alternate between the two warps (14 tiles each)
+      // tiles of a row strip alternate between the two warps; the strips with an odd tile count give their extra tile to the
+      // first warp (strips 0, 6) or to the second (2, 4): 14 tiles each (a plain (it + half) & 1 start made it 16 / 12)
+      for (int jt = (half + ((it == 0 || it == 6) ? 0 : 1)) & 1; jt <= it; jt += 2) {
         const int jb = min(8 * jt + g, NX - 1);
         double c0 = 0.0, c1 = 0.0;
 #pragma unroll
@@ -502,8 +514,8 @@ H1_DEV void ph_cq_store(int lane, const DynModel& md, const H1Weights& wt, const
       const int i = e % NU, j = e / NU;
       if (i != j) luu[e] = (FULLQ && Ro) ? Ro[e] : 0.0;                     // luu = R + ... (ilqr.cpp:150)
     }
-    if (lane < NU) {
-      const int i = lane;
+    if (lane >= 32 && lane < 32 + NU) {   // (second warp: the first one has the rank-1 setup of the tile phase above)
+      const int i = lane - 32;
       double g = wt.Rdiag[i] * (u[i] - u_ref[i]);
       if (FULLQ && Ro) for (int j = 0; j < NU; ++j) g += Ro[j * NU + i] * (u[j] - u_ref[j]);   // lu = R (u - u_ref) (ilqr.cpp:146)
       double h = wt.Rdiag[i];
@@ -516,8 +528,16 @@ H1_DEV void ph_cq_store(int lane, const DynModel& md, const H1Weights& wt, const
 
 #if defined(__CUDACC__)
 // the two warps of a knot meet at a named barrier (ids 1.. : one per knot slot of the CTA)
+#ifdef CQ_PROF   // debug build only (tools/cq_prof.py): per phase and per warp of the pair, cycles of work before / wait at the pair barrier
+__device__ unsigned long long cq_prof_sum[2][16][2];
+#define H1_CQ_PHASE(call) { call; const long long t1_ = clock64(); asm volatile("bar.sync %0, 64;" ::"r"(1 + (int)(threadIdx.x >> 6)) : "memory"); \
+    const long long t2_ = clock64(); if ((threadIdx.x & 31) == 0) { atomicAdd(&cq_prof_sum[(threadIdx.x >> 5) & 1][cq_ph_][0], (unsigned long long)(t1_ - cq_t_)); \
+    atomicAdd(&cq_prof_sum[(threadIdx.x >> 5) & 1][cq_ph_][1], (unsigned long long)(t2_ - t1_)); } cq_t_ = t2_; ++cq_ph_; }
+#define H1_CQ_LANE const int lane = threadIdx.x & (CQ_LANES - 1); long long cq_t_ = clock64(); int cq_ph_ = 0;
+#else
 #define H1_CQ_PHASE(call) { call; asm volatile("bar.sync %0, 64;" ::"r"(1 + (int)(threadIdx.x >> 6)) : "memory"); }
 #define H1_CQ_LANE const int lane = threadIdx.x & (CQ_LANES - 1);
+#endif
 #else
 #define H1_CQ_PHASE(call) { for (int lane = 0; lane < CQ_LANES; ++lane) { call; } }
 #define H1_CQ_LANE
@@ -533,8 +553,7 @@ H1_DEV void cost_quadratics_warp(const CostModel& cm, const DynModel& md, const 
   H1_CQ_PHASE(ph_cq_walk(lane, cm, w))
   H1_CQ_PHASE(ph_cq_sets(lane, cm, w))
   H1_CQ_PHASE(ph_cq_vel(lane, cm, w))
-  H1_CQ_PHASE(ph_cq_terms(lane, wt, kt, w))
-  H1_CQ_PHASE(ph_cq_rows(lane, cm, w))
+  H1_CQ_PHASE((ph_cq_terms(lane, wt, kt, w), ph_cq_rows(lane, cm, w)))   // measured (tools/cq_prof.py): 5.4 k + 2.5 k cycles one after the other
   H1_CQ_PHASE(ph_cq_rows2(lane, w))
   H1_CQ_PHASE(ph_cq_tables(lane, cm, w))
   H1_CQ_PHASE(ph_cq_grad<FULLQ>(lane, md, wt, qo, w, x, x_ref, kt.terminal, lx))
