@@ -203,12 +203,38 @@ struct KnotTargets {
   const int* stance;          // [2]
   bool terminal;
 };
+// The part of the term setup that needs the state only — the upright term and the zero fills — runs on the SECOND warp during the
+// kinematic walk, which occupies the first warp alone (measured, tools/cq_prof.py: 4.0 k cycles of the 43 k of a knot).
+H1_DEV void ph_cq_pre(int lane, const H1Weights& wt, CostWarp& w) {
+  if (lane > 32) {
+    for (int e = lane - 33; e < 2 * CQ_SETS * 3 + CQ_ROWS + 1; e += CQ_LANES - 33) {
+      if (e < CQ_SETS * 3) w.lamP[e / 3][e % 3] = 0.0;
+      else if (e < 2 * CQ_SETS * 3) w.lamU[(e - CQ_SETS * 3) / 3][e % 3] = 0.0;
+      else if (e < 2 * CQ_SETS * 3 + CQ_ROWS) w.gcoef[e - 2 * CQ_SETS * 3] = 0.0;
+      else w.bal_on = 0;
+    }
+    return;
+  }
+  if (lane != 32) return;
+  // upright: closed form on x~[3..6] read as (qw,qx,qy,qz)  (derivatives.cpp:646-666)
+  for (int a = 0; a < 4; ++a) { w.gq[a] = 0.0; for (int b = 0; b < 4; ++b) w.QQ[a][b] = 0.0; }
+  if (wt.w_upright > 0.0) {
+    const double* s = &w.xt[3];
+    const double z[3] = {2 * (s[1] * s[3] + s[0] * s[2]), 2 * (s[2] * s[3] - s[0] * s[1]), 1 - 2 * (s[1] * s[1] + s[2] * s[2])};
+    const double r[3] = {z[0], z[1], z[2] - 1.0};
+    const double J[3][4] = {{2 * s[2], 2 * s[3], 2 * s[0], 2 * s[1]}, {-2 * s[1], -2 * s[0], 2 * s[3], 2 * s[2]}, {0, -4 * s[1], -4 * s[2], 0}};
+    const double wu = wt.w_upright;
+    for (int a = 0; a < 4; ++a) {
+      w.gq[a] = wu * (J[0][a] * r[0] + J[1][a] * r[1] + J[2][a] * r[2]);
+      for (int b = 0; b < 4; ++b) w.QQ[a][b] = wu * (J[0][a] * J[0][b] + J[1][a] * J[1][b] + J[2][a] * J[2][b]);
+    }
+    w.QQ[0][2] += wu * r[0] * 2; w.QQ[2][0] += wu * r[0] * 2; w.QQ[1][3] += wu * r[0] * 2; w.QQ[3][1] += wu * r[0] * 2;
+    w.QQ[0][1] += wu * r[1] * -2; w.QQ[1][0] += wu * r[1] * -2; w.QQ[2][3] += wu * r[1] * 2; w.QQ[3][2] += wu * r[1] * 2;
+    w.QQ[1][1] += wu * r[2] * -4; w.QQ[2][2] += wu * r[2] * -4;
+  }
+}
 H1_DEV void ph_cq_terms(int lane, const H1Weights& wt, const KnotTargets& kt, CostWarp& w) {
   if (lane != 32) return;
-  for (int s = 0; s < CQ_SETS; ++s)
-    for (int i = 0; i < 3; ++i) { w.lamP[s][i] = 0.0; w.lamU[s][i] = 0.0; }
-  for (int r = 0; r < CQ_ROWS; ++r) w.gcoef[r] = 0.0;
-  w.bal_on = 0;
   int no = 0;
   double P[CQ_SETS][3], U[CQ_SETS][3];
   for (int s = 0; s < CQ_SETS; ++s) {
@@ -234,22 +260,6 @@ H1_DEV void ph_cq_terms(int lane, const H1Weights& wt, const KnotTargets& kt, Co
   if (wt.w_ee_vel > 0.0)
     for (int f = 0; f < H1_NFOOT; ++f)
       if (kt.stance[f] == 1) sq_term(1 + f, true, zero3, wt.w_ee_vel);
-  // upright: closed form on x~[3..6] read as (qw,qx,qy,qz)  (derivatives.cpp:646-666)
-  for (int a = 0; a < 4; ++a) { w.gq[a] = 0.0; for (int b = 0; b < 4; ++b) w.QQ[a][b] = 0.0; }
-  if (wt.w_upright > 0.0) {
-    const double* s = &w.xt[3];
-    const double z[3] = {2 * (s[1] * s[3] + s[0] * s[2]), 2 * (s[2] * s[3] - s[0] * s[1]), 1 - 2 * (s[1] * s[1] + s[2] * s[2])};
-    const double r[3] = {z[0], z[1], z[2] - 1.0};
-    const double J[3][4] = {{2 * s[2], 2 * s[3], 2 * s[0], 2 * s[1]}, {-2 * s[1], -2 * s[0], 2 * s[3], 2 * s[2]}, {0, -4 * s[1], -4 * s[2], 0}};
-    const double wu = wt.w_upright;
-    for (int a = 0; a < 4; ++a) {
-      w.gq[a] = wu * (J[0][a] * r[0] + J[1][a] * r[1] + J[2][a] * r[2]);
-      for (int b = 0; b < 4; ++b) w.QQ[a][b] = wu * (J[0][a] * J[0][b] + J[1][a] * J[1][b] + J[2][a] * J[2][b]);
-    }
-    w.QQ[0][2] += wu * r[0] * 2; w.QQ[2][0] += wu * r[0] * 2; w.QQ[1][3] += wu * r[0] * 2; w.QQ[3][1] += wu * r[0] * 2;
-    w.QQ[0][1] += wu * r[1] * -2; w.QQ[1][0] += wu * r[1] * -2; w.QQ[2][3] += wu * r[1] * 2; w.QQ[3][2] += wu * r[1] * 2;
-    w.QQ[1][1] += wu * r[2] * -4; w.QQ[2][2] += wu * r[2] * -4;
-  }
   // balance: 0.5 w || com_xy + vcom_xy sqrt(com_z / 9.81) - p_support ||^2  (derivatives.cpp:668-707)
   if (wt.w_balance > 0.0) {
     double ps[2];
@@ -550,7 +560,7 @@ H1_DEV void cost_quadratics_warp(const CostModel& cm, const DynModel& md, const 
                                  const double* qo = nullptr) {   // qo: off-diagonal parts of full Q / R / Qf (DevWeights::qoff) or nullptr
   H1_CQ_LANE
   H1_CQ_PHASE(ph_cq_load(lane, w, x))
-  H1_CQ_PHASE(ph_cq_walk(lane, cm, w))
+  H1_CQ_PHASE((ph_cq_walk(lane, cm, w), ph_cq_pre(lane, wt, w)))
   H1_CQ_PHASE(ph_cq_sets(lane, cm, w))
   H1_CQ_PHASE(ph_cq_vel(lane, cm, w))
   H1_CQ_PHASE((ph_cq_terms(lane, wt, kt, w), ph_cq_rows(lane, cm, w)))   // measured (tools/cq_prof.py): 5.4 k + 2.5 k cycles one after the other
