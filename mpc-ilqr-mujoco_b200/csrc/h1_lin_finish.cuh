@@ -176,6 +176,12 @@ k_linearize_tangents(const DynModel* gmd, long nknots, int N, const int* __restr
 }
 
 // ---- step 2 ----
+#ifdef LINF_PROF   // debug build only (tools/linf_prof.py): cycles of a warp between the numbered steps of k_linearize_finish, summed over all knots
+__device__ unsigned long long linf_prof_sum[8];
+#define LF_MARK(p) { const long long n_ = clock64(); if (lane == 0) atomicAdd(&linf_prof_sum[p], (unsigned long long)(n_ - lf_t)); lf_t = n_; }
+#else
+#define LF_MARK(p)
+#endif
 constexpr int LINF_WARPS = 5, LINF_THREADS = LINF_WARPS * 32;   // 22.5 KB of shared memory per warp: two CTAs = 10 warps per SM
 constexpr int LDF = 28;                 // leading dimension of the 25-row operands: = 4 (mod 8) doubles, k padded to 28
 struct LinFinishWarp {
@@ -206,6 +212,9 @@ k_linearize_finish(const DynModel* __restrict__ md, long nknots, int N, const in
   const double h = md->h;
   double* Ak = A + (size_t)id * A_STRIDE;
   double* Bk = Bm + (size_t)id * B_STRIDE;
+#ifdef LINF_PROF
+  long long lf_t = clock64();
+#endif
   // ---- 1. stage with asynchronous copies in two groups: (A) factor + state, needed at once; (B) the parked tangents,
   //      needed only by the contraction of step 4 — their memory latency hides behind N = L^-1 and Mhat^-1.
   //      Columns 0, 1, 6 and the pad rows of T are zero ----
@@ -229,7 +238,9 @@ k_linearize_finish(const DynModel* __restrict__ md, long nknots, int N, const in
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     for (int i = lane; i < 32 * LDF; i += 32) W.Nm[i] = 0.0;
+    LF_MARK(0)   // issue of the copies + zero fill
     asm volatile("cp.async.wait_group 1;\n" ::: "memory");            // group A has landed
+    LF_MARK(1)   // wait for the factor
     if (lane < NU) {
       const double uj = W.umask[lane];
       W.umask[lane] = (uj < md->ctrl_lo[lane] || uj > md->ctrl_hi[lane]) ? 0.0 : 1.0;   // clamped torque: no sensitivity
@@ -266,6 +277,7 @@ k_linearize_finish(const DynModel* __restrict__ md, long nknots, int N, const in
     }
   }
   __syncwarp();
+  LF_MARK(2)   // N = L^-1
   // ---- 3. Mhat^-1 = (N D^-1) N' : tile (mi, nj) only needs k < 8 (min(mi, nj) + 1) (N is lower triangular). All 16
   //      tiles are accumulated in registers and then written over N ----
   {
@@ -302,7 +314,9 @@ k_linearize_finish(const DynModel* __restrict__ md, long nknots, int N, const in
       }
   }
   __syncwarp();
+  LF_MARK(3)   // Mhat^-1
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");              // group B (the tangents) has landed
+  LF_MARK(4)   // wait for the tangents
   __syncwarp();
   // the four raw-quaternion tangents = combinations of the three rotation tangents (parked in columns 3..5)
   if (lane < NV) {
@@ -343,6 +357,7 @@ k_linearize_finish(const DynModel* __restrict__ md, long nknots, int N, const in
       }
   }
   __syncwarp();
+  LF_MARK(5)   // Adot = Mhat^-1 T
   // ---- 5. integrator tangent (state order: q(26) then v(25)). A lane owns output rows `lane` and `lane + 32` of all
   //      70 columns: row r reads Adot row j(r); position rows get the extra factor h and the unit entries of
   //      d q_next / d q and h d q_next / d v_next. The four quaternion rows follow from the staged Jacobians ----
@@ -356,7 +371,7 @@ k_linearize_finish(const DynModel* __restrict__ md, long nknots, int N, const in
     {
       const double* ad = W.T;
       double* dst = Ak;
-#pragma unroll 3
+#pragma unroll 6
       for (int c = 0; c < NX; ++c, ad += LDF, dst += NX) {
         const double b = ((c == cv0) ? 1.0 : 0.0) + h * ad[j0];
         const double v0 = pos0 ? ((c == r0) ? 1.0 : 0.0) + h * b : b;
@@ -366,7 +381,7 @@ k_linearize_finish(const DynModel* __restrict__ md, long nknots, int N, const in
     }
     {
       double* dst = Bk;
-#pragma unroll 1
+#pragma unroll 4
       for (int j = 0; j < NU; ++j, dst += NX) {
         const double* ad = W.Nm + (6 + j) * LDF;                // (Mhat^-1 is symmetric: row = column)
         const double sc = h * W.umask[j];
@@ -388,6 +403,7 @@ k_linearize_finish(const DynModel* __restrict__ md, long nknots, int N, const in
       (isu ? Bk + (size_t)(c - NX) * NX : Ak + (size_t)c * NX)[3 + q] = v;
     }
   }
+  LF_MARK(6)   // integrator tangent + stores
 }
 
 #endif  // __CUDACC__

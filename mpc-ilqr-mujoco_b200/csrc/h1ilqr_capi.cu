@@ -945,6 +945,15 @@ int h1ilqr_rollout_nominal(H1Ilqr* h, const double* x0) {
 }
 int h1ilqr_linearize(H1Ilqr* h) { GUARD(h); launch_linearize(h, nullptr); SYNC(); CU(cudaGetLastError()); return 0; }
 int h1ilqr_cost_quadratics(H1Ilqr* h) { GUARD(h); launch_cost_quadratics(h, nullptr); SYNC(); CU(cudaGetLastError()); return 0; }
+#ifdef LINF_PROF   // debug build only: read and clear the per-step cycle sums of k_linearize_finish (not part of the ABI)
+int h1ilqr_debug_linf_prof(unsigned long long* out8) {
+  CU(cudaDeviceSynchronize());
+  static const unsigned long long zeros[8] = {0};
+  CU(cudaMemcpyFromSymbol(out8, h1::linf_prof_sum, sizeof(zeros)));
+  CU(cudaMemcpyToSymbol(h1::linf_prof_sum, zeros, sizeof(zeros)));
+  return 0;
+}
+#endif
 #ifdef CQ_PROF   // debug build only: read and clear the per-phase cycle sums of k_cost_quadratics (not part of the ABI)
 int h1ilqr_debug_cq_prof(unsigned long long* out64) {
   CU(cudaDeviceSynchronize());
